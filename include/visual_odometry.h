@@ -1,0 +1,68 @@
+// VisualOdometry: the reference's per-frame VO API (src/visual_odometry.h:31-66) on top of the
+// B200 kernels.  Same class name, constructor, process_frame / get_trajectory /
+// get_trajectory_poses / has_last_F / last_F, same fallback semantics
+// (src/visual_odometry.cpp:323-378).  Extensions that the reference lacks are marked [ext]:
+// an options overload (the reference hard-codes nfeatures = 1200) and a batched
+// process_sequence (a per-frame streaming call cannot be batched or partitioned).
+#pragma once
+#include <cstdint>
+#include <mutex>
+#include <vector>
+
+#include "frame.h"
+#include "vo_cv_compat.h"
+
+struct b200vo_ctx;
+
+class VisualOdometry {
+public:
+    struct Options {                       // [ext]
+        int nfeatures = 1200;              // reference src/visual_odometry.cpp:65
+        int ransac_hypotheses = 1024;
+        uint64_t ransac_seed = 42;
+        int device = 0;
+        int batch_frames = 64;             // frames per launch batch in process_sequence
+    };
+
+    VisualOdometry(int image_width, int image_height);
+    VisualOdometry(int image_width, int image_height, const Options& options);   // [ext]
+    ~VisualOdometry();
+    VisualOdometry(const VisualOdometry&) = delete;
+    VisualOdometry& operator=(const VisualOdometry&) = delete;
+
+    // Detects features into frame.keypoints/descriptors, writes frame.pose (T_wc), appends to the
+    // trajectory and MOVES the frame into the internal previous frame (as the reference does).
+    // Returns the display image; this headless build returns a copy of the input image (the
+    // reference draws the keypoints on it for its GUI).
+    cv::Mat process_frame(Frame& frame);
+
+    // [ext] Batched path: all frames are uploaded, detected and matched in launch batches; the
+    // relative poses are chained on the host exactly as process_frame would.  Appends to the
+    // trajectory; returns the poses of the processed frames.
+    std::vector<Pose> process_sequence(const std::vector<cv::Mat>& images);
+
+    std::vector<cv::Mat> get_trajectory();
+    std::vector<Pose> get_trajectory_poses();
+    bool has_last_F() const;
+    cv::Matx33d last_F() const;
+
+    const cv::Mat& camera_matrix() const { return camera_matrix_; }   // [ext]
+
+private:
+    void init(int w, int h, const Options& o);
+    void push_pose(const Pose& p);
+
+    Options options_;
+    int width_ = 0, height_ = 0;
+    b200vo_ctx* ctx_ = nullptr;
+    cv::Mat camera_matrix_;
+    bool has_last_F_ = false;
+    cv::Matx33d last_F_{};
+    std::vector<Pose> trajectory_poses_;
+    std::vector<cv::Mat> trajectory_positions_;
+    std::mutex trajectory_mutex_;
+    Frame previous_frame_;
+    int previous_slot_ = 0;
+    int64_t frame_counter_ = 0;
+    bool initialized_ = false;
+};

@@ -1,0 +1,142 @@
+// Shared declarations of the b200vo CUDA library: context, level geometry, launch helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/b200vo.h"
+
+namespace b200vo {
+
+constexpr int kLevels = B200VO_NLEVELS;
+constexpr int kEdge = 31;          // ORB edgeThreshold (reference src/visual_odometry.cpp:68)
+constexpr int kHalfPatch = 15;     // patchSize 31
+constexpr int kDescBytes = 32;
+constexpr int kMaxSolutions = 10;  // real roots of the degree-10 five-point polynomial
+
+struct LevelGeom {
+    int w, h, pitch;       // pitch: bytes per row, multiple of 128 (TMA needs 16)
+    size_t offset;         // byte offset of the level inside a slot's pyramid buffer
+    float scale;           // (float)pow((double)1.2f, l)
+    int nfeat;             // per-level budget N_l
+    int cand_cap;          // FAST candidate list capacity
+    int sel_cap;           // power-of-two capacity of the selection working set
+    int kp_cap;            // capacity of the level keypoint list
+    int tab_off;           // offset of this level's resize tables (x then y) in d_tab
+};
+
+// Device-visible description of the frame store (passed by value to kernels).
+struct StoreView {
+    LevelGeom lv[kLevels];
+    uint8_t* pyr;              // [slots][slot_bytes]
+    uint8_t* blur;             // [slots][slot_bytes]
+    size_t slot_bytes;
+    int slots;
+    // FAST candidates: per (slot, level)
+    uint32_t* cand;            // [slots][cand_total]  packed (y<<20 | x<<8 | score)
+    int cand_total;            // sum of cand_cap
+    int cand_off[kLevels];
+    int* cand_count;           // [slots][kLevels]
+    int* fast_hist;            // [slots][kLevels][256]
+    // per-level selected keypoints
+    uint32_t* lkp_key;         // [slots][lkp_total]  packed (y<<20 | x<<8 | score), raster order
+    float* lkp_resp;           // [slots][lkp_total]
+    int lkp_total;
+    int lkp_off[kLevels];
+    int* lkp_count;            // [slots][kLevels]
+    // final features
+    b200vo_keypoint* kp;       // [slots][kp_cap]
+    uint8_t* desc;             // [slots][kp_cap][32]
+    int* kp_count;             // [slots]
+    int* flags;                // [slots] overflow flags
+    int kp_cap;
+    int fast_threshold;
+};
+
+struct PairView {
+    // matching
+    uint32_t* nnq;             // [pairs][kp_cap] packed (dist<<16 | idx)
+    uint32_t* nnt;             // [pairs][kp_cap]
+    b200vo_dmatch* good;       // [pairs][kp_cap]
+    int* n_good;               // [pairs]
+    int* n_cross;              // [pairs]
+    double* thr;               // [pairs]
+    // geometry (normalised coordinates of the good matches, SoA)
+    double* x1x; double* x1y; double* x2x; double* x2y;   // [pairs][kp_cap]
+    unsigned long long* best;  // [pairs] packed (count<<32 | ~model)
+    double* E;                 // [pairs][9]
+    uint8_t* inl;              // [pairs][kp_cap] inlier mask of the best model
+    b200vo_pose_record* rec;   // [pairs]
+    double* models;            // [pairs][nhyp_cap][10][9] five-point solutions
+    int* nsol;                 // [pairs][nhyp_cap]
+    int* counts;               // [pairs][nhyp_cap][10] inlier counts (parity hook; may be NULL)
+    int nhyp_cap;
+    int kp_cap;
+};
+
+}  // namespace b200vo
+
+struct b200vo_ctx {
+    b200vo_options opt;
+    int device;
+    cudaStream_t stream;
+    b200vo::StoreView store;
+    b200vo::PairView pairs;
+    int max_pairs;
+    // resize coefficient tables
+    int* d_tab;                // per level l>=1: xofs[w], xc1[w], yofs[h], yc1[h]
+    // scratch for parity hooks / raw matcher
+    void* d_scratch; size_t scratch_bytes;
+    void* h_pinned; size_t pinned_bytes;
+    uint8_t* d_bgr; size_t bgr_bytes;      // staging for 3-channel uploads
+    int64_t launches;
+    bool timing;
+    b200vo_stage_times times;
+    cudaEvent_t ev[16];
+    double K[4];               // fx, fy, cx, cy
+    std::vector<void*> allocs;
+};
+
+namespace b200vo {
+
+void set_error(const char* fmt, ...);
+
+#define B200VO_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            b200vo::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return B200VO_ERR_CUDA;                                                               \
+        }                                                                                         \
+    } while (0)
+
+#define B200VO_LAUNCH_CHECK(ctx)                                                                  \
+    do {                                                                                          \
+        (ctx)->launches++;                                                                        \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                  \
+            b200vo::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return B200VO_ERR_CUDA;                                                               \
+        }                                                                                         \
+    } while (0)
+
+inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// stage launchers (each enqueues on ctx->stream and returns a b200vo_status)
+int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int first_slot, int n);
+int launch_pyramid(b200vo_ctx* ctx, int first_slot, int n);
+int launch_fast(b200vo_ctx* ctx, int first_slot, int n);
+int launch_select(b200vo_ctx* ctx, int first_slot, int n);
+int launch_orient(b200vo_ctx* ctx, int first_slot, int n);
+int launch_blur(b200vo_ctx* ctx, int first_slot, int n);
+int launch_brief(b200vo_ctx* ctx, int first_slot, int n);
+int launch_match_slots(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_override);
+int launch_match_raw(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t, int n2, int npairs,
+                     uint32_t* nnq, uint32_t* nnt);
+int launch_filter(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_override);
+int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int32_t* d_samples, int nhyp);
+int launch_recover_pose(b200vo_ctx* ctx, int npairs);
+
+}  // namespace b200vo

@@ -1,0 +1,174 @@
+// K9 brute-force Hamming matching with row AND column arg-min in one pass.
+//
+// What it replaces: cv::BFMatcher(NORM_HAMMING, crossCheck=true)::match
+// (reference src/visual_odometry.cpp:87,153), which OpenCV evaluates as three batchDistance
+// passes.  Semantics: distance = popcount over 256 bits; nearest train of
+// every query and nearest query of every train, LOWEST INDEX wins ties.
+//
+// Design: this is integer work (XOR + POPC), bound by the POPC pipe, not by HBM and not a dense
+// floating-point contraction -- no tensor cores.  Each thread keeps R query descriptors
+// (R x 8 words) in registers; a CTA streams a chunk of train descriptors through shared memory
+// (every lane reads the same train descriptor: a broadcast, conflict-free).  A distance is used
+// twice: folded into the thread's running row minimum, and -- packed as (dist<<16 | row) --
+// reduced over the warp with redux.sync.min and merged into a per-column minimum in shared
+// memory.  Packing (dist<<16 | index) makes the integer minimum implement "smallest distance,
+// then smallest index" under any order of reduction.  Partial results of the (row tile x column
+// chunk) grid are merged with atomicMin on the packed words, so the whole distance matrix is
+// computed exactly once for both directions.  grid.z batches independent pairs.
+#include "common.cuh"
+
+namespace b200vo {
+
+constexpr int MT_THREADS = 256;
+constexpr int MT_MAXCHUNK = 512;
+
+struct MatchArgs {
+    const uint8_t* q; const uint8_t* t;   // descriptor bases
+    size_t q_stride, t_stride;            // bytes between consecutive pairs (raw mode)
+    const int* counts;                    // slot mode: kp_count per slot (NULL in raw mode)
+    int n1, n2;                           // raw mode sizes
+    int slots, first_slot, slot_b_override, kp_cap;
+    uint32_t* nnq; uint32_t* nnt;         // [pairs][out_stride]
+    int out_stride;
+    int chunk;                            // train columns per CTA (<= MT_MAXCHUNK)
+};
+
+template <int R>
+__global__ void __launch_bounds__(MT_THREADS)
+match_kernel(MatchArgs a) {
+    __shared__ __align__(16) uint32_t s_t[MT_MAXCHUNK * 8];
+    __shared__ uint32_t s_col[MT_MAXCHUNK];
+
+    const int pair = blockIdx.z;
+    const uint8_t* q; const uint8_t* t;
+    int n1, n2;
+    if (a.counts) {
+        const int sa = (a.first_slot + pair) % a.slots;
+        const int sb = (a.slot_b_override >= 0) ? a.slot_b_override : (a.first_slot + pair + 1) % a.slots;
+        q = a.q + (size_t)sa * a.kp_cap * kDescBytes;
+        t = a.t + (size_t)sb * a.kp_cap * kDescBytes;
+        n1 = a.counts[sa]; n2 = a.counts[sb];
+    } else {
+        q = a.q + (size_t)pair * a.q_stride;
+        t = a.t + (size_t)pair * a.t_stride;
+        n1 = a.n1; n2 = a.n2;
+    }
+    const int row0 = blockIdx.y * (MT_THREADS * R);
+    const int col0 = blockIdx.x * a.chunk;
+    if (row0 >= n1 || col0 >= n2) return;
+    const int ncols = min(a.chunk, n2 - col0);
+    const int tid = threadIdx.x;
+
+    // stage the train chunk (coalesced 16-B loads) and reset the column minima
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(t + (size_t)col0 * kDescBytes);
+        uint4* dst = reinterpret_cast<uint4*>(s_t);
+        for (int i = tid; i < ncols * 2; i += MT_THREADS) dst[i] = __ldg(src + i);
+        for (int i = tid; i < ncols; i += MT_THREADS) s_col[i] = 0xFFFFFFFFu;
+    }
+
+    uint32_t qd[R][8];
+    uint32_t rowpack[R];       // row index, or a huge distance offset for padding rows
+    uint32_t best[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * MT_THREADS + tid;
+        best[r] = 0xFFFFFFFFu;
+        if (row < n1) {
+            const uint4* p = reinterpret_cast<const uint4*>(q + (size_t)row * kDescBytes);
+            const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+            qd[r][0] = lo.x; qd[r][1] = lo.y; qd[r][2] = lo.z; qd[r][3] = lo.w;
+            qd[r][4] = hi.x; qd[r][5] = hi.y; qd[r][6] = hi.z; qd[r][7] = hi.w;
+            rowpack[r] = (uint32_t)row;
+        } else {
+#pragma unroll
+            for (int w = 0; w < 8; ++w) qd[r][w] = 0;
+            rowpack[r] = 0x80000000u;      // loses every minimum
+        }
+    }
+    __syncthreads();
+
+    const int lane = tid & 31;
+#pragma unroll 2
+    for (int j = 0; j < ncols; ++j) {
+        const uint4 t0 = *reinterpret_cast<const uint4*>(&s_t[j * 8]);
+        const uint4 t1 = *reinterpret_cast<const uint4*>(&s_t[j * 8 + 4]);
+        uint32_t colmin = 0xFFFFFFFFu;
+        const uint32_t colidx = (uint32_t)(col0 + j);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t d = __popc(qd[r][0] ^ t0.x) + __popc(qd[r][1] ^ t0.y) + __popc(qd[r][2] ^ t0.z) +
+                               __popc(qd[r][3] ^ t0.w) + __popc(qd[r][4] ^ t1.x) + __popc(qd[r][5] ^ t1.y) +
+                               __popc(qd[r][6] ^ t1.z) + __popc(qd[r][7] ^ t1.w);
+            best[r] = min(best[r], (d << 16) | colidx);
+            colmin = min(colmin, (d << 16) + rowpack[r]);
+        }
+        colmin = __reduce_min_sync(0xffffffffu, colmin);
+        if (lane == 0) atomicMin(&s_col[j], colmin);
+    }
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * MT_THREADS + tid;
+        if (row < n1) atomicMin(&a.nnq[(size_t)pair * a.out_stride + row], best[r]);
+    }
+    __syncthreads();
+    for (int i = tid; i < ncols; i += MT_THREADS) atomicMin(&a.nnt[(size_t)pair * a.out_stride + col0 + i], s_col[i]);
+}
+
+static int pick_rows_per_thread(int n1) {
+    // least padding wins; prefer more rows per thread (fewer shared-memory reads per distance)
+    int bestR = 1;
+    long bestpad = -1;
+    const int cand[3] = {4, 2, 1};
+    for (int k = 0; k < 3; ++k) {
+        const int tile = MT_THREADS * cand[k];
+        const long padded = (long)div_up(n1, tile) * tile;
+        if (bestpad < 0 || padded < bestpad) { bestpad = padded; bestR = cand[k]; }
+    }
+    return bestR;
+}
+
+static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_expected, int npairs) {
+    if (npairs <= 0 || n1max <= 0 || n2max <= 0) return B200VO_OK;
+    const int R = pick_rows_per_thread(n1_expected);
+    const int row_tiles = div_up(n1max, MT_THREADS * R);
+    // enough CTAs to fill 148 SMs a few times over when the batch is small
+    int chunk = MT_MAXCHUNK;
+    while (chunk > 64 && (long)row_tiles * div_up(n2max, chunk) * npairs < 4 * 148) chunk >>= 1;
+    a.chunk = chunk;
+    dim3 grid(div_up(n2max, chunk), row_tiles, npairs);
+    switch (R) {
+        case 4: match_kernel<4><<<grid, MT_THREADS, 0, ctx->stream>>>(a); break;
+        case 2: match_kernel<2><<<grid, MT_THREADS, 0, ctx->stream>>>(a); break;
+        default: match_kernel<1><<<grid, MT_THREADS, 0, ctx->stream>>>(a); break;
+    }
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
+int launch_match_slots(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_override) {
+    const StoreView& sv = ctx->store;
+    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.nnq, 0xFF, (size_t)npairs * sv.kp_cap * sizeof(uint32_t), ctx->stream));
+    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.nnt, 0xFF, (size_t)npairs * sv.kp_cap * sizeof(uint32_t), ctx->stream));
+    MatchArgs a{};
+    a.q = sv.desc; a.t = sv.desc; a.counts = sv.kp_count;
+    a.slots = sv.slots; a.first_slot = first_slot; a.slot_b_override = slot_b_override; a.kp_cap = sv.kp_cap;
+    a.nnq = ctx->pairs.nnq; a.nnt = ctx->pairs.nnt; a.out_stride = sv.kp_cap;
+    // the grid is sized for the capacity; CTAs beyond the actual counts exit immediately
+    return run_match(ctx, a, sv.kp_cap, sv.kp_cap, ctx->opt.nfeatures, npairs);
+}
+
+int launch_match_raw(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t, int n2, int npairs,
+                     uint32_t* nnq, uint32_t* nnt) {
+    const int stride = max(n1, n2);
+    B200VO_CUDA_CHECK(cudaMemsetAsync(nnq, 0xFF, (size_t)npairs * stride * sizeof(uint32_t), ctx->stream));
+    B200VO_CUDA_CHECK(cudaMemsetAsync(nnt, 0xFF, (size_t)npairs * stride * sizeof(uint32_t), ctx->stream));
+    MatchArgs a{};
+    a.q = q; a.t = t; a.q_stride = (size_t)n1 * kDescBytes; a.t_stride = (size_t)n2 * kDescBytes;
+    a.counts = nullptr; a.n1 = n1; a.n2 = n2;
+    a.nnq = nnq; a.nnt = nnt; a.out_stride = stride;
+    return run_match(ctx, a, n1, n2, n1, npairs);
+}
+
+}  // namespace b200vo

@@ -1,0 +1,156 @@
+// K6 intensity-centroid orientation and K8 rotated-BRIEF 256-bit descriptors.
+//
+// What it replaces: ICAngles + computeOrbDescriptors inside cv::ORB::detectAndCompute
+// (reference src/visual_odometry.cpp:113).  Semantics from SURVEY.md App. A.6/A.7:
+//   * moments m10, m01 over the radius-15 disc (749 px) of the UNBLURRED level, integers;
+//     angle = fastAtan2((float)m01, (float)m10) -- OpenCV's degree-7 polynomial, float32, no FMA;
+//   * descriptor on the BLURRED level: theta = angle * (float)(pi/180); a = (float)cos((double)theta),
+//     b = (float)sin((double)theta); each of the 512 pattern points is rotated with separate float
+//     multiplies/adds (no FMA) and rounded half-to-even; bit k of byte i = I(p[16i+2k]) < I(p[16i+2k+1]).
+//
+// One warp per keypoint.  Orientation: lane = column u of the disc, loop over rows, integer
+// redux.sync reduction.  Descriptor: lane = descriptor byte; the lane keeps its 16 pattern points
+// in registers for the lifetime of the warp; the 32 bytes go out as one coalesced 32-B store.
+// The kernel also assembles the frame's final keypoint array in canonical (octave, y, x) order.
+#include "common.cuh"
+#include "brief_pattern.h"
+
+namespace b200vo {
+
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+__device__ int8_t d_pattern[1024];
+
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float deg = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = __fmul_rn(0.9997878412794807f, deg), p3 = __fmul_rn(-0.3258083974640975f, deg),
+                p5 = __fmul_rn(0.1555786518463281f, deg), p7 = __fmul_rn(-0.04432655554792128f, deg);
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, 2.2204460492503131e-16f));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, 2.2204460492503131e-16f));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.0f,
+                      __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0.0f) a = __fsub_rn(180.0f, a);
+    if (y < 0.0f) a = __fsub_rn(360.0f, a);
+    return a;
+}
+
+// grid: (ceil(max level kp / warps per block), kLevels, n); block: 256 threads = 8 warps
+__global__ void __launch_bounds__(256)
+orient_kernel(StoreView sv, int first_slot) {
+    const int level = blockIdx.y;
+    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int* counts = sv.lkp_count + slot * kLevels;
+    const int cnt = counts[level];
+    int base = 0, total = 0;
+#pragma unroll
+    for (int l = 0; l < kLevels; ++l) {
+        const int c = counts[l];
+        if (l < level) base += c;
+        total += c;
+    }
+    if (level == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (total > sv.kp_cap) atomicOr(&sv.flags[slot], 8);
+        sv.kp_count[slot] = min(total, sv.kp_cap);
+    }
+    if (i >= cnt || base + i >= sv.kp_cap) return;
+    const LevelGeom g = sv.lv[level];
+    const uint32_t key = sv.lkp_key[(size_t)slot * sv.lkp_total + sv.lkp_off[level] + i];
+    const int x = (key >> 8) & 0xFFF, y = key >> 20;
+    const uint8_t* __restrict__ c = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset + (size_t)y * g.pitch + x;
+    const int u = lane - kHalfPatch;
+    const int au = abs(u);
+    int m10 = 0, m01 = 0;
+    if (lane < 31) {
+#pragma unroll 1
+        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+            if (au <= c_umax[abs(v)]) {
+                const int val = __ldg(c + v * g.pitch + u);
+                m10 += u * val;
+                m01 += v * val;
+            }
+        }
+    }
+    m10 = __reduce_add_sync(0xffffffffu, m10);
+    m01 = __reduce_add_sync(0xffffffffu, m01);
+    if (lane == 0) {
+        b200vo_keypoint kp;
+        kp.x = __fmul_rn((float)x, g.scale);
+        kp.y = __fmul_rn((float)y, g.scale);
+        kp.size = __fmul_rn(31.0f, g.scale);
+        kp.angle = fast_atan2_deg((float)m01, (float)m10);
+        kp.response = sv.lkp_resp[(size_t)slot * sv.lkp_total + sv.lkp_off[level] + i];
+        kp.octave = level;
+        kp.class_id = -1;
+        kp.lx = (int16_t)x;
+        kp.ly = (int16_t)y;
+        sv.kp[(size_t)slot * sv.kp_cap + base + i] = kp;
+    }
+}
+
+// grid: (ceil(kp_cap / 8), n); one warp per keypoint
+__global__ void __launch_bounds__(256)
+brief_kernel(StoreView sv, int first_slot) {
+    const int slot = (first_slot + blockIdx.y) % sv.slots;
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= sv.kp_count[slot]) return;
+    // this lane's 8 tests = pattern rows 8*lane .. 8*lane+7
+    int8_t pat[32];
+    {
+        const int4* p = reinterpret_cast<const int4*>(d_pattern + lane * 32);
+        *reinterpret_cast<int4*>(&pat[0]) = p[0];
+        *reinterpret_cast<int4*>(&pat[16]) = p[1];
+    }
+    const b200vo_keypoint kp = sv.kp[(size_t)slot * sv.kp_cap + i];
+    const LevelGeom g = sv.lv[kp.octave];
+    const uint8_t* __restrict__ c = sv.blur + (size_t)slot * sv.slot_bytes + g.offset + (size_t)kp.ly * g.pitch + kp.lx;
+    const float theta = __fmul_rn(kp.angle, (float)(3.14159265358979323846 / 180.0));
+    const float a = (float)cos((double)theta), b = (float)sin((double)theta);
+    uint32_t byte = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1];
+        const float x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+        const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+        const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+        const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+        const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+        const int t0 = __ldg(c + iy0 * g.pitch + ix0);
+        const int t1 = __ldg(c + iy1 * g.pitch + ix1);
+        byte |= (uint32_t)(t0 < t1) << k;
+    }
+    sv.desc[((size_t)slot * sv.kp_cap + i) * kDescBytes + lane] = (uint8_t)byte;
+}
+
+int upload_brief_pattern() {
+    cudaError_t e = cudaMemcpyToSymbol(d_pattern, kBriefPattern31, sizeof(kBriefPattern31));
+    if (e != cudaSuccess) { set_error("pattern upload failed: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
+    return B200VO_OK;
+}
+
+int launch_orient(b200vo_ctx* ctx, int first_slot, int n) {
+    int maxkp = 1;
+    for (int l = 0; l < kLevels; ++l) maxkp = max(maxkp, ctx->store.lv[l].kp_cap);
+    dim3 grid(div_up(maxkp, 8), kLevels, n);
+    orient_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, first_slot);
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
+int launch_brief(b200vo_ctx* ctx, int first_slot, int n) {
+    dim3 grid(div_up(ctx->store.kp_cap, 8), n);
+    brief_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, first_slot);
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
+}  // namespace b200vo

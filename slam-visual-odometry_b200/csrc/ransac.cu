@@ -1,0 +1,258 @@
+// K13 batched five-point hypotheses, K14 Sampson scoring, K15 best-model selection,
+// K16 recoverPose (decomposition, triangulation, cheirality vote).
+//
+// What it replaces: cv::findEssentialMat(p1, p2, K, RANSAC, 0.999, 2.0, mask) and
+// cv::recoverPose(E, p1, p2, K, R, t, mask) as called by estimate_relative_pose
+// (reference src/visual_odometry.cpp:213-216, :265-277).  The math is in geom_core.cuh.
+//
+// OpenCV draws its samples from a private RNG and stops adaptively; here every pair evaluates a
+// fixed, seeded set of H hypotheses (a pure function of (seed, pair id, hypothesis index), never
+// of the rank or batch), all in one launch:
+//   five_point_kernel : one thread per hypothesis -> up to 10 essential matrices
+//   score_kernel      : one warp per hypothesis; lanes stride over the correspondences, ballot +
+//                       popc counts inliers of each model; the best (count, first index) of the
+//                       pair is kept with one 64-bit atomicMax on (count << 32 | ~model_index)
+//   finalize_kernel   : winning E, its inlier mask, record fields
+//   recover_pose_kernel: one CTA per pair; the four (R,t) candidates are voted on by all points.
+// "First arg-max wins" is exactly OpenCV's rule (a model replaces the best only if strictly
+// better), realised order-independently by the packed atomicMax.
+#include "common.cuh"
+#include "geom_core.cuh"
+
+namespace b200vo {
+
+struct RansacArgs {
+    const int32_t* samples;     // [pairs][nhyp][5] or NULL (draw on device)
+    uint64_t seed;
+    int64_t first_pair_id;
+    int nhyp;
+    float thr2f;                // (float)(thr*thr), thr in normalised units
+    int min_matches;            // reference kMinMatchesForPose
+};
+
+__global__ void __launch_bounds__(128)
+five_point_kernel(PairView pv, RansacArgs ra) {
+    const int pair = blockIdx.y;
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= ra.nhyp) return;
+    const int m = pv.n_good[pair];
+    int* nsol = pv.nsol + (size_t)pair * pv.nhyp_cap;
+    if (m < ra.min_matches || m < 5) { nsol[h] = 0; return; }
+    int idx[5];
+    if (ra.samples) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) idx[k] = ra.samples[((size_t)pair * ra.nhyp + h) * 5 + k];
+    } else {
+        geom::draw_sample(geom::pair_stream(ra.seed, ra.first_pair_id + pair), h, m, idx);
+    }
+    const size_t base = (size_t)pair * pv.kp_cap;
+    double x1[5][2], x2[5][2];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int i = min(max(idx[k], 0), m - 1);
+        x1[k][0] = pv.x1x[base + i]; x1[k][1] = pv.x1y[base + i];
+        x2[k][0] = pv.x2x[base + i]; x2[k][1] = pv.x2y[base + i];
+    }
+    double E[10][9];
+    const int ns = geom::five_point(x1, x2, E);
+    double* out = pv.models + ((size_t)pair * pv.nhyp_cap + h) * 90;
+    for (int s = 0; s < ns; ++s)
+        for (int k = 0; k < 9; ++k) out[s * 9 + k] = E[s][k];
+    nsol[h] = ns;
+}
+
+// one warp per hypothesis
+__global__ void __launch_bounds__(256)
+score_kernel(PairView pv, RansacArgs ra) {
+    const int pair = blockIdx.y;
+    const int h = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (h >= ra.nhyp) return;
+    const int ns = pv.nsol[(size_t)pair * pv.nhyp_cap + h];
+    if (ns == 0) return;
+    const int m = pv.n_good[pair];
+    const size_t base = (size_t)pair * pv.kp_cap;
+    const double* __restrict__ x1x = pv.x1x + base;
+    const double* __restrict__ x1y = pv.x1y + base;
+    const double* __restrict__ x2x = pv.x2x + base;
+    const double* __restrict__ x2y = pv.x2y + base;
+    const double* models = pv.models + ((size_t)pair * pv.nhyp_cap + h) * 90;
+    unsigned long long best = 0ull;
+    for (int s = 0; s < ns; ++s) {
+        double E[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) E[k] = models[s * 9 + k];
+        int cnt = 0;
+        for (int i0 = 0; i0 < m; i0 += 32) {
+            const int i = i0 + lane;
+            bool in = false;
+            if (i < m) in = geom::sampson_inlier(E, x1x[i], x1y[i], x2x[i], x2y[i], ra.thr2f);
+            cnt += __popc(__ballot_sync(0xffffffffu, in));
+        }
+        if (pv.counts && lane == 0) pv.counts[((size_t)pair * pv.nhyp_cap + h) * 10 + s] = cnt;
+        const unsigned long long packed =
+            ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(h * 10 + s));
+        best = (packed > best) ? packed : best;
+    }
+    if (lane == 0 && best) atomicMax(&pv.best[pair], best);
+}
+
+__global__ void __launch_bounds__(256)
+finalize_kernel(PairView pv, RansacArgs ra) {
+    const int pair = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int m = pv.n_good[pair];
+    const unsigned long long best = pv.best[pair];
+    const int cnt = (int)(best >> 32);
+    const bool found = (m >= ra.min_matches) && (m >= 8) && cnt >= 5;
+    const uint32_t model = 0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFu);
+    const int h = found ? (int)(model / 10) : -1, s = found ? (int)(model % 10) : -1;
+    double E[9];
+    if (found) {
+        const double* src = pv.models + ((size_t)pair * pv.nhyp_cap + h) * 90 + s * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) E[k] = src[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) E[k] = 0.0;
+    }
+    const size_t base = (size_t)pair * pv.kp_cap;
+    for (int i = tid; i < m; i += blockDim.x)
+        pv.inl[base + i] = found ? (uint8_t)geom::sampson_inlier(E, pv.x1x[base + i], pv.x1y[base + i], pv.x2x[base + i],
+                                                                 pv.x2y[base + i], ra.thr2f)
+                                 : (uint8_t)0;
+    if (tid == 0) {
+        for (int k = 0; k < 9; ++k) pv.E[(size_t)pair * 9 + k] = E[k];
+        b200vo_pose_record r;
+        for (int k = 0; k < 9; ++k) r.R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+        r.t[0] = r.t[1] = r.t[2] = 0.0;
+        r.n_matches = m;
+        r.n_inliers = found ? cnt : 0;
+        r.n_valid = 0;
+        r.status = ((m >= ra.min_matches) ? B200VO_ST_MATCHED : 0) | (found ? B200VO_ST_E_FOUND : 0);
+        r.n_cross = pv.n_cross[pair];
+        r.best_hyp = h;
+        r.best_sol = s;
+        r.threshold = (float)pv.thr[pair];
+        pv.rec[pair] = r;
+    }
+}
+
+struct PoseArgs { int min_valid, min_inliers; uint8_t* mask_out; /* [pairs][kp_cap] or NULL */ };
+
+__global__ void __launch_bounds__(256)
+recover_pose_kernel(PairView pv, PoseArgs pa) {
+    __shared__ double s_R[2][9], s_t[3];
+    __shared__ int s_cnt[4], s_best;
+    const int pair = blockIdx.x;
+    const int tid = threadIdx.x;
+    b200vo_pose_record* rec = pv.rec + pair;
+    if (!(rec->status & B200VO_ST_E_FOUND)) return;
+    if (tid == 0) {
+        geom::decompose_essential(pv.E + (size_t)pair * 9, s_R[0], s_R[1], s_t);
+        s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
+    }
+    __syncthreads();
+    const int m = pv.n_good[pair];
+    const size_t base = (size_t)pair * pv.kp_cap;
+    const double tp[3] = {s_t[0], s_t[1], s_t[2]}, tn[3] = {-s_t[0], -s_t[1], -s_t[2]};
+    int c[4] = {0, 0, 0, 0};
+    for (int i = tid; i < m; i += blockDim.x) {
+        if (!pv.inl[base + i]) continue;
+        const double a = pv.x1x[base + i], b = pv.x1y[base + i], cc = pv.x2x[base + i], d = pv.x2y[base + i];
+        // candidate order of cv::recoverPose: (R1,t), (R2,t), (R1,-t), (R2,-t)
+        c[0] += geom::cheirality_ok(s_R[0], tp, a, b, cc, d, 50.0);
+        c[1] += geom::cheirality_ok(s_R[1], tp, a, b, cc, d, 50.0);
+        c[2] += geom::cheirality_ok(s_R[0], tn, a, b, cc, d, 50.0);
+        c[3] += geom::cheirality_ok(s_R[1], tn, a, b, cc, d, 50.0);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int w = __reduce_add_sync(0xffffffffu, c[k]);
+        if ((tid & 31) == 0 && w) atomicAdd(&s_cnt[k], w);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int bi = 0;
+        for (int k = 1; k < 4; ++k)
+            if (s_cnt[k] > s_cnt[bi]) bi = k;      // first maximum wins
+        const double* R = s_R[bi & 1];
+        const double sg = (bi >= 2) ? -1.0 : 1.0;
+        for (int k = 0; k < 9; ++k) rec->R[k] = R[k];
+        for (int k = 0; k < 3; ++k) rec->t[k] = sg * s_t[k];
+        rec->n_valid = s_cnt[bi];
+        if (s_cnt[bi] >= pa.min_valid && rec->n_inliers >= pa.min_inliers) rec->status |= B200VO_ST_POSE_OK;
+        s_best = bi;
+    }
+    if (pa.mask_out) {      // parity hook only: cv::recoverPose overwrites the mask with the winner's test
+        __syncthreads();
+        const int bi = s_best;
+        const double* R = s_R[bi & 1];
+        const double* tt = (bi >= 2) ? tn : tp;
+        for (int i = tid; i < m; i += blockDim.x)
+            pa.mask_out[base + i] = pv.inl[base + i] &&
+                geom::cheirality_ok(R, tt, pv.x1x[base + i], pv.x1y[base + i], pv.x2x[base + i], pv.x2y[base + i], 50.0);
+    }
+}
+
+int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int32_t* d_samples, int nhyp) {
+    if (nhyp > ctx->pairs.nhyp_cap) { set_error("nhyp %d exceeds capacity %d", nhyp, ctx->pairs.nhyp_cap); return B200VO_ERR_CAPACITY; }
+    RansacArgs ra;
+    ra.samples = d_samples; ra.seed = ctx->opt.ransac_seed; ra.first_pair_id = first_pair_id; ra.nhyp = nhyp;
+    const double thr = ctx->opt.ransac_threshold_px / ((ctx->K[0] + ctx->K[1]) / 2.0);
+    ra.thr2f = (float)(thr * thr);
+    ra.min_matches = ctx->opt.min_matches_for_pose;
+    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.best, 0, (size_t)npairs * sizeof(unsigned long long), ctx->stream));
+    five_point_kernel<<<dim3(div_up(nhyp, 128), npairs), 128, 0, ctx->stream>>>(ctx->pairs, ra);
+    B200VO_LAUNCH_CHECK(ctx);
+    score_kernel<<<dim3(div_up(nhyp, 8), npairs), 256, 0, ctx->stream>>>(ctx->pairs, ra);
+    B200VO_LAUNCH_CHECK(ctx);
+    finalize_kernel<<<npairs, 256, 0, ctx->stream>>>(ctx->pairs, ra);
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
+int launch_recover_pose_masked(b200vo_ctx* ctx, int npairs, uint8_t* d_mask_out) {
+    PoseArgs pa{ctx->opt.min_valid_points, ctx->opt.min_inliers, d_mask_out};
+    recover_pose_kernel<<<npairs, 256, 0, ctx->stream>>>(ctx->pairs, pa);
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
+int launch_recover_pose(b200vo_ctx* ctx, int npairs) { return launch_recover_pose_masked(ctx, npairs, nullptr); }
+
+// parity hook: solve the given samples for pair 0 (points staged by the caller)
+int launch_five_point_only(b200vo_ctx* ctx, const int32_t* d_samples, int nhyp) {
+    RansacArgs ra;
+    ra.samples = d_samples; ra.seed = 0; ra.first_pair_id = 0; ra.nhyp = nhyp; ra.thr2f = 0.f; ra.min_matches = 5;
+    five_point_kernel<<<dim3(div_up(nhyp, 128), 1), 128, 0, ctx->stream>>>(ctx->pairs, ra);
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
+// ------------------------------------------------------------------ parity hooks (device side)
+__global__ void score_models_kernel(const double* x1, const double* x2, int npts, const double* models, int nmodels,
+                                    float thr2f, int* counts) {
+    const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (w >= nmodels) return;
+    double E[9];
+    for (int k = 0; k < 9; ++k) E[k] = models[(size_t)w * 9 + k];
+    int cnt = 0;
+    for (int i0 = 0; i0 < npts; i0 += 32) {
+        const int i = i0 + lane;
+        bool in = false;
+        if (i < npts) in = geom::sampson_inlier(E, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], thr2f);
+        cnt += __popc(__ballot_sync(0xffffffffu, in));
+    }
+    if (lane == 0) counts[w] = cnt;
+}
+
+int launch_score_models(b200vo_ctx* ctx, const double* d_x1, const double* d_x2, int npts, const double* d_models,
+                        int nmodels, float thr2f, int* d_counts) {
+    score_models_kernel<<<div_up(nmodels, 8), 256, 0, ctx->stream>>>(d_x1, d_x2, npts, d_models, nmodels, thr2f, d_counts);
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
+}  // namespace b200vo

@@ -1,0 +1,80 @@
+// Flat C wrappers around the C++ VisualOdometry class so the Python parity tests can drive the
+// reference-shaped API (construct, process_frame per frame, read the trajectory) through ctypes.
+#include <cstring>
+#include <exception>
+#include <string>
+#include <vector>
+
+#include "visual_odometry.h"
+
+namespace { thread_local std::string g_msg; }
+
+extern "C" {
+
+const char* vo_host_last_error() { return g_msg.c_str(); }
+
+void* vo_host_create(int width, int height, int nfeatures, int ransac_hypotheses, unsigned long long seed, int device,
+                     int batch_frames) {
+    try {
+        VisualOdometry::Options o;
+        if (nfeatures > 0) o.nfeatures = nfeatures;
+        if (ransac_hypotheses > 0) o.ransac_hypotheses = ransac_hypotheses;
+        o.ransac_seed = seed; o.device = device;
+        if (batch_frames > 0) o.batch_frames = batch_frames;
+        return new VisualOdometry(width, height, o);
+    } catch (const std::exception& e) { g_msg = e.what(); return nullptr; }
+}
+
+void vo_host_destroy(void* h) { delete static_cast<VisualOdometry*>(h); }
+
+// pose_out: 12 doubles (R_wc row-major, then t_wc); returns number of keypoints or <0 on error
+int vo_host_process_frame(void* h, int frame_id, const unsigned char* img, int width, int height, int channels,
+                          double* pose_out, int* moved_from) {
+    try {
+        VisualOdometry* vo = static_cast<VisualOdometry*>(h);
+        cv::Mat wrap(height, width, channels == 3 ? CV_8UC3 : CV_8UC1, const_cast<unsigned char*>(img));
+        Frame f(frame_id, wrap);
+        const cv::Mat disp = vo->process_frame(f);
+        // the reference moves the frame into previous_frame_: the caller's keypoints are gone
+        if (moved_from) *moved_from = f.keypoints.empty() ? 1 : 0;
+        const std::vector<Pose> tr = vo->get_trajectory_poses();
+        const Pose& p = tr.back();
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) pose_out[i * 3 + j] = p.R_wc.at<double>(i, j);
+            pose_out[9 + i] = p.t_wc.at<double>(i, 0);
+        }
+        return disp.empty() ? -2 : (int)tr.size();
+    } catch (const std::exception& e) { g_msg = e.what(); return -1; }
+}
+
+// frames: n tightly packed images; poses_out: n*12 doubles
+int vo_host_process_sequence(void* h, const unsigned char* frames, int n, int width, int height, int channels,
+                             double* poses_out) {
+    try {
+        VisualOdometry* vo = static_cast<VisualOdometry*>(h);
+        std::vector<cv::Mat> imgs;
+        const size_t fb = (size_t)width * height * channels;
+        for (int i = 0; i < n; ++i)
+            imgs.emplace_back(height, width, channels == 3 ? CV_8UC3 : CV_8UC1, const_cast<unsigned char*>(frames + (size_t)i * fb));
+        const std::vector<Pose> ps = vo->process_sequence(imgs);
+        for (size_t k = 0; k < ps.size(); ++k)
+            for (int i = 0; i < 3; ++i) {
+                for (int j = 0; j < 3; ++j) poses_out[k * 12 + i * 3 + j] = ps[k].R_wc.at<double>(i, j);
+                poses_out[k * 12 + 9 + i] = ps[k].t_wc.at<double>(i, 0);
+            }
+        return (int)ps.size();
+    } catch (const std::exception& e) { g_msg = e.what(); return -1; }
+}
+
+int vo_host_trajectory_size(void* h) { return (int)static_cast<VisualOdometry*>(h)->get_trajectory().size(); }
+
+int vo_host_last_F(void* h, double* F) {
+    VisualOdometry* vo = static_cast<VisualOdometry*>(h);
+    if (!vo->has_last_F()) return 0;
+    const cv::Matx33d f = vo->last_F();
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) F[i * 3 + j] = f(i, j);
+    return 1;
+}
+
+}  // extern "C"

@@ -1,0 +1,183 @@
+// Host side of the VO pipeline: the reference's VisualOdometry::process_frame orchestration
+// (reference src/visual_odometry.cpp:323-378) over the b200vo C ABI.  Everything the reference
+// delegates to OpenCV runs on the GPU; what stays here is what the reference also does on the
+// host: the fallback logic, F = K^-T E K^-1 bookkeeping, pose chaining and trajectory storage.
+#include "visual_odometry.h"
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+
+#include "b200vo.h"
+
+namespace {
+void check(int rc, const char* what) {
+    if (rc != B200VO_OK) throw std::runtime_error(std::string(what) + ": " + b200vo_last_error());
+}
+
+Pose chained(const Pose& prev, const b200vo_pose_record& rec) {
+    double R[9], t[3], Ro[9], to[3];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R[i * 3 + j] = prev.R_wc.at<double>(i, j);
+        t[i] = prev.t_wc.at<double>(i, 0);
+    }
+    check(b200vo_chain_pose(&rec, R, t, Ro, to), "chain_pose");
+    cv::Mat Rm(3, 3, CV_64F), tm(3, 1, CV_64F);
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Rm.at<double>(i, j) = Ro[i * 3 + j];
+        tm.at<double>(i, 0) = to[i];
+    }
+    return Pose(Rm, tm);
+}
+
+// rows of an image as a tightly described u8 buffer
+struct ImageView { const uint8_t* data; size_t pitch; int channels; };
+ImageView view_of(const cv::Mat& img, int w, int h) {
+    if (img.empty() || img.cols != w || img.rows != h) throw std::runtime_error("image size does not match the VisualOdometry instance");
+    const int ch = img.channels();
+    if (img.depth() != CV_8U || (ch != 1 && ch != 3)) throw std::runtime_error("image must be 8-bit with 1 or 3 channels");
+    return ImageView{img.data, (size_t)img.step, ch};
+}
+}  // namespace
+
+VisualOdometry::VisualOdometry(int image_width, int image_height) { init(image_width, image_height, Options{}); }
+VisualOdometry::VisualOdometry(int image_width, int image_height, const Options& options) { init(image_width, image_height, options); }
+
+void VisualOdometry::init(int w, int h, const Options& o) {
+    options_ = o;
+    width_ = w; height_ = h;
+    b200vo_options opt;
+    check(b200vo_default_options(&opt, w, h), "default_options");
+    opt.nfeatures = o.nfeatures;
+    opt.ransac_hypotheses = o.ransac_hypotheses;
+    opt.ransac_seed = o.ransac_seed;
+    opt.max_frames = std::max(2, o.batch_frames + 1);
+    check(b200vo_create(&opt, o.device, &ctx_), "create");
+    // intrinsics synthesised from the image size (reference src/visual_odometry.cpp:90-98)
+    camera_matrix_ = cv::Mat::eye(3, 3, CV_64F);
+    camera_matrix_.at<double>(0, 0) = opt.fx; camera_matrix_.at<double>(1, 1) = opt.fy;
+    camera_matrix_.at<double>(0, 2) = opt.cx; camera_matrix_.at<double>(1, 2) = opt.cy;
+}
+
+VisualOdometry::~VisualOdometry() { b200vo_destroy(ctx_); }
+
+void VisualOdometry::push_pose(const Pose& p) {
+    std::lock_guard<std::mutex> lock(trajectory_mutex_);
+    trajectory_positions_.push_back(p.C_w().clone());
+    trajectory_poses_.emplace_back(p.R_wc.clone(), p.t_wc.clone());
+}
+
+cv::Mat VisualOdometry::process_frame(Frame& frame) {
+    const int slots = std::max(2, options_.batch_frames + 1);
+    const int cur = initialized_ ? (previous_slot_ + 1) % slots : 0;
+    const ImageView v = view_of(frame.image, width_, height_);
+    check(b200vo_upload_frames(ctx_, v.data, 1, v.pitch, v.pitch * height_, v.channels, cur), "upload_frames");
+    check(b200vo_detect(ctx_, cur, 1), "detect");
+
+    // detect_features(): fill frame.keypoints / frame.descriptors (reference :103-117)
+    const int cap = b200vo_max_keypoints(ctx_);
+    std::vector<b200vo_keypoint> kps((size_t)cap);
+    cv::Mat desc(cap, 32, CV_8UC1);
+    int n = 0;
+    check(b200vo_get_features(ctx_, cur, kps.data(), desc.data, cap, &n), "get_features");
+    frame.keypoints.resize((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        cv::KeyPoint& k = frame.keypoints[(size_t)i];
+        k.pt.x = kps[i].x; k.pt.y = kps[i].y; k.size = kps[i].size; k.angle = kps[i].angle;
+        k.response = kps[i].response; k.octave = kps[i].octave; k.class_id = kps[i].class_id;
+    }
+    cv::Mat d(n, 32, CV_8UC1);
+    for (int i = 0; i < n; ++i) std::copy(desc.data + (size_t)i * 32, desc.data + (size_t)(i + 1) * 32, d.data + (size_t)i * d.step);
+    frame.descriptors = d;
+    frame.processed = true;
+    const cv::Mat display_image = frame.image.clone();
+
+    if (!initialized_) {
+        frame.pose = Pose();
+        push_pose(frame.pose);
+        previous_frame_ = std::move(frame);
+        previous_slot_ = cur;
+        frame_counter_ = 1;
+        initialized_ = true;
+        return display_image;
+    }
+
+    // Default to the last known pose; the record's status bits encode the reference's fallbacks.
+    frame.pose = Pose(previous_frame_.pose.R_wc, previous_frame_.pose.t_wc);
+    b200vo_pose_record rec;
+    double E[9];
+    check(b200vo_relative_pose(ctx_, previous_slot_, cur, frame_counter_ - 1, nullptr, 0, &rec, E, nullptr, 0), "relative_pose");
+    if (rec.status & B200VO_ST_E_FOUND) {
+        double F[9];
+        check(b200vo_fundamental_from_essential(ctx_, E, F), "fundamental");
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) last_F_(i, j) = F[i * 3 + j];
+        has_last_F_ = true;
+        frame.pose = chained(previous_frame_.pose, rec);
+    }
+    push_pose(frame.pose);
+    previous_frame_ = std::move(frame);
+    previous_slot_ = cur;
+    ++frame_counter_;
+    return display_image;
+}
+
+std::vector<Pose> VisualOdometry::process_sequence(const std::vector<cv::Mat>& images) {
+    std::vector<Pose> out;
+    const int slots = std::max(2, options_.batch_frames + 1);
+    const int B = slots - 1;
+    size_t next = 0;
+    if (!initialized_ && !images.empty()) {
+        const ImageView v = view_of(images[0], width_, height_);
+        check(b200vo_upload_frames(ctx_, v.data, 1, v.pitch, v.pitch * height_, v.channels, 0), "upload_frames");
+        check(b200vo_detect(ctx_, 0, 1), "detect");
+        Frame f(0, cv::Mat());
+        f.pose = Pose();
+        push_pose(f.pose);
+        out.emplace_back(f.pose.R_wc, f.pose.t_wc);
+        previous_frame_ = std::move(f);
+        previous_slot_ = 0;
+        frame_counter_ = 1;
+        initialized_ = true;
+        next = 1;
+    }
+    std::vector<b200vo_pose_record> recs((size_t)B);
+    while (next < images.size()) {
+        const int n = (int)std::min<size_t>((size_t)B, images.size() - next);
+        const int first = (previous_slot_ + 1) % slots;
+        for (int i = 0; i < n; ++i) {
+            const ImageView v = view_of(images[next + i], width_, height_);
+            check(b200vo_upload_frames(ctx_, v.data, 1, v.pitch, v.pitch * height_, v.channels, (first + i) % slots), "upload_frames");
+        }
+        check(b200vo_detect(ctx_, first, n), "detect");
+        check(b200vo_process_pairs(ctx_, previous_slot_, n, frame_counter_ - 1, recs.data()), "process_pairs");
+        Pose cur(previous_frame_.pose.R_wc, previous_frame_.pose.t_wc);
+        for (int i = 0; i < n; ++i) {
+            if (recs[i].status & B200VO_ST_E_FOUND) cur = chained(cur, recs[i]);
+            push_pose(cur);
+            out.emplace_back(cur.R_wc, cur.t_wc);
+        }
+        previous_frame_.pose = Pose(cur.R_wc, cur.t_wc);
+        previous_frame_.id = (int)(frame_counter_ + n - 1);
+        previous_slot_ = (first + n - 1) % slots;
+        frame_counter_ += n;
+        next += (size_t)n;
+    }
+    return out;
+}
+
+std::vector<cv::Mat> VisualOdometry::get_trajectory() {
+    std::lock_guard<std::mutex> lock(trajectory_mutex_);
+    return trajectory_positions_;
+}
+
+std::vector<Pose> VisualOdometry::get_trajectory_poses() {
+    std::lock_guard<std::mutex> lock(trajectory_mutex_);
+    std::vector<Pose> copy;
+    copy.reserve(trajectory_poses_.size());
+    for (const Pose& p : trajectory_poses_) copy.emplace_back(p.R_wc, p.t_wc);
+    return copy;
+}
+
+bool VisualOdometry::has_last_F() const { return has_last_F_; }
+cv::Matx33d VisualOdometry::last_F() const { return last_F_; }

@@ -1,0 +1,150 @@
+"""GPU parity, geometry stages (K12-K17) through the C ABI, under a shared seeded hypothesis set
+(SURVEY D5 / section 8c).  Tolerances: solution sets |dE| <= 1e-6 (max-abs, up to sign) for >= 95 %
+of the cv2/oracle solutions (the remainder are ill-conditioned roots where cv2 itself only holds the
+cubic constraints to ~1e-6); inlier counts equal for >= 99 % of models; relative rotation within
+0.1 deg and translation direction within 0.5 deg (north star)."""
+import numpy as np
+import pytest
+
+from oracle import geometry as G
+from oracle import match as M
+from oracle import orb as O
+
+pytestmark = pytest.mark.gpu
+
+NF, NHYP = 2000, 256
+
+
+@pytest.fixture(scope="module")
+def scene(built, seq_kitti):
+    frames, R_wc, C_w, K = seq_kitti
+    ctx = built.Context(1241, 376, nfeatures=NF, max_frames=4, ransac_hypotheses=NHYP)
+    ctx.upload_frames(frames, 0)
+    ctx.detect(0, 2)
+    f0, f1 = ctx.get_features(0), ctx.get_features(1)
+    good, n_cross, thr = ctx.match(0, 1)
+    p1 = np.stack([f0[0]["x"][good["queryIdx"]], f0[0]["y"][good["queryIdx"]]], 1)
+    p2 = np.stack([f1[0]["x"][good["trainIdx"]], f1[0]["y"][good["trainIdx"]]], 1)
+    x1, x2 = G.normalize_points(p1, K), G.normalize_points(p2, K)
+    yield dict(ctx=ctx, K=K, x1=x1, x2=x2, p1=p1, p2=p2, good=good, b=built, gt=(R_wc, C_w))
+    ctx.close()
+
+
+def _set_err(a, b):
+    return min(np.abs(a - b).max(), np.abs(a + b).max())
+
+
+def test_sampler_matches_oracle(built):
+    for (seed, pid, m) in ((42, 0, 371), (42, 998, 37), (7, 123456789, 5), (2**63 + 5, 3, 100000)):
+        assert np.array_equal(built.draw_samples(seed, pid, 64, m), G.draw_samples(seed, pid, 64, m))
+
+
+def test_five_point_solution_sets(scene):
+    x1, x2 = scene["x1"], scene["x2"]
+    S = G.draw_samples(42, 0, NHYP, len(x1))
+    E, ns = scene["ctx"].five_point(x1, x2, S)
+    errs, count_mismatch, res = [], 0, []
+    for h, s in enumerate(S):
+        ref = G.five_point(x1[s], x2[s])
+        got = E[h, :ns[h]].reshape(-1, 3, 3)
+        count_mismatch += (len(ref) != len(got))
+        for e in ref:
+            errs.append(min([_set_err(e, g) for g in got], default=1.0))
+        for g in got:
+            assert abs(np.linalg.norm(g) - 1.0) < 1e-12
+            res.append(max(abs(np.linalg.det(g)), np.abs(2 * g @ g.T @ g - np.trace(g @ g.T) * g).max()))
+            X1 = np.c_[x1[s], np.ones(5)]; X2 = np.c_[x2[s], np.ones(5)]
+            assert np.abs(((X2 @ g) * X1).sum(1)).max() < 1e-12        # epipolar constraint on the sample
+    errs = np.array(errs)
+    assert (errs <= 1e-6).mean() >= 0.95, "only %.3f of oracle solutions reproduced to 1e-6" % (errs <= 1e-6).mean()
+    assert count_mismatch <= 0.03 * NHYP
+    assert np.percentile(res, 99) < 1e-9        # the GPU solutions satisfy the cubic constraints
+
+
+def test_five_point_vs_cv2_live(scene):
+    cv2 = pytest.importorskip("cv2")
+    x1, x2, p1, p2, K = scene["x1"], scene["x2"], scene["p1"], scene["p2"], scene["K"]
+    S = G.draw_samples(42, 1, 128, len(x1))
+    E, ns = scene["ctx"].five_point(x1, x2, S)
+    errs = []
+    for h, s in enumerate(S):
+        ref = cv2.findEssentialMat(p1[s].astype(np.float32), p2[s].astype(np.float32), K, cv2.RANSAC, 0.999, 2.0)[0]
+        if ref is None:
+            continue
+        for e in ref.reshape(-1, 3, 3):
+            errs.append(min([_set_err(e, g) for g in E[h, :ns[h]].reshape(-1, 3, 3)], default=1.0))
+    errs = np.array(errs)
+    assert (errs <= 1e-6).mean() >= 0.93
+
+
+def test_inlier_counts_match_oracle(scene):
+    x1, x2, K = scene["x1"], scene["x2"], scene["K"]
+    S = G.draw_samples(42, 2, 64, len(x1))
+    E, ns = scene["ctx"].five_point(x1, x2, S)
+    models = np.concatenate([E[h, :ns[h]] for h in range(len(S))])
+    thr = G.normalized_threshold(K)
+    counts = scene["ctx"].score_models(x1, x2, models, thr)
+    ref = np.array([int(G.inlier_mask(m.reshape(3, 3), x1, x2, thr).sum()) for m in models])
+    assert (counts == ref).mean() >= 0.99 and np.abs(counts - ref).max() <= 2
+
+
+def test_recover_pose_matches_oracle_and_cv2(scene):
+    x1, x2, K = scene["x1"], scene["x2"], scene["K"]
+    S = G.draw_samples(42, 0, 32, len(x1))
+    best = G.ransac_shared(x1, x2, G.normalized_threshold(K), S)
+    n, R, t, mask = scene["ctx"].recover_pose(best["E"], x1, x2, best["mask"])
+    c, Ro, to, ok = G.recover_pose(best["E"], x1, x2, best["mask"])
+    assert n == c and np.array_equal(mask.astype(bool), ok)
+    assert np.abs(R - Ro).max() < 1e-9 and np.abs(t - to).max() < 1e-9
+    try:
+        import cv2
+    except Exception:
+        return
+    nc, Rc, tc, mc = cv2.recoverPose(best["E"], scene["p1"].astype(np.float32), scene["p2"].astype(np.float32), K,
+                                     mask=best["mask"].astype(np.uint8).reshape(-1, 1).copy())
+    assert n == nc and np.abs(R - Rc).max() < 1e-9 and np.abs(t - tc.ravel()).max() < 1e-9
+
+
+def test_relative_pose_shared_hypotheses(scene):
+    """Full K9-K16 for one pair with an explicit sample list, against the oracle run on the same list."""
+    ctx, x1, x2, K = scene["ctx"], scene["x1"], scene["x2"], scene["K"]
+    S = G.draw_samples(1234, 0, NHYP, len(x1))
+    rec, E, mask = ctx.relative_pose(0, 1, pair_id=0, samples=S, want_mask=True)
+    assert rec["n_matches"] == len(x1)
+    assert rec["status"] & 1 and rec["status"] & 2
+    best = G.ransac_shared(x1, x2, G.normalized_threshold(K), S)
+    # arg-max: the GPU's winner must be a maximum under the oracle's scoring too
+    assert abs(int(rec["n_inliers"]) - best["count"]) <= 1
+    og = G.inlier_mask(E, x1, x2, G.normalized_threshold(K))
+    assert abs(int(og.sum()) - best["count"]) <= 1
+    if (rec["best_hyp"], rec["best_sol"]) == (best["hyp"], best["sol"]) or _set_err(E, best["E"]) < 1e-6:
+        c, Ro, to, ok = G.recover_pose(best["E"], x1, x2, best["mask"])
+        R = rec["R"].reshape(3, 3)
+        assert G.rotation_angle_deg(R, Ro) < 0.1 and G.direction_angle_deg(rec["t"], to) < 0.5
+        assert abs(int(rec["n_valid"]) - c) <= 1
+    # F = K^-T E K^-1 (reference visual_odometry.cpp:225-246)
+    F = ctx.fundamental_from_essential(E)
+    assert np.allclose(F, G.fundamental_from_essential(E, K), rtol=1e-12, atol=1e-18)
+
+
+def test_device_sampler_equals_explicit_samples(scene):
+    ctx, x1 = scene["ctx"], scene["x1"]
+    S = scene["b"].draw_samples(42, 17, NHYP, len(x1))
+    a, Ea, _ = ctx.relative_pose(0, 1, pair_id=17, samples=S)
+    b, Eb, _ = ctx.relative_pose(0, 1, pair_id=17)
+    assert a.tobytes() == b.tobytes() and np.array_equal(Ea, Eb)
+
+
+def test_too_few_matches_fallback(built):
+    """< 10 good matches -> status 0, identity pose (reference fallback a, visual_odometry.cpp:344-345)."""
+    rng = np.random.default_rng(0)
+    with built.Context(640, 240, nfeatures=500, max_frames=2, ransac_hypotheses=64) as ctx:
+        d = rng.integers(0, 256, (6, 32), dtype=np.uint8)
+        kp = np.zeros(6, built.KEYPOINT_DTYPE)
+        kp["x"] = rng.uniform(40, 600, 6); kp["y"] = rng.uniform(40, 200, 6)
+        ctx.set_features(0, kp, d); ctx.set_features(1, kp, d)
+        rec = ctx.process_pairs(0, 1, 0)[0]
+        assert rec["status"] == 0 and rec["n_matches"] < 10
+        assert np.array_equal(rec["R"].reshape(3, 3), np.eye(3)) and not rec["t"].any()
+        R, t = built.chain_pose(rec, np.eye(3), np.array([1.0, 2, 3]))
+        assert np.array_equal(R, np.eye(3)) and np.array_equal(t, [1, 2, 3])
