@@ -195,6 +195,14 @@ int b200vo_draw_samples(uint64_t seed, int64_t pair_id, int nhyp, int m, int32_t
 int b200vo_chain_pose(const b200vo_pose_record* rec, const double* R_wc, const double* t_wc, double* R_out, double* t_out);
 int b200vo_fundamental_from_essential(const b200vo_ctx* ctx, const double* essential, double* fundamental);
 
+/* process_frame's accumulation over a whole range of records (reference src/visual_odometry.cpp:340-374):
+ * poses_out[i] = pose after applying recs[0..i] to (R0, t0); 12 doubles each (R_wc row-major, t_wc). */
+int b200vo_chain_trajectory(const b200vo_pose_record* recs, int n, const double* R0, const double* t0, double* poses_out);
+
+/* Microbenchmark of the XOR+POPC+ADD instruction mix the matcher is bound by: sustained 32-bit
+ * population counts per second on this device (the matcher's roofline denominator). */
+int b200vo_measure_popc_rate(b200vo_ctx* ctx, double* popc_per_second);
+
 /* Per-stage CUDA-event timings of the most recent detect / process_pairs call (ms). */
 int b200vo_enable_timing(b200vo_ctx* ctx, int on);
 int b200vo_get_stage_times(b200vo_ctx* ctx, b200vo_stage_times* out);

@@ -50,7 +50,7 @@ EXPORTS = [
     "b200vo_get_fast_candidates", "b200vo_set_features", "b200vo_match_descriptors",
     "b200vo_match_descriptors_device", "b200vo_match", "b200vo_relative_pose", "b200vo_process_pairs",
     "b200vo_process_pairs_device", "b200vo_five_point", "b200vo_score_models", "b200vo_recover_pose",
-    "b200vo_draw_samples", "b200vo_chain_pose", "b200vo_fundamental_from_essential", "b200vo_enable_timing",
+    "b200vo_draw_samples", "b200vo_chain_pose", "b200vo_chain_trajectory", "b200vo_measure_popc_rate", "b200vo_fundamental_from_essential", "b200vo_enable_timing",
     "b200vo_get_stage_times", "b200vo_kernel_launches", "b200vo_stream",
 ]
 
@@ -119,6 +119,21 @@ def chain_pose(rec, R_wc, t_wc):
     if rc:
         raise B200VOError(rc, lib.b200vo_last_error().decode())
     return Ro.reshape(3, 3), to
+
+
+def chain_trajectory(recs, R0=None, t0=None):
+    """Poses (n,12) after applying each record in turn to (R0,t0) -- process_frame's accumulation."""
+    lib = load_library()
+    r = np.ascontiguousarray(recs, POSE_RECORD_DTYPE)
+    R0 = np.eye(3) if R0 is None else R0
+    t0 = np.zeros(3) if t0 is None else t0
+    Rin = np.ascontiguousarray(R0, np.float64).reshape(9)
+    tin = np.ascontiguousarray(t0, np.float64).reshape(3)
+    out = np.zeros((len(r), 12))
+    rc = lib.b200vo_chain_trajectory(_p(r), len(r), _p(Rin), _p(tin), _p(out))
+    if rc:
+        raise B200VOError(rc, lib.b200vo_last_error().decode())
+    return out
 
 
 class Context:
@@ -300,6 +315,11 @@ class Context:
         st = StageTimes()
         self._chk(self.lib.b200vo_get_stage_times(self.h, C.byref(st)))
         return {n: getattr(st, n) for n, _ in StageTimes._fields_}
+
+    def measure_popc_rate(self):
+        v = C.c_double()
+        self._chk(self.lib.b200vo_measure_popc_rate(self.h, C.byref(v)))
+        return v.value
 
     def kernel_launches(self):
         return int(self.lib.b200vo_kernel_launches(self.h))

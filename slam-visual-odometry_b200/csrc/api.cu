@@ -25,6 +25,7 @@ int upload_brief_pattern();
 int launch_score_models(b200vo_ctx* ctx, const double* d_x1, const double* d_x2, int npts, const double* d_models,
                         int nmodels, float thr2f, int* d_counts);
 int launch_recover_pose_masked(b200vo_ctx* ctx, int npairs, uint8_t* d_mask_out);
+int measure_popc_rate(b200vo_ctx* ctx, double* popc_per_second);
 
 static inline int cv_round(float v) { return (int)lrintf(v); }
 static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -690,6 +691,26 @@ int b200vo_chain_pose(const b200vo_pose_record* rec, const double* R_wc, const d
     std::memcpy(R_out, Rn, sizeof(Rn));
     std::memcpy(t_out, tn, sizeof(tn));
     return B200VO_OK;
+}
+
+int b200vo_chain_trajectory(const b200vo_pose_record* recs, int n, const double* R0, const double* t0, double* poses_out) {
+    if (!recs || n < 0 || !R0 || !t0 || !poses_out) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
+    double R[9], t[3];
+    std::memcpy(R, R0, sizeof(R));
+    std::memcpy(t, t0, sizeof(t));
+    for (int i = 0; i < n; ++i) {
+        int rc = b200vo_chain_pose(recs + i, R, t, R, t);
+        if (rc) return rc;
+        std::memcpy(poses_out + (size_t)i * 12, R, sizeof(R));
+        std::memcpy(poses_out + (size_t)i * 12 + 9, t, sizeof(t));
+    }
+    return B200VO_OK;
+}
+
+int b200vo_measure_popc_rate(b200vo_ctx* ctx, double* popc_per_second) {
+    if (!ctx || !popc_per_second) { set_error("null argument"); return B200VO_ERR_BAD_ARG; }
+    B200VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    return measure_popc_rate(ctx, popc_per_second);
 }
 
 int b200vo_fundamental_from_essential(const b200vo_ctx* ctx, const double* E, double* F) {

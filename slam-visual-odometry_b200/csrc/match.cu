@@ -171,4 +171,42 @@ int launch_match_raw(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t
     return run_match(ctx, a, n1, n2, n1, npairs);
 }
 
+// ------------------------------------------------------------------ POPC-pipe microbenchmark
+// Same instruction mix as the matcher's inner loop (LOP3 xor, POPC, IADD), 8 independent chains
+// per thread, enough CTAs to fill every SM; reports sustained popc32/s.
+__global__ void __launch_bounds__(256)
+popc_rate_kernel(uint32_t* out, int iters) {
+    uint32_t a[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a[k] = threadIdx.x * 2654435761u + k * 40503u + blockIdx.x; acc[k] = 0; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += __popc(a[k] ^ (uint32_t)i);
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += acc[k];
+    if (s == 0xFFFFFFFFu) out[0] = s;       // never true; keeps the loop alive
+}
+
+int measure_popc_rate(b200vo_ctx* ctx, double* popc_per_second) {
+    uint32_t* d = nullptr;
+    B200VO_CUDA_CHECK(cudaMalloc(&d, 256));
+    const int blocks = 148 * 8, iters = 1 << 15;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        B200VO_CUDA_CHECK(cudaEventRecord(ctx->ev[14], ctx->stream));
+        popc_rate_kernel<<<blocks, 256, 0, ctx->stream>>>(d, iters);
+        B200VO_LAUNCH_CHECK(ctx);
+        B200VO_CUDA_CHECK(cudaEventRecord(ctx->ev[15], ctx->stream));
+        B200VO_CUDA_CHECK(cudaEventSynchronize(ctx->ev[15]));
+        float ms = 0.f;
+        B200VO_CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev[14], ctx->ev[15]));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d);
+    *popc_per_second = (double)blocks * 256.0 * iters * 8.0 / (best * 1e-3);
+    return B200VO_OK;
+}
+
 }  // namespace b200vo

@@ -1,0 +1,91 @@
+"""Host build of the product's geometry header (csrc/geom_core.cuh -> tests/hostsim) checked on
+the CPU against the cv2 golden vectors and the numpy oracle.  This is how the five-point solver,
+the sampler, the SVD decomposition and the cheirality test are validated without a GPU; the
+GPU tests then check the SAME code compiled for sm_100a."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import geometry as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def hs(built):
+    lib = ctypes.CDLL(os.path.join(ROOT, "tests", "hostsim", "libgeom_host.so"))
+    return lib
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _pts(golden):
+    g = golden["good"]
+    K = golden["K"]
+    x1 = np.ascontiguousarray(G.normalize_points(golden["f0_pt"][g[:, 0]], K))
+    x2 = np.ascontiguousarray(G.normalize_points(golden["f1_pt"][g[:, 1]], K))
+    return x1, x2, K
+
+
+def test_sampler_equals_oracle(hs):
+    for (seed, pid, m) in ((42, 0, 60), (1, 999, 5), (2**64 - 1, 12345, 7000)):
+        out = np.zeros((32, 5), np.int32)
+        hs.hs_draw_samples(ctypes.c_ulonglong(seed), ctypes.c_longlong(pid), 32, m, P(out))
+        assert np.array_equal(out, G.draw_samples(seed, pid, 32, m))
+
+
+def test_real_roots_known_polynomial(hs):
+    roots = np.array([-0.9, -0.5, -0.1, 0.2, 0.7])
+    c = np.poly(roots)[::-1].copy()                      # ascending
+    c = np.concatenate([c, np.zeros(11 - len(c))])
+    out = np.zeros(10)
+    n = hs.hs_real_roots(P(c), 10, P(out))
+    assert n == 5 and np.allclose(out[:5], roots, atol=1e-13)
+    # a polynomial with complex pairs only has no real roots
+    c2 = np.poly([0.3 + 0.4j, 0.3 - 0.4j, -0.2 + 0.1j, -0.2 - 0.1j])[::-1].real.copy()
+    c2 = np.concatenate([c2, np.zeros(11 - len(c2))])
+    assert hs.hs_real_roots(P(c2), 10, P(out)) == 0
+
+
+def test_five_point_vs_cv2_golden(hs, golden):
+    x1, x2, K = _pts(golden)
+    S = golden["samples"]; ns = golden["fivept_nsol"]; Eg = golden["fivept_E"].reshape(-1, 3, 3)
+    off, errs, same, res = 0, [], 0, []
+    for h, s in enumerate(S):
+        ref = Eg[off:off + ns[h]]; off += ns[h]
+        a, b = np.ascontiguousarray(x1[s]), np.ascontiguousarray(x2[s])
+        E = np.zeros((10, 9))
+        n = hs.hs_five_point(P(a), P(b), P(E))
+        got = E[:n].reshape(-1, 3, 3)
+        same += n == len(ref)
+        for e in ref:
+            errs.append(min([min(np.abs(e - g).max(), np.abs(e + g).max()) for g in got], default=1.0))
+        for g in got:
+            res.append(max(abs(np.linalg.det(g)), np.abs(2 * g @ g.T @ g - np.trace(g @ g.T) * g).max()))
+    assert same >= 0.95 * len(S) and (np.array(errs) <= 1e-6).mean() >= 0.90
+    assert np.percentile(res, 95) < 1e-12
+
+
+def test_scoring_decomposition_cheirality_vs_golden(hs, golden):
+    x1, x2, K = _pts(golden)
+    thr = G.normalized_threshold(K)
+    E = np.ascontiguousarray(golden["E_cv"]).reshape(9)
+    mask = np.zeros(len(x1), np.uint8)
+    c = hs.hs_count_inliers(P(E), P(x1), P(x2), len(x1), ctypes.c_float(np.float32(thr * thr)), P(mask))
+    assert c == int(golden["E_mask"].sum()) and np.array_equal(mask, golden["E_mask"])
+    R1 = np.zeros(9); R2 = np.zeros(9); t = np.zeros(3)
+    hs.hs_decompose(P(E), P(R1), P(R2), P(t))
+    best = None
+    for (R, tt) in ((R1, t), (R2, t), (R1, -t), (R2, -t)):
+        ok = np.zeros(len(x1), np.uint8)
+        tt = np.ascontiguousarray(tt)
+        hs.hs_cheirality(P(R), P(tt), P(x1), P(x2), len(x1), ctypes.c_double(50.0), P(ok))
+        ok &= mask
+        if best is None or ok.sum() > best[0]:
+            best = (int(ok.sum()), R.reshape(3, 3).copy(), tt.copy(), ok.copy())
+    assert best[0] == int(golden["rp_count"]) and np.array_equal(best[3], golden["rp_mask"])
+    assert np.abs(best[1] - golden["rp_R"]).max() < 1e-9 and np.abs(best[2] - golden["rp_t"]).max() < 1e-9
