@@ -319,6 +319,12 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+        del recs_dev, recs_all, d_frames, recs_host, h_frames, stream
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+        ctx.close()
         return 0
 
     hbm_peak, peak_src = peaks()
@@ -389,10 +395,16 @@ def run_b200(args):
                          "trajectory_end": [round(float(x), 3) for x in traj[-1][9:12]] if traj is not None else None},
         "wall_ms_per_step": round(wall_dev * 1e3, 3),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    # torch tensors that were used on the context's stream must be released before the stream dies
+    del recs_dev, recs_all, d_frames, recs_host, h_frames, ok, stream
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     ctx.close()
     return 0
 
