@@ -26,6 +26,7 @@ int launch_score_models(b200vo_ctx* ctx, const double* d_x1, const double* d_x2,
                         int nmodels, float thr2f, int* d_counts);
 int launch_recover_pose_masked(b200vo_ctx* ctx, int npairs, uint8_t* d_mask_out);
 int measure_popc_rate(b200vo_ctx* ctx, double* popc_per_second);
+int init_ransac_kernels();
 
 static inline int cv_round(float v) { return (int)lrintf(v); }
 static inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -241,6 +242,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         TRYCUDA(cudaMemcpy(ctx->d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     TRY(upload_brief_pattern());
+    TRY(init_ransac_kernels());
 
     // ---- pair buffers
     PairView& pv = ctx->pairs;
@@ -265,6 +267,15 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     TRY(dev_alloc(ctx, &pv.rec, P));
     TRY(dev_alloc(ctx, &pv.models, P * pv.nhyp_cap * 90));
     TRY(dev_alloc(ctx, &pv.nsol, P * pv.nhyp_cap));
+    TRY(dev_alloc(ctx, &pv.model_ok, P * pv.nhyp_cap * 10));
+    TRY(dev_alloc(ctx, &pv.fp_setup, P * pv.nhyp_cap * 86));
+    TRY(dev_alloc(ctx, &pv.fp_ok, P * pv.nhyp_cap));
+    TRY(dev_alloc(ctx, &pv.cand_count, 4));
+    pv.cand_cap = (int)std::min<size_t>(P * pv.nhyp_cap * 10, (size_t)1 << 30);
+    TRY(dev_alloc(ctx, &pv.cand_gid, (size_t)pv.cand_cap));
+    TRY(dev_alloc(ctx, &pv.cand_tag, (size_t)pv.cand_cap));
+    TRY(dev_alloc(ctx, &pv.cand_a, (size_t)pv.cand_cap));
+    TRY(dev_alloc(ctx, &pv.cand_b, (size_t)pv.cand_cap));
     pv.counts = nullptr;
 #undef TRY
 #undef TRYCUDA
@@ -601,9 +612,18 @@ int b200vo_five_point(b200vo_ctx* ctx, const double* x1, const double* x2, int n
     if ((rc = ensure_scratch(ctx, (size_t)nhyp * 5 * sizeof(int32_t)))) return rc;
     B200VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_scratch, samples, (size_t)nhyp * 5 * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = launch_five_point_only(ctx, static_cast<const int32_t*>(ctx->d_scratch), nhyp))) return rc;
-    B200VO_CUDA_CHECK(cudaMemcpyAsync(essentials, ctx->pairs.models, (size_t)nhyp * 90 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    B200VO_CUDA_CHECK(cudaMemcpyAsync(nsol, ctx->pairs.nsol, (size_t)nhyp * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<double> raw((size_t)nhyp * 90);
+    std::vector<uint8_t> okv((size_t)nhyp * 10);
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(raw.data(), ctx->pairs.models, raw.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(okv.data(), ctx->pairs.model_ok, okv.size(), cudaMemcpyDeviceToHost, ctx->stream));
     B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (int h = 0; h < nhyp; ++h) {          // solutions of a hypothesis, in root order, without the rejected roots
+        int n = 0;
+        for (int k = 0; k < 10; ++k)
+            if (okv[(size_t)h * 10 + k]) { std::memcpy(essentials + ((size_t)h * 10 + n) * 9, raw.data() + ((size_t)h * 10 + k) * 9, 9 * sizeof(double)); ++n; }
+        for (int k = n; k < 10; ++k) std::memset(essentials + ((size_t)h * 10 + k) * 9, 0, 9 * sizeof(double));
+        nsol[h] = n;
+    }
     return B200VO_OK;
 }
 

@@ -72,6 +72,15 @@ struct PairView {
     double* models;            // [pairs][nhyp_cap][10][9] five-point solutions
     int* nsol;                 // [pairs][nhyp_cap]
     int* counts;               // [pairs][nhyp_cap][10] inlier counts (parity hook; may be NULL)
+    uint8_t* model_ok;         // [pairs][nhyp_cap][10] 1 where models[...] holds a solution
+    // phased five-point solver work space (ransac.cu)
+    double* fp_setup;          // [86][pairs*nhyp_cap] element-major FivePointSetup
+    uint8_t* fp_ok;            // [pairs*nhyp_cap] setup succeeded
+    unsigned int* cand_count;  // [1] number of root brackets in the compact list
+    int* cand_gid;             // [cand_cap] pair*nhyp_cap + hypothesis
+    int* cand_tag;             // [cand_cap] solution index | reversed << 8
+    double* cand_a; double* cand_b;   // [cand_cap] bracket
+    int cand_cap;
     int nhyp_cap;
     int kp_cap;
 };

@@ -125,6 +125,156 @@ GEOM_HD inline int real_roots_unit(const double* c, int deg, double* roots) {
     return nprev;
 }
 
+// Sturm-sequence isolation of the simple real roots of c[0..deg] in (-1, 1], ascending.
+// p0 = p, p1 = p', p_{k-1} = (a_k x + b_k) p_k - p_{k+1}; every remainder is rescaled by a positive
+// factor s_k (sign counts are unaffected).  The chain is evaluated by its three-term recurrence
+// (46 FMAs per point for degree 10).  Returns -1 when a degree drops by more than one (leading
+// coefficient of a remainder ~ 0): the caller then falls back to real_roots_unit.
+template <int MAXDEG>
+struct SturmChain {
+    double a[MAXDEG + 1], b[MAXDEG + 1], s[MAXDEG + 1];
+    double dp[MAXDEG + 1];           // p'
+    const double* p;
+    int n;                            // degree of p; chain has n+1 members
+
+    GEOM_HD int build(const double* c, int deg) {
+        p = c; n = deg;
+        double f[MAXDEG + 1], g[MAXDEG + 1];
+        for (int i = 0; i <= deg; ++i) f[i] = c[i];
+        for (int i = 0; i < deg; ++i) { dp[i] = c[i + 1] * (double)(i + 1); g[i] = dp[i]; }
+        int m = deg;                  // deg f = m, deg g = m-1
+        for (int k = 1; k < deg; ++k, --m) {
+            const double lead = g[m - 1];
+            double gmax = 0.0;
+            for (int i = 0; i < m; ++i) gmax = fmax(gmax, fabs(g[i]));
+            if (!(fabs(lead) > 1e-13 * gmax) || !(gmax > 0.0)) return -1;
+            const double inv = 1.0 / lead;
+            const double ak = f[m] * inv;
+            const double bk = (f[m - 1] - ak * ((m >= 2) ? g[m - 2] : 0.0)) * inv;
+            // r = f - (ak x + bk) g  (degree <= m-2);  p_{k+1} = -r * s
+            double rmax = 0.0;
+            for (int i = 0; i <= m - 2; ++i) {
+                const double gi1 = (i >= 1) ? g[i - 1] : 0.0;
+                const double r = f[i] - ak * gi1 - bk * g[i];
+                f[i] = -r;                                     // reuse f as the new remainder
+                rmax = fmax(rmax, fabs(r));
+            }
+            if (!(rmax > 0.0)) return -1;                      // exact common factor (multiple root)
+            const double sk = 1.0 / rmax;
+            a[k] = ak; b[k] = bk; s[k] = sk;
+            // rotate: f <- g, g <- scaled remainder
+            for (int i = 0; i <= m - 2; ++i) { const double t = f[i] * sk; f[i] = g[i]; g[i] = t; }
+            f[m - 1] = g[m - 1];      // g had m coefficients (0..m-1); slot m-1 was not overwritten above
+        }
+        return 0;
+    }
+
+    // number of sign changes of the chain at x
+    GEOM_HD int changes(double x) const {
+        double v0 = p[n], v1 = dp[n - 1];
+        for (int i = n - 1; i >= 0; --i) v0 = v0 * x + p[i];
+        for (int i = n - 2; i >= 0; --i) v1 = v1 * x + dp[i];
+        int cnt = 0;
+        int last = (v0 > 0.0) - (v0 < 0.0);
+        int sg = (v1 > 0.0) - (v1 < 0.0);
+        if (sg != 0) { if (last != 0 && sg != last) ++cnt; last = sg; }
+        for (int k = 1; k < n; ++k) {
+            const double v2 = s[k] * ((a[k] * x + b[k]) * v1 - v0);
+            v0 = v1; v1 = v2;
+            sg = (v2 > 0.0) - (v2 < 0.0);
+            if (sg != 0) { if (last != 0 && sg != last) ++cnt; last = sg; }
+        }
+        return cnt;
+    }
+};
+
+// Newton inside a sign-changing bracket, bisection when unsafe; stops as soon as the step is small
+// enough that one more Newton step reaches working precision (quadratic convergence).
+GEOM_HD inline double bracket_root_fast(const double* c, int deg, double a, double b, double fa) {
+    double x = 0.5 * (a + b);
+    for (int it = 0; it < 64; ++it) {
+        double f, df;
+        horner2(c, deg, x, f, df);
+        if (f == 0.0) return x;
+        if ((f < 0.0) == (fa < 0.0)) a = x; else b = x;
+        double xn = x - f / df;
+        const bool newton_ok = (xn > a && xn < b);
+        if (!newton_ok) xn = 0.5 * (a + b);
+        const double step = fabs(xn - x);
+        x = xn;
+        if (newton_ok && step < 1e-6 * (fabs(x) + 1e-3)) {      // next step ~ step^2: polish once and stop
+            horner2(c, deg, x, f, df);
+            const double x2 = x - f / df;
+            return (x2 > a && x2 < b) ? x2 : x;
+        }
+        if (b - a <= 4e-16 * fabs(x) + 1e-300) return x;
+    }
+    return x;
+}
+
+// Brackets (lo, hi] that each contain exactly one simple real root of c in (-1, 1], ascending.
+// lo == hi marks a root that is already known exactly (end point, unresolved cluster, or the
+// derivative-chain fallback, which returns refined roots).
+template <int MAXDEG>
+GEOM_HD inline int real_root_brackets(const double* c, int deg, double* lo, double* hi) {
+    while (deg > 0 && c[deg] == 0.0) --deg;
+    if (deg <= 0) return 0;
+    if (deg == 1) { const double r = -c[0] / c[1]; if (r > -1.0 && r <= 1.0) { lo[0] = hi[0] = r; return 1; } return 0; }
+    SturmChain<MAXDEG> ch;
+    bool ok = (ch.build(c, deg) == 0);
+    double sa[26], sb[26];
+    signed char va[26], vb[26];
+    int top = 0, nr = 0;
+    if (ok) {
+        sa[0] = -1.0; sb[0] = 1.0; va[0] = (signed char)ch.changes(-1.0); vb[0] = (signed char)ch.changes(1.0);
+        // parity check: the root count in (-1,1] is odd iff p changes sign between the ends.  A
+        // numerically unreliable chain (near-multiple roots: last members ~ 0) fails it -> fallback.
+        const double fm = horner(c, deg, -1.0), fp = horner(c, deg, 1.0);
+        const int k = va[0] - vb[0];
+        const bool odd = (fm < 0.0) != (fp < 0.0);
+        if (k < 0 || fm == 0.0 || fp == 0.0 || ((k & 1) != 0) != odd) ok = false;
+        top = 1;
+    }
+    if (!ok) {
+        // Unreliable chain (near-multiple roots): the derivative-chain method is exact but slow and
+        // divergent.  (A fixed-grid sign scan was tried as a warp-uniform fallback: it loses the
+        // close root pairs in up to 8 % of the hypotheses of a small scene -- rejected.)
+        double r[MAXDEG];
+        const int n = real_roots_unit<MAXDEG>(c, deg, r);
+        for (int i = 0; i < n; ++i) lo[i] = hi[i] = r[i];
+        return n;
+    }
+    // depth-first interval splitting; left interval first so the roots come out ascending
+    while (top > 0 && nr < MAXDEG) {
+        --top;
+        const double a = sa[top], b = sb[top];
+        const int ca = va[top], cb = vb[top];
+        const int k = ca - cb;
+        if (k <= 0) continue;
+        if (k == 1) {
+            const double fa = horner(c, deg, a), fb = horner(c, deg, b);
+            if (fb == 0.0) { lo[nr] = hi[nr] = b; ++nr; continue; }
+            if (fa != 0.0 && (fa < 0.0) != (fb < 0.0)) { lo[nr] = a; hi[nr] = b; ++nr; continue; }
+            // fa == 0 (root sits on the open end) or inconsistent signs: split further
+        }
+        if (b - a < 5e-7 || top + 2 > 26) { lo[nr] = hi[nr] = 0.5 * (a + b); ++nr; continue; }   // unresolved cluster: report once
+        const double m = 0.5 * (a + b);
+        const int cm = ch.changes(m);
+        sa[top] = m; sb[top] = b; va[top] = (signed char)cm; vb[top] = (signed char)cb; ++top;        // right half (popped second)
+        sa[top] = a; sb[top] = m; va[top] = (signed char)ca; vb[top] = (signed char)cm; ++top;        // left half (popped first)
+    }
+    return nr;
+}
+
+template <int MAXDEG>
+GEOM_HD inline int real_roots_sturm(const double* c, int deg, double* roots) {
+    double lo[MAXDEG], hi[MAXDEG];
+    const int n = real_root_brackets<MAXDEG>(c, deg, lo, hi);
+    for (int i = 0; i < n; ++i)
+        roots[i] = (lo[i] == hi[i]) ? lo[i] : bracket_root_fast(c, deg, lo[i], hi[i], horner(c, deg, lo[i]));
+    return n;
+}
+
 // ----------------------------------------------------------------------------- five-point
 // lin x lin -> quad index, quad x lin -> cubic column (Nister's column order:
 // x3 y3 x2y xy2 x2z x2 y2z y2 xyz xy | xz2 xz x yz2 yz y z3 z2 z 1)
@@ -138,16 +288,55 @@ GEOM_HD inline int cidx(int q, int l) {
     return t[q][l];
 }
 
-// out(10) += s * a(4) * b(4)
+// out(10) += s * a(4) * b(4)      (fully unrolled: every index is a compile-time constant)
+// a, b: linear polynomials stored with stride 9 (column k of the 4x9 null-space basis)
 GEOM_HD inline void lin_mul_acc(const double* a, const double* b, double s, double* out) {
-    for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) out[qidx(i, j)] += s * a[i] * b[j];
+    double bb[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; ++j) bb[j] = b[9 * j];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 4; ++i) {
+        const double sa = s * a[9 * i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; ++j) out[qidx(i, j)] += sa * bb[j];
+    }
 }
-// out(20) += s * q(10) * l(4)
-GEOM_HD inline void quad_mul_acc(const double* q, const double* l, double s, double* out) {
-    for (int i = 0; i < 10; ++i)
-        for (int j = 0; j < 4; ++j) out[cidx(i, j)] += s * q[i] * l[j];
+// out(20) += q(10) * l(4)
+GEOM_HD inline void quad_mul_acc(const double* q, const double* l, double* out) {
+    double ll[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; ++j) ll[j] = l[9 * j];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 10; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; ++j) out[cidx(i, j)] += q[i] * ll[j];
+    }
 }
+
+// Storage policies for the 10x20 constraint matrix.  The product keeps it in SHARED memory,
+// element-major / thread-minor (conflict-free, and the only way the working set stays on chip:
+// 1600 B per hypothesis); the host test build uses a plain array.
+struct LocalMat {
+    double m[200];
+    GEOM_HD double& operator()(int i, int j) { return m[i * 20 + j]; }
+};
+struct StridedMat {
+    double* base;      // &smem[thread]
+    int stride;        // threads per CTA
+    GEOM_HD double& operator()(int i, int j) { return base[(i * 20 + j) * stride]; }
+};
 
 // Orthonormal basis (4 x 9) of the null space of the 5x9 epipolar system.
 GEOM_HD inline void null_space_5x9(double A[5][9], double N[4][9]) {
@@ -197,145 +386,211 @@ GEOM_HD inline void null_space_5x9(double A[5][9], double N[4][9]) {
         }
 }
 
-// Gauss-Newton refinement of one root (x, y, z) on the ten ORIGINAL cubic constraints: removes the
-// digits lost in the elimination / degree-10 expansion.  Accepted only if the residual shrinks.
-GEOM_HD inline double cubic_residuals(const double M0[10][20], double x, double y, double z, double* r, double (*J)[3]) {
-    const double x2 = x * x, y2 = y * y, z2 = z * z;
-    const double m[20] = {x2 * x, y2 * y, x2 * y, x * y2, x2 * z, x2, y2 * z, y2, x * y * z, x * y,
-                          x * z2, x * z, x, y * z2, y * z, y, z2 * z, z2, z, 1.0};
-    const double dx[20] = {3 * x2, 0, 2 * x * y, y2, 2 * x * z, 2 * x, 0, 0, y * z, y, z2, z, 1, 0, 0, 0, 0, 0, 0, 0};
-    const double dy[20] = {0, 3 * y2, x2, 2 * x * y, 0, 0, 2 * y * z, 2 * y, x * z, x, 0, 0, 0, z2, z, 1, 0, 0, 0, 0};
-    const double dz[20] = {0, 0, 0, 0, x2, 0, y2, 0, x * y, 0, 2 * x * z, x, 0, 2 * y * z, y, 0, 3 * z2, 2 * z, 1, 0};
-    double ss = 0.0;
-    for (int i = 0; i < 10; ++i) {
-        double a = 0.0, b = 0.0, c = 0.0, d = 0.0;
-        for (int j = 0; j < 20; ++j) {
-            const double w = M0[i][j];
-            a += w * m[j];
-            if (J) { b += w * dx[j]; c += w * dy[j]; d += w * dz[j]; }
-        }
-        r[i] = a;
-        ss += a * a;
-        if (J) { J[i][0] = b; J[i][1] = c; J[i][2] = d; }
-    }
-    return ss;
+// Residuals of the ten cubic constraints at a numeric E, r[0] = det E, r[1..9] = (E E^T - 1/2 tr I) E.
+// With D != nullptr also the directional derivative dr along dE = D (all 3x3 row-major).
+GEOM_HD inline void essential_residuals(const double* E, double* r) {
+    double G[9];                      // Lambda = E E^T - 1/2 tr(E E^T) I
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) G[i * 3 + j] = E[i * 3] * E[j * 3] + E[i * 3 + 1] * E[j * 3 + 1] + E[i * 3 + 2] * E[j * 3 + 2];
+    const double ht = 0.5 * (G[0] + G[4] + G[8]);
+    G[0] -= ht; G[4] -= ht; G[8] -= ht;
+    r[0] = E[0] * (E[4] * E[8] - E[5] * E[7]) - E[1] * (E[3] * E[8] - E[5] * E[6]) + E[2] * (E[3] * E[7] - E[4] * E[6]);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r[1 + i * 3 + j] = G[i * 3] * E[j] + G[i * 3 + 1] * E[3 + j] + G[i * 3 + 2] * E[6 + j];
 }
 
-GEOM_HD inline void polish_xyz(const double M0[10][20], double& x, double& y, double& z) {
-    if (!(fabs(x) < 1e3 && fabs(y) < 1e3 && fabs(z) < 1e3)) return;
-    double r[10], J[10][3];
-    double ss = cubic_residuals(M0, x, y, z, r, J);
-    for (int it = 0; it < 3; ++it) {
+GEOM_HD inline void essential_residual_derivative(const double* E, const double* D, double* dr) {
+    // d det = sum cof(E)_ij D_ij
+    const double c0 = E[4] * E[8] - E[5] * E[7], c1 = E[5] * E[6] - E[3] * E[8], c2 = E[3] * E[7] - E[4] * E[6];
+    const double c3 = E[2] * E[7] - E[1] * E[8], c4 = E[0] * E[8] - E[2] * E[6], c5 = E[1] * E[6] - E[0] * E[7];
+    const double c6 = E[1] * E[5] - E[2] * E[4], c7 = E[2] * E[3] - E[0] * E[5], c8 = E[0] * E[4] - E[1] * E[3];
+    dr[0] = c0 * D[0] + c1 * D[1] + c2 * D[2] + c3 * D[3] + c4 * D[4] + c5 * D[5] + c6 * D[6] + c7 * D[7] + c8 * D[8];
+    // d[(EE^T - 1/2 tr I)E] = (D E^T + E D^T - tr(E D^T) I) E + (E E^T - 1/2 tr(EE^T) I) D
+    double S[9], G[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            S[i * 3 + j] = D[i * 3] * E[j * 3] + D[i * 3 + 1] * E[j * 3 + 1] + D[i * 3 + 2] * E[j * 3 + 2] +
+                           E[i * 3] * D[j * 3] + E[i * 3 + 1] * D[j * 3 + 1] + E[i * 3 + 2] * D[j * 3 + 2];
+            G[i * 3 + j] = E[i * 3] * E[j * 3] + E[i * 3 + 1] * E[j * 3 + 1] + E[i * 3 + 2] * E[j * 3 + 2];
+        }
+    const double hs = 0.5 * (S[0] + S[4] + S[8]);      // tr(E D^T) = 1/2 tr(S)
+    S[0] -= hs; S[4] -= hs; S[8] -= hs;
+    const double ht = 0.5 * (G[0] + G[4] + G[8]);
+    G[0] -= ht; G[4] -= ht; G[8] -= ht;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            dr[1 + i * 3 + j] = S[i * 3] * E[j] + S[i * 3 + 1] * E[3 + j] + S[i * 3 + 2] * E[6 + j] +
+                                G[i * 3] * D[j] + G[i * 3 + 1] * D[3 + j] + G[i * 3 + 2] * D[6 + j];
+}
+
+// Gauss-Newton refinement of one root on the ten ORIGINAL cubic constraints, evaluated at
+// E = u0 N0 + u1 N1 + u2 N2 + u3 N3.  The root arrives as u = (x, y, z, 1); the component of
+// largest magnitude is fixed to 1 and the other three are refined, so the iteration is well scaled
+// for roots near infinity too (|z| >> 1 comes from the reversed polynomial).  This removes the
+// digits lost in the elimination / degree-10 expansion.  A step is accepted only if the residual
+// shrinks; at most 4 steps, stopping at |r| ~ 1e-13.
+GEOM_HD inline void polish_u(const double N[4][9], double* u) {
+    int f = 3;
+    for (int i = 0; i < 3; ++i) if (fabs(u[i]) > fabs(u[f])) f = i;
+    if (!(fabs(u[f]) > 0.0) || !(fabs(u[f]) < 1e300)) return;
+    {
+        const double inv = 1.0 / u[f];
+        for (int i = 0; i < 4; ++i) u[i] *= inv;
+        u[f] = 1.0;
+    }
+    int fr[3];
+    { int k = 0; for (int i = 0; i < 4; ++i) if (i != f) fr[k++] = i; }
+    double E[9], r[10];
+    for (int k = 0; k < 9; ++k) E[k] = u[0] * N[0][k] + u[1] * N[1][k] + u[2] * N[2][k] + u[3] * N[3][k];
+    essential_residuals(E, r);
+    double ss = 0.0;
+    for (int i = 0; i < 10; ++i) ss += r[i] * r[i];
+    for (int it = 0; it < 4; ++it) {
+        if (ss < 1e-26) return;           // |r| ~ 1e-13: already at working precision
+        double J[3][10];
+        for (int d = 0; d < 3; ++d) essential_residual_derivative(E, N[fr[d]], J[d]);
         // normal equations (3x3, symmetric) solved by Cramer's rule
         double A[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
         for (int i = 0; i < 10; ++i) {
-            A[0] += J[i][0] * J[i][0]; A[1] += J[i][0] * J[i][1]; A[2] += J[i][0] * J[i][2];
-            A[3] += J[i][1] * J[i][1]; A[4] += J[i][1] * J[i][2]; A[5] += J[i][2] * J[i][2];
-            g[0] += J[i][0] * r[i]; g[1] += J[i][1] * r[i]; g[2] += J[i][2] * r[i];
+            A[0] += J[0][i] * J[0][i]; A[1] += J[0][i] * J[1][i]; A[2] += J[0][i] * J[2][i];
+            A[3] += J[1][i] * J[1][i]; A[4] += J[1][i] * J[2][i]; A[5] += J[2][i] * J[2][i];
+            g[0] += J[0][i] * r[i]; g[1] += J[1][i] * r[i]; g[2] += J[2][i] * r[i];
         }
         const double c00 = A[3] * A[5] - A[4] * A[4], c01 = A[2] * A[4] - A[1] * A[5], c02 = A[1] * A[4] - A[2] * A[3];
         const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
         if (!(fabs(det) > 0.0)) return;
         const double c11 = A[0] * A[5] - A[2] * A[2], c12 = A[1] * A[2] - A[0] * A[4], c22 = A[0] * A[3] - A[1] * A[1];
         const double inv = 1.0 / det;
-        const double sx = -(c00 * g[0] + c01 * g[1] + c02 * g[2]) * inv;
-        const double sy = -(c01 * g[0] + c11 * g[1] + c12 * g[2]) * inv;
-        const double sz = -(c02 * g[0] + c12 * g[1] + c22 * g[2]) * inv;
-        const double nx = x + sx, ny = y + sy, nz = z + sz;
-        const double ns = cubic_residuals(M0, nx, ny, nz, r, J);
+        double un[4];
+        for (int i = 0; i < 4; ++i) un[i] = u[i];
+        un[fr[0]] -= (c00 * g[0] + c01 * g[1] + c02 * g[2]) * inv;
+        un[fr[1]] -= (c01 * g[0] + c11 * g[1] + c12 * g[2]) * inv;
+        un[fr[2]] -= (c02 * g[0] + c12 * g[1] + c22 * g[2]) * inv;
+        double En[9], rn[10];
+        for (int k = 0; k < 9; ++k) En[k] = un[0] * N[0][k] + un[1] * N[1][k] + un[2] * N[2][k] + un[3] * N[3][k];
+        essential_residuals(En, rn);
+        double ns = 0.0;
+        for (int i = 0; i < 10; ++i) ns += rn[i] * rn[i];
         if (!(ns < ss)) return;           // no improvement (or NaN): keep the current root
-        x = nx; y = ny; z = nz;
-        if (ns < 1e-30 || ss - ns < 1e-3 * ss) return;   // converged to working precision
+        for (int i = 0; i < 4; ++i) u[i] = un[i];
+        for (int k = 0; k < 9; ++k) E[k] = En[k];
+        for (int i = 0; i < 10; ++i) r[i] = rn[i];
+        if (ss - ns < 1e-3 * ss) return;  // stalled
         ss = ns;
     }
 }
 
-// x1, x2: 5 normalised correspondences (x2^T E x1 = 0).  E: up to 10 row-major 3x3, |E|_F = 1.
-GEOM_HD inline int five_point(const double x1[5][2], const double x2[5][2], double E[][9]) {
-    double A[5][9], N[4][9];
-    for (int i = 0; i < 5; ++i) {
-        const double a = x1[i][0], b = x1[i][1], c = x2[i][0], d = x2[i][1];
-        A[i][0] = c * a; A[i][1] = c * b; A[i][2] = c;
-        A[i][3] = d * a; A[i][4] = d * b; A[i][5] = d;
-        A[i][6] = a;     A[i][7] = b;     A[i][8] = 1.0;
-    }
-    null_space_5x9(A, N);
-    // e[r*3+c] = linear polynomial (x, y, z, 1) of entry (r,c)
-    double e[9][4];
-    for (int k = 0; k < 9; ++k)
-        for (int v = 0; v < 4; ++v) e[k][v] = N[v][k];
+// One scaled row of the constraint matrix -> storage
+template <class Mat>
+GEOM_HD inline void store_row(Mat& M, int row, const double* acc) {
+    double mx = 0.0;
+    for (int j = 0; j < 20; ++j) mx = fmax(mx, fabs(acc[j]));
+    const double inv = (mx > 0.0) ? 1.0 / mx : 1.0;     // row equilibration: pure scaling
+    for (int j = 0; j < 20; ++j) M(row, j) = acc[j] * inv;
+}
 
-    double M[10][20];
-    for (int i = 0; i < 10; ++i)
-        for (int j = 0; j < 20; ++j) M[i][j] = 0.0;
-    // det E
+// ---- the solver in three phases (so the GPU can re-pack work between them, see ransac.cu) ----
+// setup   : per hypothesis -- null space, constraint matrix, elimination, B(z), det B(z)
+// isolate : per hypothesis -- brackets (a,b] each holding one real root of p or of the reversed p
+// finish  : per bracket    -- refine the root, back-substitute x,y, polish, normalise E
+struct FivePointSetup {          // 86 doubles, kept flat so it can be stored element-major
+    double N[4][9];              // null-space basis: E = x N0 + y N1 + z N2 + N3
+    double Bx[3][4], By[3][4], B1[3][5];   // B(z), ascending powers of z
+    double c[11];                // det B(z), normalised to max |c| = 1
+};
+constexpr int kSetupDoubles = 86;
+
+struct RootBracket {
+    double a, b;                 // one root in (a, b]; a == b: already refined
+    int reversed;                // 1: root w of the reversed polynomial, z = 1/w
+};
+
+template <class Mat>
+GEOM_HD inline bool five_point_setup(const double x1[5][2], const double x2[5][2], Mat& M, FivePointSetup& S) {
+    double (*N)[9] = S.N;
     {
-        const int perm[3][3] = {{0, 1, 2}, {1, 2, 0}, {2, 0, 1}};
+        double A[5][9];
+        for (int i = 0; i < 5; ++i) {
+            const double a = x1[i][0], b = x1[i][1], c = x2[i][0], d = x2[i][1];
+            A[i][0] = c * a; A[i][1] = c * b; A[i][2] = c;
+            A[i][3] = d * a; A[i][4] = d * b; A[i][5] = d;
+            A[i][6] = a;     A[i][7] = b;     A[i][8] = 1.0;
+        }
+        null_space_5x9(A, N);
+    }
+    // e(k) = linear polynomial (x, y, z, 1) of entry k = r*3+c = column k of N (stride 9)
+    const double* e0 = &N[0][0];
+#define E_(k) (e0 + (k))
+    // row 0: det E
+    {
+        double acc[20];
+        for (int j = 0; j < 20; ++j) acc[j] = 0.0;
         for (int p = 0; p < 3; ++p) {
-            const int a = perm[p][0], b = perm[p][1], c = perm[p][2];
+            const int a = p, b = (p + 1) % 3, c = (p + 2) % 3;
             double q[10];
             for (int i = 0; i < 10; ++i) q[i] = 0.0;
-            lin_mul_acc(e[3 + b], e[6 + c], 1.0, q);       // e1b * e2c
-            lin_mul_acc(e[3 + c], e[6 + b], -1.0, q);      // - e1c * e2b
-            quad_mul_acc(q, e[a], 1.0, M[0]);
+            lin_mul_acc(E_(3 + b), E_(6 + c), 1.0, q);       // e1b * e2c
+            lin_mul_acc(E_(3 + c), E_(6 + b), -1.0, q);      // - e1c * e2b
+            quad_mul_acc(q, E_(a), acc);
+        }
+        store_row(M, 0, acc);
+    }
+    // rows 1..9: (E E^T - 1/2 tr(E E^T) I) E, one row of Lambda at a time
+    {
+        double tr[10];
+        for (int i = 0; i < 10; ++i) tr[i] = 0.0;
+        for (int k = 0; k < 9; ++k) lin_mul_acc(E_(k), E_(k), 0.5, tr);
+        for (int r = 0; r < 3; ++r) {
+            double L[3][10];
+            for (int k = 0; k < 3; ++k) {
+                for (int i = 0; i < 10; ++i) L[k][i] = (k == r) ? -tr[i] : 0.0;
+                for (int m = 0; m < 3; ++m) lin_mul_acc(E_(r * 3 + m), E_(k * 3 + m), 1.0, L[k]);
+            }
+            for (int c = 0; c < 3; ++c) {
+                double acc[20];
+                for (int j = 0; j < 20; ++j) acc[j] = 0.0;
+                for (int k = 0; k < 3; ++k) quad_mul_acc(L[k], E_(k * 3 + c), acc);
+                store_row(M, 1 + r * 3 + c, acc);
+            }
         }
     }
-    // Lambda = E E^T - 1/2 tr(E E^T) I ;  rows 1..9 = Lambda E
-    {
-        double L[3][3][10];
-        for (int r = 0; r < 3; ++r)
-            for (int c = r; c < 3; ++c) {
-                for (int i = 0; i < 10; ++i) L[r][c][i] = 0.0;
-                for (int k = 0; k < 3; ++k) lin_mul_acc(e[r * 3 + k], e[c * 3 + k], 1.0, L[r][c]);
-            }
-        double tr[10];
-        for (int i = 0; i < 10; ++i) tr[i] = 0.5 * (L[0][0][i] + L[1][1][i] + L[2][2][i]);
-        for (int r = 0; r < 3; ++r)
-            for (int i = 0; i < 10; ++i) L[r][r][i] -= tr[i];
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < r; ++c)
-                for (int i = 0; i < 10; ++i) L[r][c][i] = L[c][r][i];
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c)
-                for (int k = 0; k < 3; ++k) quad_mul_acc(L[r][k], e[k * 3 + c], 1.0, M[1 + r * 3 + c]);
-    }
-    double M0[10][20];
-    for (int i = 0; i < 10; ++i) {
-        // equilibrate rows (pure scaling: the solution set is unchanged)
-        double mx = 0.0;
-        for (int j = 0; j < 20; ++j) mx = fmax(mx, fabs(M[i][j]));
-        const double inv = (mx > 0.0) ? 1.0 / mx : 1.0;
-        for (int j = 0; j < 20; ++j) { M[i][j] *= inv; M0[i][j] = M[i][j]; }
-    }
-    // Gauss-Jordan on the first 10 columns, partial pivoting
+#undef E_
+    // Gaussian elimination with partial pivoting, reduced only where it is read later: the right
+    // block (columns 10..19) completely, the left block only to the right of the pivot.
     for (int col = 0; col < 10; ++col) {
         int pr = col;
-        double best = fabs(M[col][col]);
-        for (int i = col + 1; i < 10; ++i)
-            if (fabs(M[i][col]) > best) { best = fabs(M[i][col]); pr = i; }
-        if (best < 1e-300) return 0;
+        double best = fabs(M(col, col));
+        for (int i = col + 1; i < 10; ++i) {
+            const double v = fabs(M(i, col));
+            if (v > best) { best = v; pr = i; }
+        }
+        if (best < 1e-300) return false;
+        double prow[20];
+        const double inv = 1.0 / M(pr, col);
+        for (int j = 0; j < 20; ++j) prow[j] = M(pr, j) * inv;
         if (pr != col)
-            for (int j = col; j < 20; ++j) { const double t = M[col][j]; M[col][j] = M[pr][j]; M[pr][j] = t; }
-        const double inv = 1.0 / M[col][col];
-        for (int j = col; j < 20; ++j) M[col][j] *= inv;
+            for (int j = 0; j < 20; ++j) M(pr, j) = M(col, j);
+        for (int j = 0; j < 20; ++j) M(col, j) = prow[j];
         for (int i = 0; i < 10; ++i) {
             if (i == col) continue;
-            const double f = M[i][col];
-            if (f != 0.0)
-                for (int j = col; j < 20; ++j) M[i][j] -= f * M[col][j];
+            const double f = M(i, col);
+            for (int j = col + 1; j < 10; ++j) M(i, j) -= f * prow[j];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+            for (int j = 10; j < 20; ++j) M(i, j) -= f * prow[j];
         }
     }
     // B(z): rows k = e - z f, l = g - z h, m = i - z j ; entries ascending in z
-    double Bx[3][4], By[3][4], B1[3][5];
     for (int r = 0; r < 3; ++r) {
-        const double* be = &M[4 + 2 * r][10];
-        const double* bf = &M[5 + 2 * r][10];
-        Bx[r][3] = -bf[0]; Bx[r][2] = be[0] - bf[1]; Bx[r][1] = be[1] - bf[2]; Bx[r][0] = be[2];
-        By[r][3] = -bf[3]; By[r][2] = be[3] - bf[4]; By[r][1] = be[4] - bf[5]; By[r][0] = be[5];
-        B1[r][4] = -bf[6]; B1[r][3] = be[6] - bf[7]; B1[r][2] = be[7] - bf[8]; B1[r][1] = be[8] - bf[9]; B1[r][0] = be[9];
+        double be[10], bf[10];
+        for (int j = 0; j < 10; ++j) { be[j] = M(4 + 2 * r, 10 + j); bf[j] = M(5 + 2 * r, 10 + j); }
+        S.Bx[r][3] = -bf[0]; S.Bx[r][2] = be[0] - bf[1]; S.Bx[r][1] = be[1] - bf[2]; S.Bx[r][0] = be[2];
+        S.By[r][3] = -bf[3]; S.By[r][2] = be[3] - bf[4]; S.By[r][1] = be[4] - bf[5]; S.By[r][0] = be[5];
+        S.B1[r][4] = -bf[6]; S.B1[r][3] = be[6] - bf[7]; S.B1[r][2] = be[7] - bf[8]; S.B1[r][1] = be[8] - bf[9]; S.B1[r][0] = be[9];
     }
     // det B(z), expansion along the third column
-    double c[11];
+    double* c = S.c;
     for (int i = 0; i < 11; ++i) c[i] = 0.0;
     {
         const int rows[3][2] = {{1, 2}, {0, 2}, {0, 1}};
@@ -344,64 +599,101 @@ GEOM_HD inline int five_point(const double x1[5][2], const double x2[5][2], doub
             double mnr[7];
             for (int i = 0; i < 7; ++i) mnr[i] = 0.0;
             for (int i = 0; i < 4; ++i)
-                for (int j = 0; j < 4; ++j) mnr[i + j] += Bx[p][i] * By[q][j] - By[p][i] * Bx[q][j];
+                for (int j = 0; j < 4; ++j) mnr[i + j] += S.Bx[p][i] * S.By[q][j] - S.By[p][i] * S.Bx[q][j];
             const double sgn = (r == 1) ? -1.0 : 1.0;
             for (int i = 0; i < 7; ++i)
-                for (int j = 0; j < 5; ++j) c[i + j] += sgn * mnr[i] * B1[r][j];
+                for (int j = 0; j < 5; ++j) c[i + j] += sgn * mnr[i] * S.B1[r][j];
         }
     }
     double cmax = 0.0;
     for (int i = 0; i < 11; ++i) cmax = fmax(cmax, fabs(c[i]));
-    if (!(cmax > 0.0) || !(cmax < 1e300)) return 0;
-    double crev[11];
-    for (int i = 0; i < 11; ++i) { c[i] /= cmax; }
-    for (int i = 0; i < 11; ++i) crev[i] = c[10 - i];
+    if (!(cmax > 0.0) || !(cmax < 1e300)) return false;
+    const double cinv = 1.0 / cmax;
+    for (int i = 0; i < 11; ++i) c[i] *= cinv;
+    return true;
+}
 
-    double zr[20];
-    int nz = real_roots_unit<10>(c, 10, zr);
+// Brackets of the real roots: first those of p in (-1,1] ascending, then those of the reversed
+// polynomial (|z| > 1) ascending in w = 1/z.  At most 10 are returned.
+GEOM_HD inline int five_point_isolate(const double* c, RootBracket* br) {
+    int n = 0;
+    for (int pass = 0; pass < 2 && n < 10; ++pass) {
+        double cc[11];
+        for (int i = 0; i < 11; ++i) cc[i] = pass ? c[10 - i] : c[i];
+        double lo[10], hi[10];
+        const int k = real_root_brackets<10>(cc, 10, lo, hi);
+        for (int i = 0; i < k && n < 10; ++i) {
+            if (pass) {      // keep 0 < |w| < 1 only (w = 0 is z = infinity; |w| = 1 belongs to pass 0)
+                if (lo[i] == hi[i] && !(fabs(lo[i]) > 1e-12 && fabs(lo[i]) < 1.0)) continue;
+                if (hi[i] <= -1.0 || lo[i] >= 1.0) continue;
+            }
+            br[n].a = lo[i]; br[n].b = hi[i]; br[n].reversed = pass;
+            ++n;
+        }
+    }
+    return n;
+}
+
+// One bracket -> one essential matrix (|E|_F = 1).  false: no valid solution from this root.
+GEOM_HD inline bool five_point_finish(const FivePointSetup& S, const RootBracket& br, double* Es) {
+    double z;
     {
-        double wr[10];
-        const int nw = real_roots_unit<10>(crev, 10, wr);
-        for (int i = 0; i < nw; ++i)
-            if (fabs(wr[i]) > 1e-12 && fabs(wr[i]) < 1.0) zr[nz++] = 1.0 / wr[i];
+        double cc[11];
+        for (int i = 0; i < 11; ++i) cc[i] = br.reversed ? S.c[10 - i] : S.c[i];
+        double w = br.a;
+        if (br.a != br.b) w = bracket_root_fast(cc, 10, br.a, br.b, horner(cc, 10, br.a));
+        if (br.reversed) {
+            if (!(fabs(w) > 1e-12 && fabs(w) < 1.0)) return false;
+            z = 1.0 / w;
+        } else {
+            z = w;
+        }
     }
+    double b[3][3];
+    for (int r = 0; r < 3; ++r) {
+        b[r][0] = horner(S.Bx[r], 3, z);
+        b[r][1] = horner(S.By[r], 3, z);
+        b[r][2] = horner(S.B1[r], 4, z);
+    }
+    // null vector of B(z): best-conditioned cross product of two rows
+    double nbest[3] = {0, 0, 0}, nn = -1.0;
+    const int pr[3][2] = {{0, 1}, {0, 2}, {1, 2}};
+    for (int k = 0; k < 3; ++k) {
+        const double* u = b[pr[k][0]];
+        const double* v = b[pr[k][1]];
+        // scale rows so the comparison is not dominated by one large row
+        const double su = fabs(u[0]) + fabs(u[1]) + fabs(u[2]), sv = fabs(v[0]) + fabs(v[1]) + fabs(v[2]);
+        if (!(su > 0.0) || !(sv > 0.0)) continue;
+        const double cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
+        const double q = (cx * cx + cy * cy + cz * cz) / (su * su * sv * sv);
+        if (q > nn) { nn = q; nbest[0] = cx; nbest[1] = cy; nbest[2] = cz; }
+    }
+    const double nrm = sqrt(nbest[0] * nbest[0] + nbest[1] * nbest[1] + nbest[2] * nbest[2]);
+    if (!(nrm > 0.0) || fabs(nbest[2]) < 1e-10 * nrm) return false;
+    double u[4] = {nbest[0] / nbest[2], nbest[1] / nbest[2], z, 1.0};
+    polish_u(S.N, u);
+    double fn = 0.0;
+    for (int k = 0; k < 9; ++k) {
+        const double v = u[0] * S.N[0][k] + u[1] * S.N[1][k] + u[2] * S.N[2][k] + u[3] * S.N[3][k];
+        Es[k] = v;
+        fn += v * v;
+    }
+    if (!(fn > 0.0) || !(fn < 1e300)) return false;
+    const double inv = 1.0 / sqrt(fn);
+    for (int k = 0; k < 9; ++k) Es[k] *= inv;
+    return true;
+}
+
+// convenience wrapper: all three phases in one call (host tests)
+GEOM_HD inline int five_point(const double x1[5][2], const double x2[5][2], double E[][9]) {
+    LocalMat M;
+    FivePointSetup S;
+    if (!five_point_setup(x1, x2, M, S)) return 0;
+    RootBracket br[10];
+    const int nb = five_point_isolate(S.c, br);
     int ns = 0;
-    for (int s = 0; s < nz && ns < 10; ++s) {
-        const double z = zr[s];
-        double b[3][3];
-        for (int r = 0; r < 3; ++r) {
-            b[r][0] = horner(Bx[r], 3, z);
-            b[r][1] = horner(By[r], 3, z);
-            b[r][2] = horner(B1[r], 4, z);
-        }
-        // null vector of B(z): best-conditioned cross product of two rows
-        double nbest[3] = {0, 0, 0}, nn = -1.0;
-        const int pr[3][2] = {{0, 1}, {0, 2}, {1, 2}};
-        for (int k = 0; k < 3; ++k) {
-            const double* u = b[pr[k][0]];
-            const double* v = b[pr[k][1]];
-            // scale rows so the comparison is not dominated by one large row
-            const double su = fabs(u[0]) + fabs(u[1]) + fabs(u[2]), sv = fabs(v[0]) + fabs(v[1]) + fabs(v[2]);
-            if (!(su > 0.0) || !(sv > 0.0)) continue;
-            const double cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
-            const double q = (cx * cx + cy * cy + cz * cz) / (su * su * sv * sv);
-            if (q > nn) { nn = q; nbest[0] = cx; nbest[1] = cy; nbest[2] = cz; }
-        }
-        const double nrm = sqrt(nbest[0] * nbest[0] + nbest[1] * nbest[1] + nbest[2] * nbest[2]);
-        if (!(nrm > 0.0) || fabs(nbest[2]) < 1e-10 * nrm) continue;
-        double x = nbest[0] / nbest[2], y = nbest[1] / nbest[2], zz = z;
-        polish_xyz(M0, x, y, zz);
-        double fn = 0.0;
-        for (int k = 0; k < 9; ++k) {
-            const double v = x * N[0][k] + y * N[1][k] + zz * N[2][k] + N[3][k];
-            E[ns][k] = v;
-            fn += v * v;
-        }
-        if (!(fn > 0.0) || !(fn < 1e300)) continue;
-        const double inv = 1.0 / sqrt(fn);
-        for (int k = 0; k < 9; ++k) E[ns][k] *= inv;
-        ++ns;
-    }
+    for (int i = 0; i < nb; ++i)
+        if (five_point_finish(S, br[i], E[ns])) ++ns;
     return ns;
 }
 
@@ -417,6 +709,35 @@ GEOM_HD inline bool sampson_inlier(const double* E, double x1, double y1, double
     const double den = a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1;
     const float err = (float)(num * num / den);
     return err <= thr2f;
+}
+
+// The same predicate without the division on the common path.  (float)q <= thr2f  <=>  q <= T',
+// T' = the midpoint between thr2f and the next float above it (round-to-nearest boundary), so the
+// test is num^2 <= T' * den; inside a 1e-14 relative guard band around equality the exact
+// expression (with the division and the float cast) decides, which keeps the mask identical.
+struct SampsonThreshold {
+    float thr2f;
+    double tmid;      // T'
+};
+GEOM_HD inline SampsonThreshold make_sampson_threshold(float thr2f) {
+    SampsonThreshold t;
+    t.thr2f = thr2f;
+    t.tmid = 0.5 * ((double)thr2f + (double)nextafterf(thr2f, 3.0e38f));
+    return t;
+}
+GEOM_HD inline bool sampson_inlier_fast(const double* E, double x1, double y1, double x2, double y2, const SampsonThreshold& t) {
+    const double a0 = E[0] * x1 + E[1] * y1 + E[2];
+    const double a1 = E[3] * x1 + E[4] * y1 + E[5];
+    const double a2 = E[6] * x1 + E[7] * y1 + E[8];
+    const double b0 = E[0] * x2 + E[3] * y2 + E[6];
+    const double b1 = E[1] * x2 + E[4] * y2 + E[7];
+    const double num = x2 * a0 + y2 * a1 + a2;
+    const double den = a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1;
+    const double lhs = num * num, rhs = t.tmid * den;
+    const double band = 1e-14 * rhs;
+    if (lhs < rhs - band) return true;
+    if (lhs > rhs + band) return false;
+    return (float)(lhs / den) <= t.thr2f;       // also NaN / den == 0 land here
 }
 
 // ----------------------------------------------------------------------------- small SVD

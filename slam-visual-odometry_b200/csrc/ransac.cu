@@ -18,6 +18,8 @@
 // better), realised order-independently by the packed atomicMax.
 #include "common.cuh"
 #include "geom_core.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace b200vo {
 
@@ -30,14 +32,24 @@ struct RansacArgs {
     int min_matches;            // reference kMinMatchesForPose
 };
 
-__global__ void __launch_bounds__(128)
-five_point_kernel(PairView pv, RansacArgs ra) {
+// ---- phased five-point solver -------------------------------------------------------------
+// A thread-per-hypothesis solver diverges badly: hypotheses have 0..10 real roots and every root
+// needs a data-dependent number of iterations (measured: 10 of 32 lanes active).  So the work is
+// re-packed between phases:
+//   fp_setup_kernel   thread / hypothesis : uniform algebra (null space, 10x20 elimination, det B(z))
+//   fp_isolate_kernel thread / hypothesis : Sturm isolation -> root brackets appended to a compact list
+//   fp_finish_kernel  thread / bracket    : refine root, back-substitute, polish, write E
+//   score_kernel      warp   / bracket    : Sampson inlier count, 64-bit atomicMax per pair
+// The compact list carries (pair, hypothesis, solution index), so "first arg-max wins" does not
+// depend on the order in which brackets were appended.
+__global__ void __launch_bounds__(128, 4)
+fp_setup_kernel(PairView pv, RansacArgs ra) {
     const int pair = blockIdx.y;
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= ra.nhyp) return;
+    const int gid = pair * pv.nhyp_cap + h;
     const int m = pv.n_good[pair];
-    int* nsol = pv.nsol + (size_t)pair * pv.nhyp_cap;
-    if (m < ra.min_matches || m < 5) { nsol[h] = 0; return; }
+    if (m < ra.min_matches || m < 5) { pv.fp_ok[gid] = 0; return; }
     int idx[5];
     if (ra.samples) {
 #pragma unroll
@@ -53,49 +65,127 @@ five_point_kernel(PairView pv, RansacArgs ra) {
         x1[k][0] = pv.x1x[base + i]; x1[k][1] = pv.x1y[base + i];
         x2[k][0] = pv.x2x[base + i]; x2[k][1] = pv.x2y[base + i];
     }
-    double E[10][9];
-    const int ns = geom::five_point(x1, x2, E);
-    double* out = pv.models + ((size_t)pair * pv.nhyp_cap + h) * 90;
-    for (int s = 0; s < ns; ++s)
-        for (int k = 0; k < 9; ++k) out[s * 9 + k] = E[s][k];
-    nsol[h] = ns;
+    geom::LocalMat M;
+    geom::FivePointSetup S;
+    const bool ok = geom::five_point_setup(x1, x2, M, S);
+    pv.fp_ok[gid] = ok ? 1 : 0;
+    if (!ok) return;
+    const size_t stride = (size_t)gridDim.y * pv.nhyp_cap;      // element-major over the hypotheses of this launch
+    const double* src = reinterpret_cast<const double*>(&S);
+    double* dst = pv.fp_setup + gid;
+#pragma unroll 2
+    for (int e = 0; e < geom::kSetupDoubles; ++e) dst[(size_t)e * stride] = src[e];
 }
 
-// one warp per hypothesis
+__global__ void __launch_bounds__(128)
+fp_isolate_kernel(PairView pv, RansacArgs ra) {
+    const int pair = blockIdx.y;
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= ra.nhyp) return;
+    const int gid = pair * pv.nhyp_cap + h;
+    int nb = 0;
+    geom::RootBracket br[10];
+    if (pv.fp_ok[gid]) {
+        const size_t stride = (size_t)gridDim.y * pv.nhyp_cap;
+        double c[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) c[i] = pv.fp_setup[(size_t)(75 + i) * stride + gid];     // FivePointSetup::c
+        nb = geom::five_point_isolate(c, br);
+    }
+    pv.nsol[gid] = nb;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) pv.model_ok[(size_t)gid * 10 + k] = 0;
+    if (nb == 0) return;
+    const unsigned pos = atomicAdd(pv.cand_count, (unsigned)nb);
+    for (int k = 0; k < nb; ++k) {
+        const unsigned p = pos + k;
+        if (p >= (unsigned)pv.cand_cap) break;
+        pv.cand_gid[p] = gid;
+        pv.cand_tag[p] = k | (br[k].reversed << 8);
+        pv.cand_a[p] = br[k].a;
+        pv.cand_b[p] = br[k].b;
+    }
+}
+
+__global__ void __launch_bounds__(128, 4)
+fp_finish_kernel(PairView pv, int npairs) {
+    const unsigned n = min(*pv.cand_count, (unsigned)pv.cand_cap);
+    const size_t stride = (size_t)npairs * pv.nhyp_cap;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int gid = pv.cand_gid[i];
+        const int tag = pv.cand_tag[i];
+        geom::RootBracket br;
+        br.a = pv.cand_a[i]; br.b = pv.cand_b[i]; br.reversed = tag >> 8;
+        geom::FivePointSetup S;
+        double* dst = reinterpret_cast<double*>(&S);
+        const double* src = pv.fp_setup + gid;
+#pragma unroll 2
+        for (int e = 0; e < geom::kSetupDoubles; ++e) dst[e] = src[(size_t)e * stride];
+        double E[9];
+        const bool ok = geom::five_point_finish(S, br, E);
+        const int s = tag & 0xFF;
+        if (ok) {
+            double* out = pv.models + (size_t)gid * 90 + s * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out[k] = E[k];
+        }
+        pv.model_ok[(size_t)gid * 10 + s] = ok ? 1 : 0;
+    }
+}
+
+// one warp per root bracket (model)
 __global__ void __launch_bounds__(256)
 score_kernel(PairView pv, RansacArgs ra) {
-    const int pair = blockIdx.y;
-    const int h = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const unsigned n = min(*pv.cand_count, (unsigned)pv.cand_cap);
     const int lane = threadIdx.x & 31;
-    if (h >= ra.nhyp) return;
-    const int ns = pv.nsol[(size_t)pair * pv.nhyp_cap + h];
-    if (ns == 0) return;
-    const int m = pv.n_good[pair];
-    const size_t base = (size_t)pair * pv.kp_cap;
-    const double* __restrict__ x1x = pv.x1x + base;
-    const double* __restrict__ x1y = pv.x1y + base;
-    const double* __restrict__ x2x = pv.x2x + base;
-    const double* __restrict__ x2y = pv.x2y + base;
-    const double* models = pv.models + ((size_t)pair * pv.nhyp_cap + h) * 90;
-    unsigned long long best = 0ull;
-    for (int s = 0; s < ns; ++s) {
+    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+    for (unsigned i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {
+        const int gid = pv.cand_gid[i];
+        const int s = pv.cand_tag[i] & 0xFF;
+        if (!pv.model_ok[(size_t)gid * 10 + s]) continue;
+        const int pair = gid / pv.nhyp_cap, h = gid - pair * pv.nhyp_cap;
+        const int m = pv.n_good[pair];
+        const size_t base = (size_t)pair * pv.kp_cap;
+        const double* __restrict__ x1x = pv.x1x + base;
+        const double* __restrict__ x1y = pv.x1y + base;
+        const double* __restrict__ x2x = pv.x2x + base;
+        const double* __restrict__ x2y = pv.x2y + base;
+        const double* mp = pv.models + (size_t)gid * 90 + s * 9;
         double E[9];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) E[k] = models[s * 9 + k];
+        for (int k = 0; k < 9; ++k) E[k] = mp[k];
+        const geom::SampsonThreshold thr = geom::make_sampson_threshold(ra.thr2f);
         int cnt = 0;
         for (int i0 = 0; i0 < m; i0 += 32) {
-            const int i = i0 + lane;
+            const int j = i0 + lane;
             bool in = false;
-            if (i < m) in = geom::sampson_inlier(E, x1x[i], x1y[i], x2x[i], x2y[i], ra.thr2f);
+            if (j < m) in = geom::sampson_inlier_fast(E, x1x[j], x1y[j], x2x[j], x2y[j], thr);
             cnt += __popc(__ballot_sync(0xffffffffu, in));
         }
-        if (pv.counts && lane == 0) pv.counts[((size_t)pair * pv.nhyp_cap + h) * 10 + s] = cnt;
-        const unsigned long long packed =
-            ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(h * 10 + s));
-        best = (packed > best) ? packed : best;
+        if (lane == 0) {
+            if (pv.counts) pv.counts[(size_t)gid * 10 + s] = cnt;
+            const unsigned long long packed =
+                ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(h * 10 + s));
+            atomicMax(&pv.best[pair], packed);
+        }
     }
-    if (lane == 0 && best) atomicMax(&pv.best[pair], best);
 }
+
+static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
+    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.cand_count, 0, sizeof(unsigned), ctx->stream));
+    const dim3 grid(div_up(ra.nhyp, 128), npairs);
+    fp_setup_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra);
+    B200VO_LAUNCH_CHECK(ctx);
+    fp_isolate_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra);
+    B200VO_LAUNCH_CHECK(ctx);
+    const long expect = (long)npairs * ra.nhyp * 5;               // ~4.9 roots per hypothesis
+    const int blocks = (int)std::min<long>(148 * 16, std::max<long>(1, (expect + 127) / 128));
+    fp_finish_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->pairs, npairs);
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
+int init_ransac_kernels() { return B200VO_OK; }
 
 __global__ void __launch_bounds__(256)
 finalize_kernel(PairView pv, RansacArgs ra) {
@@ -203,10 +293,13 @@ int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int3
     ra.thr2f = (float)(thr * thr);
     ra.min_matches = ctx->opt.min_matches_for_pose;
     B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.best, 0, (size_t)npairs * sizeof(unsigned long long), ctx->stream));
-    five_point_kernel<<<dim3(div_up(nhyp, 128), npairs), 128, 0, ctx->stream>>>(ctx->pairs, ra);
-    B200VO_LAUNCH_CHECK(ctx);
-    score_kernel<<<dim3(div_up(nhyp, 8), npairs), 256, 0, ctx->stream>>>(ctx->pairs, ra);
-    B200VO_LAUNCH_CHECK(ctx);
+    { const int rc = launch_five_point(ctx, ra, npairs); if (rc) return rc; }
+    {
+        const long expect = (long)npairs * nhyp * 5;
+        const int blocks = (int)std::min<long>(148 * 8, std::max<long>(1, (expect + 7) / 8));
+        score_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pairs, ra);
+        B200VO_LAUNCH_CHECK(ctx);
+    }
     finalize_kernel<<<npairs, 256, 0, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
@@ -225,9 +318,7 @@ int launch_recover_pose(b200vo_ctx* ctx, int npairs) { return launch_recover_pos
 int launch_five_point_only(b200vo_ctx* ctx, const int32_t* d_samples, int nhyp) {
     RansacArgs ra;
     ra.samples = d_samples; ra.seed = 0; ra.first_pair_id = 0; ra.nhyp = nhyp; ra.thr2f = 0.f; ra.min_matches = 5;
-    five_point_kernel<<<dim3(div_up(nhyp, 128), 1), 128, 0, ctx->stream>>>(ctx->pairs, ra);
-    B200VO_LAUNCH_CHECK(ctx);
-    return B200VO_OK;
+    return launch_five_point(ctx, ra, 1);
 }
 
 // ------------------------------------------------------------------ parity hooks (device side)

@@ -31,3 +31,14 @@ void hs_draw_samples(unsigned long long seed, long long pair_id, int nhyp, int m
 }
 int hs_real_roots(const double* c, int deg, double* roots) { return real_roots_unit<10>(c, deg, roots); }
 }
+extern "C" int hs_real_roots_sturm(const double* c, int deg, double* roots) { return real_roots_sturm<10>(c, deg, roots); }
+extern "C" int hs_count_inliers_fast(const double* E, const double* x1, const double* x2, int n, float thr2f, unsigned char* mask) {
+    const SampsonThreshold t = make_sampson_threshold(thr2f);
+    int c = 0;
+    for (int i = 0; i < n; ++i) {
+        const bool ok = sampson_inlier_fast(E, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], t);
+        if (mask) mask[i] = ok;
+        c += ok;
+    }
+    return c;
+}
