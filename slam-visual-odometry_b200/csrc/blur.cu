@@ -13,8 +13,10 @@
 
 namespace b200vo {
 
-constexpr int BL_W = 64, BL_H = 32;
-constexpr int BL_SW = BL_W + 6, BL_SH = BL_H + 6;
+constexpr int BL_W = 128, BL_H = 32;
+constexpr int BL_HALO = 4;                              // 3 needed; 4 keeps the staged rows word-aligned
+constexpr int BL_SWW = (BL_W + 2 * BL_HALO) / 4;        // 34 words per staged row
+constexpr int BL_SH = BL_H + 6;                         // 38 staged rows
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -22,9 +24,11 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return i;
 }
 
+// Each thread produces 4 horizontally adjacent pixels in both passes: the row pass reads 3 aligned
+// shared-memory words (10 bytes) for 4 outputs, the column pass 7 float4.
 __global__ void __launch_bounds__(256)
 blur_kernel(StoreView sv, int level, int first_slot) {
-    __shared__ uint8_t s_in[BL_SH][BL_SW + 2];
+    __shared__ uint32_t s_in[BL_SH][BL_SWW];
     __shared__ __align__(16) float s_row[BL_SH][BL_W];
     // kernel taps as the float32 bit patterns OpenCV's getGaussianKernel(7, 2, CV_32F) yields
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu),
@@ -36,36 +40,61 @@ blur_kernel(StoreView sv, int level, int first_slot) {
     const int ox = blockIdx.x * BL_W, oy = blockIdx.y * BL_H;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < BL_SH * BL_SW; i += 256) {
-        const int ty = i / BL_SW, tx = i - ty * BL_SW;
-        // clamp first so that far-outside tile coordinates stay reflectable, then reflect
+    // stage rows oy-3 .. oy+BL_H+2, bytes ox-4 .. ox+BL_W+3 (BORDER_REFLECT_101 at the image edges)
+    for (int i = tid; i < BL_SH * BL_SWW; i += 256) {
+        const int ty = i / BL_SWW, wx = i - ty * BL_SWW;
         const int gy = reflect101(min(oy - 3 + ty, g.h + 2), g.h);
-        const int gx = reflect101(min(ox - 3 + tx, g.w + 2), g.w);
-        s_in[ty][tx] = __ldg(img + (size_t)gy * g.pitch + gx);
+        const int gx = ox - BL_HALO + 4 * wx;
+        const uint8_t* row = img + (size_t)gy * g.pitch;
+        uint32_t v;
+        if (gx >= 0 && gx + 3 < g.w) {
+            v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+        } else {
+            v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int x = reflect101(min(gx + b, g.w + 2), g.w);
+                v |= (uint32_t)__ldg(row + x) << (8 * b);
+            }
+        }
+        s_in[ty][wx] = v;
     }
     __syncthreads();
 
-    for (int i = tid; i < BL_SH * BL_W; i += 256) {
-        const int ty = i / BL_W, tx = i - ty * BL_W;
-        const uint8_t* p = &s_in[ty][tx];
-        float s = __fmul_rn(k0, (float)p[0]);
-        s = __fmaf_rn((float)p[1], k1, s);
-        s = __fmaf_rn((float)p[2], k2, s);
-        s = __fmaf_rn((float)p[3], k3, s);
-        s = __fmaf_rn((float)p[4], k2, s);
-        s = __fmaf_rn((float)p[5], k1, s);
-        s = __fmaf_rn((float)p[6], k0, s);
-        s_row[ty][tx] = s;
+    // row pass: s = k0*p[-3]; s = fma(p[-3+i], k[i], s), i = 1..6   (sequential, as OpenCV)
+    for (int i = tid; i < BL_SH * (BL_W / 4); i += 256) {
+        const int ty = i / (BL_W / 4), q = i - ty * (BL_W / 4);
+        // outputs x = 4q..4q+3 need staged bytes 4q+1 .. 4q+10 -> words q, q+1, q+2
+        const uint32_t w0 = s_in[ty][q], w1 = s_in[ty][q + 1], w2 = s_in[ty][q + 2];
+        float p[10];
+        p[0] = (float)((w0 >> 8) & 0xFF); p[1] = (float)((w0 >> 16) & 0xFF); p[2] = (float)(w0 >> 24);
+        p[3] = (float)(w1 & 0xFF); p[4] = (float)((w1 >> 8) & 0xFF); p[5] = (float)((w1 >> 16) & 0xFF); p[6] = (float)(w1 >> 24);
+        p[7] = (float)(w2 & 0xFF); p[8] = (float)((w2 >> 8) & 0xFF); p[9] = (float)((w2 >> 16) & 0xFF);
+        float4 r;
+        float* rr = &r.x;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float s = __fmul_rn(k0, p[c]);
+            s = __fmaf_rn(p[c + 1], k1, s);
+            s = __fmaf_rn(p[c + 2], k2, s);
+            s = __fmaf_rn(p[c + 3], k3, s);
+            s = __fmaf_rn(p[c + 4], k2, s);
+            s = __fmaf_rn(p[c + 5], k1, s);
+            s = __fmaf_rn(p[c + 6], k0, s);
+            rr[c] = s;
+        }
+        *reinterpret_cast<float4*>(&s_row[ty][4 * q]) = r;
     }
     __syncthreads();
 
-    const int tx4 = (tid & 15) * 4;
-    for (int ty = tid >> 4; ty < BL_H; ty += 16) {
-        const int gy = oy + ty, gx = ox + tx4;
+    // column pass: s = k3*r[y]; s = fma(r[y+j] + r[y-j], k[3+j], s), j = 1..3; round-half-even, saturate
+    for (int i = tid; i < BL_H * (BL_W / 4); i += 256) {
+        const int ty = i / (BL_W / 4), q = i - ty * (BL_W / 4);
+        const int gy = oy + ty, gx = ox + 4 * q;
         if (gy >= g.h || gx >= g.w) continue;
         float4 r[7];
 #pragma unroll
-        for (int j = 0; j < 7; ++j) r[j] = *reinterpret_cast<const float4*>(&s_row[ty + j][tx4]);
+        for (int j = 0; j < 7; ++j) r[j] = *reinterpret_cast<const float4*>(&s_row[ty + j][4 * q]);
         uint32_t packed = 0;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -75,9 +104,9 @@ blur_kernel(StoreView sv, int level, int first_slot) {
             s = __fmaf_rn(__fadd_rn(v4, v2), k2, s);
             s = __fmaf_rn(__fadd_rn(v5, v1), k1, s);
             s = __fmaf_rn(__fadd_rn(v6, v0), k0, s);
-            int q = __float2int_rn(s);
-            q = min(max(q, 0), 255);
-            packed |= (uint32_t)q << (8 * c);
+            int qv = __float2int_rn(s);
+            qv = min(max(qv, 0), 255);
+            packed |= (uint32_t)qv << (8 * c);
         }
         *reinterpret_cast<uint32_t*>(out + (size_t)gy * g.pitch + gx) = packed;   // pitch >= round_up(w,4)
     }

@@ -73,6 +73,8 @@ struct PairView {
     int* nsol;                 // [pairs][nhyp_cap]
     int* counts;               // [pairs][nhyp_cap][10] inlier counts (parity hook; may be NULL)
     uint8_t* model_ok;         // [pairs][nhyp_cap][10] 1 where models[...] holds a solution
+    double* pose_cand;         // [pairs][24] R1(9) R2(9) t(3) from decomposeEssentialMat
+    int* pose_cnt;             // [pairs][4] cheirality votes of the four candidates
     // phased five-point solver work space (ransac.cu)
     double* fp_setup;          // [86][pairs*nhyp_cap] element-major FivePointSetup
     uint8_t* fp_ok;            // [pairs*nhyp_cap] setup succeeded
@@ -99,7 +101,12 @@ struct b200vo_ctx {
     // scratch for parity hooks / raw matcher
     void* d_scratch; size_t scratch_bytes;
     void* h_pinned; size_t pinned_bytes;
-    uint8_t* d_bgr; size_t bgr_bytes;      // staging for 3-channel uploads
+    // host uploads: dense H2D copy on a dedicated copy stream into one of two staging buffers, then a
+    // device-side repack (or BGR->gray) on the compute stream; events order the two streams
+    cudaStream_t copy_stream;
+    uint8_t* d_stage[2]; size_t stage_bytes[2];
+    cudaEvent_t stage_ready[2], stage_free[2];
+    int stage_idx;
     int64_t launches;
     bool timing;
     b200vo_stage_times times;

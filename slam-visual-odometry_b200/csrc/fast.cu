@@ -13,101 +13,174 @@
 
 namespace b200vo {
 
-constexpr int FT_W = 64, FT_H = 32;             // output tile
-constexpr int FT_SW = FT_W + 8, FT_SH = FT_H + 8;   // pixel tile (halo 3 ring + 1 NMS)
-constexpr int FT_CW = FT_W + 2, FT_CH = FT_H + 2;   // score tile (halo 1)
+// Tile geometry: 62x30 outputs -> a 64x32 score tile (1-px NMS halo) -> a 70x38 pixel tile (+3 ring).
+// The pixel tile is fetched as aligned 32-bit words (row of 20 words; `shift` = misalignment of the
+// tile origin), so staging costs ~4 instructions per pixel instead of one byte load each.
+constexpr int FT_W = 62, FT_H = 30;
+constexpr int FT_CW = 64, FT_CH = 32;            // score tile
+constexpr int FT_SWW = 20, FT_SW = FT_SWW * 4;   // pixel tile row: 20 words = 80 bytes (>= 70 + 3)
+constexpr int FT_SH = FT_CH + 6;                 // 38 rows
 
 __device__ __forceinline__ bool has_arc9(uint32_t m) {
     uint32_t r = m | (m << 16);
+    const uint32_t m2 = r;
     r &= r >> 1;
     r &= r >> 2;
     r &= r >> 4;
-    r &= (m | (m << 16)) >> 8;
+    r &= m2 >> 8;
     return (r & 0xFFFFu) != 0;
 }
 
-// p points at the centre pixel inside the shared tile (row stride FT_SW).
-__device__ __forceinline__ int fast_score(const uint8_t* p, int t) {
+__device__ __forceinline__ void load_ring(const uint8_t* p, int* v) {
     const int S = FT_SW;
-    const int c = p[0];
-    const int hi = c + t, lo = c - t;
-    // every 9-arc contains one pixel of each opposite pair: cheap rejection on (0,8) and (4,12)
-    const int r0 = p[3 * S], r8 = p[-3 * S];
-    if (!((r0 > hi) | (r8 > hi) | (r0 < lo) | (r8 < lo))) return 0;
-    const int r4 = p[3], r12 = p[-3];
-    if (!((r4 > hi) | (r12 > hi) | (r4 < lo) | (r12 < lo))) return 0;
-    int v[16];
-    v[0] = r0;            v[1] = p[3 * S + 1];   v[2] = p[2 * S + 2];   v[3] = p[S + 3];
-    v[4] = r4;            v[5] = p[-S + 3];      v[6] = p[-2 * S + 2];  v[7] = p[-3 * S + 1];
-    v[8] = r8;            v[9] = p[-3 * S - 1];  v[10] = p[-2 * S - 2]; v[11] = p[-S - 3];
-    v[12] = r12;          v[13] = p[S - 3];      v[14] = p[2 * S - 2];  v[15] = p[3 * S - 1];
-    uint32_t mb = 0, md = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        mb |= (uint32_t)(v[i] > hi) << i;
-        md |= (uint32_t)(v[i] < lo) << i;
-    }
-    const bool bright = has_arc9(mb);
-    if (!bright && !has_arc9(md)) return 0;
-    // exactly one polarity can hold a 9-arc; its arc-min maximum is the corner's best threshold
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = bright ? (v[i] - c) : (c - v[i]);
-    int m2[16], m4[16], best = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) m2[i] = min(v[i], v[(i + 1) & 15]);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) m4[i] = min(m2[i], m2[(i + 2) & 15]);
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const int m8 = min(m4[i], m4[(i + 4) & 15]);
-        best = max(best, min(m8, v[(i + 8) & 15]));
-    }
-    return best - 1;    // best > t is implied by the mask test
+    v[0] = p[3 * S];       v[1] = p[3 * S + 1];   v[2] = p[2 * S + 2];   v[3] = p[S + 3];
+    v[4] = p[3];           v[5] = p[-S + 3];      v[6] = p[-2 * S + 2];  v[7] = p[-3 * S + 1];
+    v[8] = p[-3 * S];      v[9] = p[-3 * S - 1];  v[10] = p[-2 * S - 2]; v[11] = p[-S - 3];
+    v[12] = p[-3];         v[13] = p[S - 3];      v[14] = p[2 * S - 2];  v[15] = p[3 * S - 1];
 }
 
+// The work is re-packed between phases so that the expensive paths run on dense lane sets:
+//   1. every pixel: compass test (a 9-arc always covers two ADJACENT compass pixels 0,4,8,12 of the
+//      same polarity) -> survivors appended to a shared list (warp-aggregated)
+//   2. survivors: full 16-pixel segment test -> corners appended to a second list
+//   3. corners: corner score (max over 9-arcs of the arc minimum, minus 1) -> score tile
+//   4. corners: strict 3x3 non-max suppression + border filter -> candidate list + histogram
 __global__ void __launch_bounds__(256)
 fast_kernel(StoreView sv, int level, int first_slot) {
     __shared__ __align__(16) uint8_t s_img[FT_SH * FT_SW];
-    __shared__ uint8_t s_score[FT_CH * FT_CW];
-    __shared__ uint32_t s_list[FT_W * FT_H / 4];
-    __shared__ int s_n, s_base;
+    __shared__ __align__(4) uint8_t s_score[FT_CH * FT_CW];
+    __shared__ uint16_t s_surv[FT_CH * FT_CW];
+    __shared__ uint16_t s_corn[FT_CH * FT_CW];
+    __shared__ uint32_t s_list[FT_CH * FT_CW / 4];
+    __shared__ int s_nsurv, s_ncorn, s_n, s_base;
 
     const LevelGeom g = sv.lv[level];
     const int slot = (first_slot + blockIdx.z) % sv.slots;
     const uint8_t* __restrict__ img = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset;
     const int ox = kEdge + blockIdx.x * FT_W;       // first output pixel of the tile
     const int oy = kEdge + blockIdx.y * FT_H;
-    const int tid = threadIdx.x;
-    if (tid == 0) s_n = 0;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int px0 = ox - 4, py0 = oy - 4;           // pixel-tile origin (>= 27: always inside the image)
+    const int x0 = px0 & ~3, shift = px0 - x0;
+    if (tid == 0) { s_nsurv = 0; s_ncorn = 0; s_n = 0; }
 
-    // stage the pixel tile: rows oy-4 .. oy+FT_H+3, cols ox-4 .. ox+FT_W+3 (clamped: clamped
-    // pixels only feed outputs beyond the border filter, which are discarded)
-    for (int i = tid; i < FT_SH * FT_SW; i += 256) {
-        const int ty = i / FT_SW, tx = i - ty * FT_SW;
-        const int gy = min(oy - 4 + ty, g.h - 1), gx = min(ox - 4 + tx, g.w - 1);
-        s_img[i] = __ldg(img + (size_t)gy * g.pitch + gx);
+    {
+        uint32_t* s32 = reinterpret_cast<uint32_t*>(s_img);
+        const int wmax = g.pitch / 4 - 1;
+        for (int i = tid; i < FT_SH * FT_SWW; i += 256) {
+            const int ty = i / FT_SWW, wx = i - ty * FT_SWW;
+            const int gy = min(py0 + ty, g.h - 1), gw = min(x0 / 4 + wx, wmax);
+            s32[i] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)gy * g.pitch) + gw);
+        }
+        uint32_t* sc32 = reinterpret_cast<uint32_t*>(s_score);
+        for (int i = tid; i < FT_CH * FT_CW / 4; i += 256) sc32[i] = 0;
     }
     __syncthreads();
 
     const int t = sv.fast_threshold;
-    for (int i = tid; i < FT_CH * FT_CW; i += 256) {
-        const int cy = i / FT_CW, cx = i - cy * FT_CW;
-        s_score[i] = (uint8_t)fast_score(&s_img[(cy + 3) * FT_SW + (cx + 3)], t);
+    // score-tile cell (cx, cy) <-> pixel-tile byte (cx + 3 + shift, cy + 3)
+    const uint8_t* s_org = s_img + 3 * FT_SW + 3 + shift;
+
+    // ---- phase 1: compass test on every cell of the score tile
+#pragma unroll
+    for (int r = 0; r < FT_CH / 8; ++r) {
+        const int cy = warp + 8 * r;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            const int cx = lane + 32 * hh;
+            const uint8_t* p = s_org + cy * FT_SW + cx;
+            const int c = p[0];
+            const int hi = c + t, lo = c - t;
+            const int r0 = p[3 * FT_SW], r4 = p[3], r8 = p[-3 * FT_SW], r12 = p[-3];
+            const bool b0 = r0 > hi, b4 = r4 > hi, b8 = r8 > hi, b12 = r12 > hi;
+            const bool d0 = r0 < lo, d4 = r4 < lo, d8 = r8 < lo, d12 = r12 < lo;
+            const bool pass = (b0 & b4) | (b4 & b8) | (b8 & b12) | (b12 & b0) | (d0 & d4) | (d4 & d8) | (d8 & d12) | (d12 & d0);
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&s_nsurv, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (pass) s_surv[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(cy * FT_CW + cx);
+            }
+        }
     }
     __syncthreads();
 
+    // ---- phase 2: full segment test on the survivors
+    const int nsurv = s_nsurv;
+    for (int k0 = 0; k0 < nsurv; k0 += 256) {
+        const int k = k0 + tid;
+        bool corner = false, bright = false;
+        int cell = 0;
+        if (k < nsurv) {
+            cell = s_surv[k];
+            const int cy = cell / FT_CW, cx = cell - cy * FT_CW;
+            const uint8_t* p = s_org + cy * FT_SW + cx;
+            const int c = p[0], hi = c + t, lo = c - t;
+            int v[16];
+            load_ring(p, v);
+            uint32_t mb = 0, md = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                mb |= (uint32_t)(v[i] > hi) << i;
+                md |= (uint32_t)(v[i] < lo) << i;
+            }
+            bright = has_arc9(mb);
+            corner = bright || has_arc9(md);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, corner);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_ncorn, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (corner) s_corn[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)(cell | (bright ? 0x8000 : 0));
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 3: corner score
+    const int ncorn = s_ncorn;
+    for (int k = tid; k < ncorn; k += 256) {
+        const int e = s_corn[k];
+        const int cell = e & 0x7FFF;
+        const bool bright = (e & 0x8000) != 0;
+        const int cy = cell / FT_CW, cx = cell - cy * FT_CW;
+        const uint8_t* p = s_org + cy * FT_SW + cx;
+        const int c = p[0];
+        int v[16];
+        load_ring(p, v);
+        // exactly one polarity can hold a 9-arc; its arc-min maximum is the corner's best threshold
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = bright ? (v[i] - c) : (c - v[i]);
+        int m2[16], m4[16], best = 0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m2[i] = min(v[i], v[(i + 1) & 15]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) m4[i] = min(m2[i], m2[(i + 2) & 15]);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const int m8 = min(m4[i], m4[(i + 4) & 15]);
+            best = max(best, min(m8, v[(i + 8) & 15]));
+        }
+        s_score[cell] = (uint8_t)(best - 1);        // best > t is implied by the mask test
+    }
+    __syncthreads();
+
+    // ---- phase 4: strict 3x3 NMS on interior corners, border filter, append
     const int xmax = g.w - kEdge, ymax = g.h - kEdge;
-    for (int i = tid; i < FT_W * FT_H; i += 256) {
-        const int ty = i / FT_W, tx = i - ty * FT_W;
-        const int gx = ox + tx, gy = oy + ty;
-        const uint8_t* s = &s_score[(ty + 1) * FT_CW + (tx + 1)];
+    for (int k = tid; k < ncorn; k += 256) {
+        const int cell = s_corn[k] & 0x7FFF;
+        const int cy = cell / FT_CW, cx = cell - cy * FT_CW;
+        if (cx < 1 || cx > FT_W || cy < 1 || cy > FT_H) continue;       // halo cells only feed their neighbours
+        const int gx = ox + cx - 1, gy = oy + cy - 1;
+        if (gx >= xmax || gy >= ymax) continue;
+        const uint8_t* s = &s_score[cell];
         const int sc = s[0];
-        if (sc == 0 || gx >= xmax || gy >= ymax) continue;
         const bool keep = sc > s[-1] && sc > s[1] && sc > s[-FT_CW - 1] && sc > s[-FT_CW] && sc > s[-FT_CW + 1] &&
                           sc > s[FT_CW - 1] && sc > s[FT_CW] && sc > s[FT_CW + 1];
         if (keep) {
-            const int k = atomicAdd(&s_n, 1);
-            s_list[k] = ((uint32_t)gy << 20) | ((uint32_t)gx << 8) | (uint32_t)sc;
+            const int j = atomicAdd(&s_n, 1);
+            s_list[j] = ((uint32_t)gy << 20) | ((uint32_t)gx << 8) | (uint32_t)sc;
             atomicAdd(&sv.fast_hist[((size_t)slot * kLevels + level) * 256 + sc], 1);
         }
     }

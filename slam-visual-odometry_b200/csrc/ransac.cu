@@ -230,59 +230,106 @@ finalize_kernel(PairView pv, RansacArgs ra) {
 
 struct PoseArgs { int min_valid, min_inliers; uint8_t* mask_out; /* [pairs][kp_cap] or NULL */ };
 
-__global__ void __launch_bounds__(256)
-recover_pose_kernel(PairView pv, PoseArgs pa) {
-    __shared__ double s_R[2][9], s_t[3];
-    __shared__ int s_cnt[4], s_best;
-    const int pair = blockIdx.x;
-    const int tid = threadIdx.x;
-    b200vo_pose_record* rec = pv.rec + pair;
-    if (!(rec->status & B200VO_ST_E_FOUND)) return;
-    if (tid == 0) {
-        geom::decompose_essential(pv.E + (size_t)pair * 9, s_R[0], s_R[1], s_t);
-        s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
-    }
-    __syncthreads();
+// recoverPose in three flat launches (a CTA-per-pair kernel with thread 0 decomposing E left the
+// SMs idle: 12 % occupancy, 35 % barrier stalls in the v1 profile):
+//   pose_decompose_kernel  thread / pair           SVD of E -> R1, R2, t
+//   pose_vote_kernel       thread / (pair, point)  4 triangulations + cheirality, warp-reduced votes
+//   pose_select_kernel     thread / pair           first maximum wins -> record
+__global__ void __launch_bounds__(64)
+pose_decompose_kernel(PairView pv, int npairs) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= npairs) return;
+    int* cnt = pv.pose_cnt + pair * 4;
+    cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+    if (!(pv.rec[pair].status & B200VO_ST_E_FOUND)) return;
+    double* c = pv.pose_cand + (size_t)pair * 24;
+    geom::decompose_essential(pv.E + (size_t)pair * 9, c, c + 9, c + 18);
+}
+
+__global__ void __launch_bounds__(128)
+pose_vote_kernel(PairView pv) {
+    const int pair = blockIdx.y;
+    if (!(pv.rec[pair].status & B200VO_ST_E_FOUND)) return;
     const int m = pv.n_good[pair];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= m) return;
     const size_t base = (size_t)pair * pv.kp_cap;
-    const double tp[3] = {s_t[0], s_t[1], s_t[2]}, tn[3] = {-s_t[0], -s_t[1], -s_t[2]};
     int c[4] = {0, 0, 0, 0};
-    for (int i = tid; i < m; i += blockDim.x) {
-        if (!pv.inl[base + i]) continue;
+    if (i < m && pv.inl[base + i]) {
+        const double* cand = pv.pose_cand + (size_t)pair * 24;
+        double R1[9], R2[9], tp[3], tn[3];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { R1[k] = cand[k]; R2[k] = cand[9 + k]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { tp[k] = cand[18 + k]; tn[k] = -tp[k]; }
         const double a = pv.x1x[base + i], b = pv.x1y[base + i], cc = pv.x2x[base + i], d = pv.x2y[base + i];
         // candidate order of cv::recoverPose: (R1,t), (R2,t), (R1,-t), (R2,-t)
-        c[0] += geom::cheirality_ok(s_R[0], tp, a, b, cc, d, 50.0);
-        c[1] += geom::cheirality_ok(s_R[1], tp, a, b, cc, d, 50.0);
-        c[2] += geom::cheirality_ok(s_R[0], tn, a, b, cc, d, 50.0);
-        c[3] += geom::cheirality_ok(s_R[1], tn, a, b, cc, d, 50.0);
+        c[0] = geom::cheirality_ok(R1, tp, a, b, cc, d, 50.0);
+        c[1] = geom::cheirality_ok(R2, tp, a, b, cc, d, 50.0);
+        c[2] = geom::cheirality_ok(R1, tn, a, b, cc, d, 50.0);
+        c[3] = geom::cheirality_ok(R2, tn, a, b, cc, d, 50.0);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int w = __reduce_add_sync(0xffffffffu, c[k]);
-        if ((tid & 31) == 0 && w) atomicAdd(&s_cnt[k], w);
+        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&pv.pose_cnt[pair * 4 + k], w);
     }
-    __syncthreads();
-    if (tid == 0) {
-        int bi = 0;
-        for (int k = 1; k < 4; ++k)
-            if (s_cnt[k] > s_cnt[bi]) bi = k;      // first maximum wins
-        const double* R = s_R[bi & 1];
-        const double sg = (bi >= 2) ? -1.0 : 1.0;
-        for (int k = 0; k < 9; ++k) rec->R[k] = R[k];
-        for (int k = 0; k < 3; ++k) rec->t[k] = sg * s_t[k];
-        rec->n_valid = s_cnt[bi];
-        if (s_cnt[bi] >= pa.min_valid && rec->n_inliers >= pa.min_inliers) rec->status |= B200VO_ST_POSE_OK;
-        s_best = bi;
+}
+
+__global__ void __launch_bounds__(64)
+pose_select_kernel(PairView pv, PoseArgs pa, int npairs) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= npairs) return;
+    b200vo_pose_record* rec = pv.rec + pair;
+    if (!(rec->status & B200VO_ST_E_FOUND)) return;
+    const int* cnt = pv.pose_cnt + pair * 4;
+    int bi = 0;
+    for (int k = 1; k < 4; ++k)
+        if (cnt[k] > cnt[bi]) bi = k;              // first maximum wins
+    const double* cand = pv.pose_cand + (size_t)pair * 24;
+    const double* R = cand + 9 * (bi & 1);
+    const double sg = (bi >= 2) ? -1.0 : 1.0;
+    for (int k = 0; k < 9; ++k) rec->R[k] = R[k];
+    for (int k = 0; k < 3; ++k) rec->t[k] = sg * cand[18 + k];
+    rec->n_valid = cnt[bi];
+    if (cnt[bi] >= pa.min_valid && rec->n_inliers >= pa.min_inliers) rec->status |= B200VO_ST_POSE_OK;
+}
+
+// parity hook only: cv::recoverPose overwrites the mask with the winning candidate's test
+__global__ void pose_mask_kernel(PairView pv, PoseArgs pa) {
+    const int pair = blockIdx.y;
+    const b200vo_pose_record* rec = pv.rec + pair;
+    if (!(rec->status & B200VO_ST_E_FOUND)) return;
+    const int m = pv.n_good[pair];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const size_t base = (size_t)pair * pv.kp_cap;
+    pa.mask_out[base + i] = pv.inl[base + i] &&
+        geom::cheirality_ok(rec->R, rec->t, pv.x1x[base + i], pv.x1y[base + i], pv.x2x[base + i], pv.x2y[base + i], 50.0);
+}
+
+int launch_recover_pose_masked(b200vo_ctx* ctx, int npairs, uint8_t* d_mask_out) {
+    PoseArgs pa{ctx->opt.min_valid_points, ctx->opt.min_inliers, d_mask_out};
+    pose_decompose_kernel<<<div_up(npairs, 64), 64, 0, ctx->stream>>>(ctx->pairs, npairs);
+    B200VO_LAUNCH_CHECK(ctx);
+    pose_vote_kernel<<<dim3(div_up(ctx->pairs.kp_cap, 128), npairs), 128, 0, ctx->stream>>>(ctx->pairs);
+    B200VO_LAUNCH_CHECK(ctx);
+    pose_select_kernel<<<div_up(npairs, 64), 64, 0, ctx->stream>>>(ctx->pairs, pa, npairs);
+    B200VO_LAUNCH_CHECK(ctx);
+    if (d_mask_out) {
+        pose_mask_kernel<<<dim3(div_up(ctx->pairs.kp_cap, 128), npairs), 128, 0, ctx->stream>>>(ctx->pairs, pa);
+        B200VO_LAUNCH_CHECK(ctx);
     }
-    if (pa.mask_out) {      // parity hook only: cv::recoverPose overwrites the mask with the winner's test
-        __syncthreads();
-        const int bi = s_best;
-        const double* R = s_R[bi & 1];
-        const double* tt = (bi >= 2) ? tn : tp;
-        for (int i = tid; i < m; i += blockDim.x)
-            pa.mask_out[base + i] = pv.inl[base + i] &&
-                geom::cheirality_ok(R, tt, pv.x1x[base + i], pv.x1y[base + i], pv.x2x[base + i], pv.x2y[base + i], 50.0);
-    }
+    return B200VO_OK;
+}
+
+int launch_recover_pose(b200vo_ctx* ctx, int npairs) { return launch_recover_pose_masked(ctx, npairs, nullptr); }
+
+// parity hook: solve the given samples for pair 0 (points staged by the caller)
+int launch_five_point_only(b200vo_ctx* ctx, const int32_t* d_samples, int nhyp) {
+    RansacArgs ra;
+    ra.samples = d_samples; ra.seed = 0; ra.first_pair_id = 0; ra.nhyp = nhyp; ra.thr2f = 0.f; ra.min_matches = 5;
+    return launch_five_point(ctx, ra, 1);
 }
 
 int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int32_t* d_samples, int nhyp) {
@@ -303,22 +350,6 @@ int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int3
     finalize_kernel<<<npairs, 256, 0, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
-}
-
-int launch_recover_pose_masked(b200vo_ctx* ctx, int npairs, uint8_t* d_mask_out) {
-    PoseArgs pa{ctx->opt.min_valid_points, ctx->opt.min_inliers, d_mask_out};
-    recover_pose_kernel<<<npairs, 256, 0, ctx->stream>>>(ctx->pairs, pa);
-    B200VO_LAUNCH_CHECK(ctx);
-    return B200VO_OK;
-}
-
-int launch_recover_pose(b200vo_ctx* ctx, int npairs) { return launch_recover_pose_masked(ctx, npairs, nullptr); }
-
-// parity hook: solve the given samples for pair 0 (points staged by the caller)
-int launch_five_point_only(b200vo_ctx* ctx, const int32_t* d_samples, int nhyp) {
-    RansacArgs ra;
-    ra.samples = d_samples; ra.seed = 0; ra.first_pair_id = 0; ra.nhyp = nhyp; ra.thr2f = 0.f; ra.min_matches = 5;
-    return launch_five_point(ctx, ra, 1);
 }
 
 // ------------------------------------------------------------------ parity hooks (device side)
