@@ -22,8 +22,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int upload_brief_pattern();
-int launch_score_models(b200vo_ctx* ctx, const double* d_x1, const double* d_x2, int npts, const double* d_models,
-                        int nmodels, float thr2f, int* d_counts);
+int launch_score_models(b200vo_ctx* ctx, const double* d_models, int nmodels, float thr2f, int* d_counts);
 int launch_recover_pose_masked(b200vo_ctx* ctx, int npairs, uint8_t* d_mask_out);
 int measure_popc_rate(b200vo_ctx* ctx, double* popc_per_second);
 int init_ransac_kernels();
@@ -273,6 +272,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     TRY(dev_alloc(ctx, &pv.x1y, P * C));
     TRY(dev_alloc(ctx, &pv.x2x, P * C));
     TRY(dev_alloc(ctx, &pv.x2y, P * C));
+    TRY(dev_alloc(ctx, &pv.xf, P * C));
     TRY(dev_alloc(ctx, &pv.best, P));
     TRY(dev_alloc(ctx, &pv.E, P * 9));
     TRY(dev_alloc(ctx, &pv.inl, P * C));
@@ -285,6 +285,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     TRY(dev_alloc(ctx, &pv.fp_setup, P * pv.nhyp_cap * 86));
     TRY(dev_alloc(ctx, &pv.fp_ok, P * pv.nhyp_cap));
     TRY(dev_alloc(ctx, &pv.cand_count, 4));
+    TRY(dev_alloc(ctx, &pv.fb_gid, P * pv.nhyp_cap));
     pv.cand_cap = (int)std::min<size_t>(P * pv.nhyp_cap * 10, (size_t)1 << 30);
     TRY(dev_alloc(ctx, &pv.cand_gid, (size_t)pv.cand_cap));
     TRY(dev_alloc(ctx, &pv.cand_tag, (size_t)pv.cand_cap));
@@ -616,6 +617,12 @@ static int stage_points(b200vo_ctx* ctx, const double* x1, const double* x2, int
     B200VO_CUDA_CHECK(cudaMemcpyAsync(pv.x1y, soa.data() + npts, b, cudaMemcpyHostToDevice, ctx->stream));
     B200VO_CUDA_CHECK(cudaMemcpyAsync(pv.x2x, soa.data() + 2 * (size_t)npts, b, cudaMemcpyHostToDevice, ctx->stream));
     B200VO_CUDA_CHECK(cudaMemcpyAsync(pv.x2y, soa.data() + 3 * (size_t)npts, b, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<float> xf((size_t)4 * npts);
+    for (int i = 0; i < npts; ++i) {
+        xf[4 * (size_t)i] = (float)x1[2 * i]; xf[4 * (size_t)i + 1] = (float)x1[2 * i + 1];
+        xf[4 * (size_t)i + 2] = (float)x2[2 * i]; xf[4 * (size_t)i + 3] = (float)x2[2 * i + 1];
+    }
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(pv.xf, xf.data(), xf.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     B200VO_CUDA_CHECK(cudaMemcpyAsync(pv.n_good, &npts, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));       // soa goes out of scope
     return B200VO_OK;
@@ -658,19 +665,16 @@ int b200vo_score_models(b200vo_ctx* ctx, const double* x1, const double* x2, int
                         int nmodels, double threshold, int32_t* counts) {
     if (!ctx || !x1 || !x2 || !essentials || !counts || npts <= 0 || nmodels <= 0) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
     B200VO_CUDA_CHECK(cudaSetDevice(ctx->device));
-    const size_t pb = round_up((size_t)npts * 2 * sizeof(double), 256), mb = round_up((size_t)nmodels * 9 * sizeof(double), 256);
-    int rc = ensure_scratch(ctx, 2 * pb + mb + (size_t)nmodels * sizeof(int));
-    if (rc) return rc;
+    int rc;
+    if ((rc = stage_points(ctx, x1, x2, npts))) return rc;
+    const size_t mb = round_up((size_t)nmodels * 9 * sizeof(double), 256);
+    if ((rc = ensure_scratch(ctx, mb + (size_t)nmodels * sizeof(int)))) return rc;
     uint8_t* base = static_cast<uint8_t*>(ctx->d_scratch);
-    double* d1 = reinterpret_cast<double*>(base);
-    double* d2 = reinterpret_cast<double*>(base + pb);
-    double* dm = reinterpret_cast<double*>(base + 2 * pb);
-    int* dc = reinterpret_cast<int*>(base + 2 * pb + mb);
-    B200VO_CUDA_CHECK(cudaMemcpyAsync(d1, x1, (size_t)npts * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    B200VO_CUDA_CHECK(cudaMemcpyAsync(d2, x2, (size_t)npts * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    double* dm = reinterpret_cast<double*>(base);
+    int* dc = reinterpret_cast<int*>(base + mb);
     B200VO_CUDA_CHECK(cudaMemcpyAsync(dm, essentials, (size_t)nmodels * 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     const float thr2f = (float)(threshold * threshold);
-    if ((rc = launch_score_models(ctx, d1, d2, npts, dm, nmodels, thr2f, dc))) return rc;
+    if ((rc = launch_score_models(ctx, dm, nmodels, thr2f, dc))) return rc;
     B200VO_CUDA_CHECK(cudaMemcpyAsync(counts, dc, (size_t)nmodels * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return B200VO_OK;

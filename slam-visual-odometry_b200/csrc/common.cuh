@@ -65,6 +65,7 @@ struct PairView {
     double* thr;               // [pairs]
     // geometry (normalised coordinates of the good matches, SoA)
     double* x1x; double* x1y; double* x2x; double* x2y;   // [pairs][kp_cap]
+    float4* xf;                // [pairs][kp_cap] the same four coordinates rounded to float (scoring prefilter)
     unsigned long long* best;  // [pairs] packed (count<<32 | ~model)
     double* E;                 // [pairs][9]
     uint8_t* inl;              // [pairs][kp_cap] inlier mask of the best model
@@ -78,7 +79,8 @@ struct PairView {
     // phased five-point solver work space (ransac.cu)
     double* fp_setup;          // [86][pairs*nhyp_cap] element-major FivePointSetup
     uint8_t* fp_ok;            // [pairs*nhyp_cap] setup succeeded
-    unsigned int* cand_count;  // [1] number of root brackets in the compact list
+    unsigned int* cand_count;  // [0] number of root brackets in the compact list, [1] number of fallback hypotheses
+    int* fb_gid;               // [pairs*nhyp_cap] hypotheses whose Sturm chain was unreliable
     int* cand_gid;             // [cand_cap] pair*nhyp_cap + hypothesis
     int* cand_tag;             // [cand_cap] solution index | reversed << 8
     double* cand_a; double* cand_b;   // [cand_cap] bracket

@@ -103,6 +103,7 @@ filter_kernel(StoreView sv, PairView pv, FilterArgs fa, int P /* pow2 >= kp_cap 
         x1y[i] = ((double)a.y - fa.cy) / fa.fy;
         x2x[i] = ((double)b.x - fa.cx) / fa.fx;
         x2y[i] = ((double)b.y - fa.cy) / fa.fy;
+        pv.xf[(size_t)pair * pv.kp_cap + i] = make_float4((float)x1x[i], (float)x1y[i], (float)x2x[i], (float)x2y[i]);
     }
     if (tid == 0) {
         pv.n_good[pair] = g;

@@ -87,6 +87,30 @@ GEOM_HD inline double bracket_root(const double* c, int deg, double a, double b,
     return x;
 }
 
+// Newton inside a sign-changing bracket, bisection when unsafe; stops as soon as the step is small
+// enough that one more Newton step reaches working precision (quadratic convergence).
+GEOM_HD inline double bracket_root_fast(const double* c, int deg, double a, double b, double fa) {
+    double x = 0.5 * (a + b);
+    for (int it = 0; it < 64; ++it) {
+        double f, df;
+        horner2(c, deg, x, f, df);
+        if (f == 0.0) return x;
+        if ((f < 0.0) == (fa < 0.0)) a = x; else b = x;
+        double xn = x - f / df;
+        const bool newton_ok = (xn > a && xn < b);
+        if (!newton_ok) xn = 0.5 * (a + b);
+        const double step = fabs(xn - x);
+        x = xn;
+        if (newton_ok && step < 1e-6 * (fabs(x) + 1e-3)) {      // next step ~ step^2: polish once and stop
+            horner2(c, deg, x, f, df);
+            const double x2 = x - f / df;
+            return (x2 > a && x2 < b) ? x2 : x;
+        }
+        if (b - a <= 4e-16 * fabs(x) + 1e-300) return x;
+    }
+    return x;
+}
+
 // All simple real roots of c[0..deg] inside [-1, 1], ascending.  MAXDEG >= deg.
 template <int MAXDEG>
 GEOM_HD inline int real_roots_unit(const double* c, int deg, double* roots) {
@@ -113,7 +137,7 @@ GEOM_HD inline int real_roots_unit(const double* c, int deg, double* roots) {
             } else if (fhi == 0.0) {
                 if (ncur < MAXDEG) cur[ncur++] = hi;
             } else if ((flo < 0.0) != (fhi < 0.0)) {
-                if (ncur < MAXDEG) cur[ncur++] = bracket_root(d, dk, lo, hi, flo);
+                if (ncur < MAXDEG) cur[ncur++] = bracket_root_fast(d, dk, lo, hi, flo);
             }
             lo = hi;
             flo = fhi;
@@ -188,35 +212,11 @@ struct SturmChain {
     }
 };
 
-// Newton inside a sign-changing bracket, bisection when unsafe; stops as soon as the step is small
-// enough that one more Newton step reaches working precision (quadratic convergence).
-GEOM_HD inline double bracket_root_fast(const double* c, int deg, double a, double b, double fa) {
-    double x = 0.5 * (a + b);
-    for (int it = 0; it < 64; ++it) {
-        double f, df;
-        horner2(c, deg, x, f, df);
-        if (f == 0.0) return x;
-        if ((f < 0.0) == (fa < 0.0)) a = x; else b = x;
-        double xn = x - f / df;
-        const bool newton_ok = (xn > a && xn < b);
-        if (!newton_ok) xn = 0.5 * (a + b);
-        const double step = fabs(xn - x);
-        x = xn;
-        if (newton_ok && step < 1e-6 * (fabs(x) + 1e-3)) {      // next step ~ step^2: polish once and stop
-            horner2(c, deg, x, f, df);
-            const double x2 = x - f / df;
-            return (x2 > a && x2 < b) ? x2 : x;
-        }
-        if (b - a <= 4e-16 * fabs(x) + 1e-300) return x;
-    }
-    return x;
-}
-
 // Brackets (lo, hi] that each contain exactly one simple real root of c in (-1, 1], ascending.
 // lo == hi marks a root that is already known exactly (end point, unresolved cluster, or the
 // derivative-chain fallback, which returns refined roots).
 template <int MAXDEG>
-GEOM_HD inline int real_root_brackets(const double* c, int deg, double* lo, double* hi) {
+GEOM_HD inline int real_root_brackets(const double* c, int deg, double* lo, double* hi, bool allow_fallback = true) {
     while (deg > 0 && c[deg] == 0.0) --deg;
     if (deg <= 0) return 0;
     if (deg == 1) { const double r = -c[0] / c[1]; if (r > -1.0 && r <= 1.0) { lo[0] = hi[0] = r; return 1; } return 0; }
@@ -235,6 +235,7 @@ GEOM_HD inline int real_root_brackets(const double* c, int deg, double* lo, doub
         if (k < 0 || fm == 0.0 || fp == 0.0 || ((k & 1) != 0) != odd) ok = false;
         top = 1;
     }
+    if (!ok && !allow_fallback) return -1;      // the caller re-queues this polynomial for the slow path
     if (!ok) {
         // Unreliable chain (near-multiple roots): the derivative-chain method is exact but slow and
         // divergent.  (A fixed-grid sign scan was tried as a warp-uniform fallback: it loses the
@@ -615,13 +616,16 @@ GEOM_HD inline bool five_point_setup(const double x1[5][2], const double x2[5][2
 
 // Brackets of the real roots: first those of p in (-1,1] ascending, then those of the reversed
 // polynomial (|z| > 1) ascending in w = 1/z.  At most 10 are returned.
-GEOM_HD inline int five_point_isolate(const double* c, RootBracket* br) {
+// allow_fallback = false: returns -1 instead of taking the slow exact path (GPU: the hypothesis is
+// re-queued to a dense fallback launch so that one slow lane does not stall its whole warp).
+GEOM_HD inline int five_point_isolate(const double* c, RootBracket* br, bool allow_fallback = true) {
     int n = 0;
     for (int pass = 0; pass < 2 && n < 10; ++pass) {
         double cc[11];
         for (int i = 0; i < 11; ++i) cc[i] = pass ? c[10 - i] : c[i];
         double lo[10], hi[10];
-        const int k = real_root_brackets<10>(cc, 10, lo, hi);
+        const int k = real_root_brackets<10>(cc, 10, lo, hi, allow_fallback);
+        if (k < 0) return -1;
         for (int i = 0; i < k && n < 10; ++i) {
             if (pass) {      // keep 0 < |w| < 1 only (w = 0 is z = infinity; |w| = 1 belongs to pass 0)
                 if (lo[i] == hi[i] && !(fabs(lo[i]) > 1e-12 && fabs(lo[i]) < 1.0)) continue;

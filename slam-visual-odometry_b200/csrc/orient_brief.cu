@@ -18,7 +18,7 @@
 namespace b200vo {
 
 __constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-__device__ int8_t d_pattern[1024];
+__device__ __align__(16) int8_t d_pattern[1024];
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     const float deg = (float)(180.0 / 3.14159265358979323846);
@@ -70,14 +70,20 @@ orient_kernel(StoreView sv, int first_slot) {
     const int au = abs(u);
     int m10 = 0, m01 = 0;
     if (lane < 31) {
-#pragma unroll 1
+        // fully unrolled: the 31 row loads are independent and issue back to back (the v1 profile
+        // showed 64 % long-scoreboard stalls with one load in flight per lane)
+        constexpr int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+        int rowsum[31];
+#pragma unroll
         for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-            if (au <= c_umax[abs(v)]) {
-                const int val = __ldg(c + v * g.pitch + u);
-                m10 += u * val;
-                m01 += v * val;
-            }
+            const int a = v < 0 ? -v : v;
+            rowsum[v + kHalfPatch] = (au <= umax[a]) ? (int)__ldg(c + v * g.pitch + u) : 0;
         }
+        int s0 = 0, s1 = 0;
+#pragma unroll
+        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) { s0 += rowsum[v + kHalfPatch]; s1 += v * rowsum[v + kHalfPatch]; }
+        m10 = u * s0;
+        m01 = s1;
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
     m01 = __reduce_add_sync(0xffffffffu, m01);

@@ -32,6 +32,16 @@ struct RansacArgs {
     int min_matches;            // reference kMinMatchesForPose
 };
 
+// tuning knobs (environment, read once): B200VO_FP_SETUP=shared|local, B200VO_FP_FALLBACK=inline|queue
+static int g_fp_setup_shared = -1, g_fp_fb_queue = -1;
+static void read_knobs() {
+    if (g_fp_setup_shared >= 0) return;
+    const char* a = getenv("B200VO_FP_SETUP");
+    g_fp_setup_shared = (a && a[0] == 's') ? 1 : 0;
+    const char* b = getenv("B200VO_FP_FALLBACK");
+    g_fp_fb_queue = (b && b[0] == 'q') ? 1 : 0;
+}
+
 // ---- phased five-point solver -------------------------------------------------------------
 // A thread-per-hypothesis solver diverges badly: hypotheses have 0..10 real roots and every root
 // needs a data-dependent number of iterations (measured: 10 of 32 lanes active).  So the work is
@@ -42,8 +52,8 @@ struct RansacArgs {
 //   score_kernel      warp   / bracket    : Sampson inlier count, 64-bit atomicMax per pair
 // The compact list carries (pair, hypothesis, solution index), so "first arg-max wins" does not
 // depend on the order in which brackets were appended.
-__global__ void __launch_bounds__(128, 4)
-fp_setup_kernel(PairView pv, RansacArgs ra) {
+template <bool SHARED>
+__device__ __forceinline__ void fp_setup_body(const PairView& pv, const RansacArgs& ra, double* s_M) {
     const int pair = blockIdx.y;
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= ra.nhyp) return;
@@ -65,9 +75,15 @@ fp_setup_kernel(PairView pv, RansacArgs ra) {
         x1[k][0] = pv.x1x[base + i]; x1[k][1] = pv.x1y[base + i];
         x2[k][0] = pv.x2x[base + i]; x2[k][1] = pv.x2y[base + i];
     }
-    geom::LocalMat M;
     geom::FivePointSetup S;
-    const bool ok = geom::five_point_setup(x1, x2, M, S);
+    bool ok;
+    if (SHARED) {
+        geom::StridedMat M{s_M + threadIdx.x, (int)blockDim.x};
+        ok = geom::five_point_setup(x1, x2, M, S);
+    } else {
+        geom::LocalMat M;
+        ok = geom::five_point_setup(x1, x2, M, S);
+    }
     pv.fp_ok[gid] = ok ? 1 : 0;
     if (!ok) return;
     const size_t stride = (size_t)gridDim.y * pv.nhyp_cap;      // element-major over the hypotheses of this launch
@@ -77,8 +93,32 @@ fp_setup_kernel(PairView pv, RansacArgs ra) {
     for (int e = 0; e < geom::kSetupDoubles; ++e) dst[(size_t)e * stride] = src[e];
 }
 
+__global__ void __launch_bounds__(128, 4)
+fp_setup_kernel(PairView pv, RansacArgs ra) { fp_setup_body<false>(pv, ra, nullptr); }
+
+// variant with the 10x20 matrix in shared memory (element-major / thread-minor, 200 KB per CTA)
 __global__ void __launch_bounds__(128)
-fp_isolate_kernel(PairView pv, RansacArgs ra) {
+fp_setup_kernel_shared(PairView pv, RansacArgs ra) {
+    extern __shared__ double s_M[];
+    fp_setup_body<true>(pv, ra, s_M);
+}
+
+__device__ __forceinline__ void emit_brackets(const PairView& pv, int gid, const geom::RootBracket* br, int nb) {
+    pv.nsol[gid] = nb;
+    if (nb == 0) return;
+    const unsigned pos = atomicAdd(pv.cand_count, (unsigned)nb);
+    for (int k = 0; k < nb; ++k) {
+        const unsigned p = pos + k;
+        if (p >= (unsigned)pv.cand_cap) break;
+        pv.cand_gid[p] = gid;
+        pv.cand_tag[p] = k | (br[k].reversed << 8);
+        pv.cand_a[p] = br[k].a;
+        pv.cand_b[p] = br[k].b;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+fp_isolate_kernel(PairView pv, RansacArgs ra, bool queue_fallback) {
     const int pair = blockIdx.y;
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= ra.nhyp) return;
@@ -90,20 +130,32 @@ fp_isolate_kernel(PairView pv, RansacArgs ra) {
         double c[11];
 #pragma unroll
         for (int i = 0; i < 11; ++i) c[i] = pv.fp_setup[(size_t)(75 + i) * stride + gid];     // FivePointSetup::c
-        nb = geom::five_point_isolate(c, br);
+        nb = geom::five_point_isolate(c, br, /*allow_fallback=*/!queue_fallback);
     }
-    pv.nsol[gid] = nb;
 #pragma unroll
     for (int k = 0; k < 10; ++k) pv.model_ok[(size_t)gid * 10 + k] = 0;
-    if (nb == 0) return;
-    const unsigned pos = atomicAdd(pv.cand_count, (unsigned)nb);
-    for (int k = 0; k < nb; ++k) {
-        const unsigned p = pos + k;
-        if (p >= (unsigned)pv.cand_cap) break;
-        pv.cand_gid[p] = gid;
-        pv.cand_tag[p] = k | (br[k].reversed << 8);
-        pv.cand_a[p] = br[k].a;
-        pv.cand_b[p] = br[k].b;
+    if (nb < 0) {                       // unreliable Sturm chain: queue for the dense exact pass
+        pv.nsol[gid] = 0;
+        pv.fb_gid[atomicAdd(pv.cand_count + 1, 1u)] = gid;
+        return;
+    }
+    emit_brackets(pv, gid, br, nb);
+}
+
+// The few hypotheses whose Sturm chain failed its parity check, packed densely: every lane of these
+// warps takes the slow exact path (derivative chain), instead of one lane stalling 31 others.
+__global__ void __launch_bounds__(128)
+fp_isolate_fallback_kernel(PairView pv, int npairs) {
+    const unsigned n = pv.cand_count[1];
+    const size_t stride = (size_t)npairs * pv.nhyp_cap;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int gid = pv.fb_gid[i];
+        double c[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) c[k] = pv.fp_setup[(size_t)(75 + k) * stride + gid];
+        geom::RootBracket br[10];
+        const int nb = geom::five_point_isolate(c, br, /*allow_fallback=*/true);
+        emit_brackets(pv, gid, br, nb);
     }
 }
 
@@ -133,6 +185,42 @@ fp_finish_kernel(PairView pv, int npairs) {
     }
 }
 
+// Inlier count of one model by one warp.  The Sampson test is evaluated in float first (one 16-byte
+// load and ~25 FFMA per point on the full-rate FP32 pipe); only points within a 0.3 % band of the
+// threshold -- where float rounding could flip the decision -- are re-evaluated with the exact
+// double-precision expression, so the count is identical to the all-double evaluation.
+__device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, int m, const double* E,
+                                                  const geom::SampsonThreshold& thr, int lane) {
+    const size_t base = (size_t)pair * pv.kp_cap;
+    const float4* __restrict__ xf = pv.xf + base;
+    float e[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) e[k] = (float)E[k];
+    const float tmid = (float)thr.tmid;
+    int cnt = 0;
+    for (int i0 = 0; i0 < m; i0 += 32) {
+        const int j = i0 + lane;
+        bool in = false;
+        if (j < m) {
+            const float4 p = xf[j];
+            const float a0 = fmaf(e[0], p.x, fmaf(e[1], p.y, e[2]));
+            const float a1 = fmaf(e[3], p.x, fmaf(e[4], p.y, e[5]));
+            const float a2 = fmaf(e[6], p.x, fmaf(e[7], p.y, e[8]));
+            const float b0 = fmaf(e[0], p.z, fmaf(e[3], p.w, e[6]));
+            const float b1 = fmaf(e[1], p.z, fmaf(e[4], p.w, e[7]));
+            const float num = fmaf(p.z, a0, fmaf(p.w, a1, a2));
+            const float den = fmaf(a0, a0, fmaf(a1, a1, fmaf(b0, b0, b1 * b1)));
+            const float lhs = num * num, rhs = tmid * den;
+            // float error of num is ~1e-7 absolute (cancellation of O(1) terms): |num| ~ 1.6e-3 at the
+            // threshold, so num^2 is good to ~2e-4 relative; 3e-3 leaves a 10x margin
+            if (fabsf(lhs - rhs) > 3e-3f * rhs) in = lhs < rhs;
+            else in = geom::sampson_inlier_fast(E, pv.x1x[base + j], pv.x1y[base + j], pv.x2x[base + j], pv.x2y[base + j], thr);
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, in));
+    }
+    return cnt;
+}
+
 // one warp per root bracket (model)
 __global__ void __launch_bounds__(256)
 score_kernel(PairView pv, RansacArgs ra) {
@@ -145,23 +233,12 @@ score_kernel(PairView pv, RansacArgs ra) {
         if (!pv.model_ok[(size_t)gid * 10 + s]) continue;
         const int pair = gid / pv.nhyp_cap, h = gid - pair * pv.nhyp_cap;
         const int m = pv.n_good[pair];
-        const size_t base = (size_t)pair * pv.kp_cap;
-        const double* __restrict__ x1x = pv.x1x + base;
-        const double* __restrict__ x1y = pv.x1y + base;
-        const double* __restrict__ x2x = pv.x2x + base;
-        const double* __restrict__ x2y = pv.x2y + base;
         const double* mp = pv.models + (size_t)gid * 90 + s * 9;
         double E[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) E[k] = mp[k];
         const geom::SampsonThreshold thr = geom::make_sampson_threshold(ra.thr2f);
-        int cnt = 0;
-        for (int i0 = 0; i0 < m; i0 += 32) {
-            const int j = i0 + lane;
-            bool in = false;
-            if (j < m) in = geom::sampson_inlier_fast(E, x1x[j], x1y[j], x2x[j], x2y[j], thr);
-            cnt += __popc(__ballot_sync(0xffffffffu, in));
-        }
+        const int cnt = warp_count_inliers(pv, pair, m, E, thr, lane);
         if (lane == 0) {
             if (pv.counts) pv.counts[(size_t)gid * 10 + s] = cnt;
             const unsigned long long packed =
@@ -172,12 +249,19 @@ score_kernel(PairView pv, RansacArgs ra) {
 }
 
 static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
-    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.cand_count, 0, sizeof(unsigned), ctx->stream));
+    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.cand_count, 0, 2 * sizeof(unsigned), ctx->stream));
     const dim3 grid(div_up(ra.nhyp, 128), npairs);
-    fp_setup_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra);
+    read_knobs();
+    if (g_fp_setup_shared) fp_setup_kernel_shared<<<grid, 128, 200 * sizeof(double) * 128, ctx->stream>>>(ctx->pairs, ra);
+    else fp_setup_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
-    fp_isolate_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra);
+    fp_isolate_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra, g_fp_fb_queue != 0);
     B200VO_LAUNCH_CHECK(ctx);
+    if (g_fp_fb_queue) {
+        const long expect_fb = std::max<long>(1, (long)npairs * ra.nhyp / 4);       // upper estimate; idle CTAs exit at once
+        fp_isolate_fallback_kernel<<<(int)std::min<long>(148 * 16, (expect_fb + 127) / 128), 128, 0, ctx->stream>>>(ctx->pairs, npairs);
+        B200VO_LAUNCH_CHECK(ctx);
+    }
     const long expect = (long)npairs * ra.nhyp * 5;               // ~4.9 roots per hypothesis
     const int blocks = (int)std::min<long>(148 * 16, std::max<long>(1, (expect + 127) / 128));
     fp_finish_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->pairs, npairs);
@@ -185,7 +269,11 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
     return B200VO_OK;
 }
 
-int init_ransac_kernels() { return B200VO_OK; }
+int init_ransac_kernels() {
+    cudaError_t e = cudaFuncSetAttribute(fp_setup_kernel_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * sizeof(double) * 128));
+    if (e != cudaSuccess) { set_error("fp_setup_kernel_shared smem attribute: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
+    return B200VO_OK;
+}
 
 __global__ void __launch_bounds__(256)
 finalize_kernel(PairView pv, RansacArgs ra) {
@@ -246,33 +334,33 @@ pose_decompose_kernel(PairView pv, int npairs) {
     geom::decompose_essential(pv.E + (size_t)pair * 9, c, c + 9, c + 18);
 }
 
+// thread = (point, candidate): 4x the threads, a quarter of the serial latency per thread
 __global__ void __launch_bounds__(128)
 pose_vote_kernel(PairView pv) {
     const int pair = blockIdx.y;
     if (!(pv.rec[pair].status & B200VO_ST_E_FOUND)) return;
     const int m = pv.n_good[pair];
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x * blockDim.x >= m) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= 4 * m) return;
+    const int i = t >> 2, k = t & 3;              // candidate order of cv::recoverPose: (R1,t), (R2,t), (R1,-t), (R2,-t)
     const size_t base = (size_t)pair * pv.kp_cap;
-    int c[4] = {0, 0, 0, 0};
+    int ok = 0;
     if (i < m && pv.inl[base + i]) {
         const double* cand = pv.pose_cand + (size_t)pair * 24;
-        double R1[9], R2[9], tp[3], tn[3];
+        double R[9], tt[3];
+        const double sg = (k >= 2) ? -1.0 : 1.0;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) { R1[k] = cand[k]; R2[k] = cand[9 + k]; }
+        for (int j = 0; j < 9; ++j) R[j] = cand[9 * (k & 1) + j];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { tp[k] = cand[18 + k]; tn[k] = -tp[k]; }
-        const double a = pv.x1x[base + i], b = pv.x1y[base + i], cc = pv.x2x[base + i], d = pv.x2y[base + i];
-        // candidate order of cv::recoverPose: (R1,t), (R2,t), (R1,-t), (R2,-t)
-        c[0] = geom::cheirality_ok(R1, tp, a, b, cc, d, 50.0);
-        c[1] = geom::cheirality_ok(R2, tp, a, b, cc, d, 50.0);
-        c[2] = geom::cheirality_ok(R1, tn, a, b, cc, d, 50.0);
-        c[3] = geom::cheirality_ok(R2, tn, a, b, cc, d, 50.0);
+        for (int j = 0; j < 3; ++j) tt[j] = sg * cand[18 + j];
+        ok = geom::cheirality_ok(R, tt, pv.x1x[base + i], pv.x1y[base + i], pv.x2x[base + i], pv.x2y[base + i], 50.0);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int w = __reduce_add_sync(0xffffffffu, c[k]);
-        if ((threadIdx.x & 31) == 0 && w) atomicAdd(&pv.pose_cnt[pair * 4 + k], w);
+    // lanes with equal (lane & 3) vote for the same candidate
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31;
+    if (lane < 4) {
+        const int w = __popc(bal & (0x11111111u << lane));
+        if (w) atomicAdd(&pv.pose_cnt[pair * 4 + lane], w);
     }
 }
 
@@ -312,7 +400,7 @@ int launch_recover_pose_masked(b200vo_ctx* ctx, int npairs, uint8_t* d_mask_out)
     PoseArgs pa{ctx->opt.min_valid_points, ctx->opt.min_inliers, d_mask_out};
     pose_decompose_kernel<<<div_up(npairs, 64), 64, 0, ctx->stream>>>(ctx->pairs, npairs);
     B200VO_LAUNCH_CHECK(ctx);
-    pose_vote_kernel<<<dim3(div_up(ctx->pairs.kp_cap, 128), npairs), 128, 0, ctx->stream>>>(ctx->pairs);
+    pose_vote_kernel<<<dim3(div_up(4 * ctx->pairs.kp_cap, 128), npairs), 128, 0, ctx->stream>>>(ctx->pairs);
     B200VO_LAUNCH_CHECK(ctx);
     pose_select_kernel<<<div_up(npairs, 64), 64, 0, ctx->stream>>>(ctx->pairs, pa, npairs);
     B200VO_LAUNCH_CHECK(ctx);
@@ -353,26 +441,19 @@ int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int3
 }
 
 // ------------------------------------------------------------------ parity hooks (device side)
-__global__ void score_models_kernel(const double* x1, const double* x2, int npts, const double* models, int nmodels,
-                                    float thr2f, int* counts) {
+__global__ void score_models_kernel(PairView pv, const double* models, int nmodels, float thr2f, int* counts) {
     const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= nmodels) return;
     double E[9];
     for (int k = 0; k < 9; ++k) E[k] = models[(size_t)w * 9 + k];
-    int cnt = 0;
-    for (int i0 = 0; i0 < npts; i0 += 32) {
-        const int i = i0 + lane;
-        bool in = false;
-        if (i < npts) in = geom::sampson_inlier(E, x1[2 * i], x1[2 * i + 1], x2[2 * i], x2[2 * i + 1], thr2f);
-        cnt += __popc(__ballot_sync(0xffffffffu, in));
-    }
+    const geom::SampsonThreshold thr = geom::make_sampson_threshold(thr2f);
+    const int cnt = warp_count_inliers(pv, 0, pv.n_good[0], E, thr, lane);      // points staged in pair 0
     if (lane == 0) counts[w] = cnt;
 }
 
-int launch_score_models(b200vo_ctx* ctx, const double* d_x1, const double* d_x2, int npts, const double* d_models,
-                        int nmodels, float thr2f, int* d_counts) {
-    score_models_kernel<<<div_up(nmodels, 8), 256, 0, ctx->stream>>>(d_x1, d_x2, npts, d_models, nmodels, thr2f, d_counts);
+int launch_score_models(b200vo_ctx* ctx, const double* d_models, int nmodels, float thr2f, int* d_counts) {
+    score_models_kernel<<<div_up(nmodels, 8), 256, 0, ctx->stream>>>(ctx->pairs, d_models, nmodels, thr2f, d_counts);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
