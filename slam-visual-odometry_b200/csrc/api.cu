@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -88,6 +89,24 @@ struct StageClock {
     void mark() { if (ctx->timing && n < 16) cudaEventRecord(ctx->ev[n++], ctx->stream); }
     float ms(int i) const { float v = 0.f; if (ctx->timing && i + 1 < n) cudaEventElapsedTime(&v, ctx->ev[i], ctx->ev[i + 1]); return v; }
 };
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int encode_level_map(EncodeTiledFn fn, CUtensorMap* out, uint8_t* base, const LevelGeom& g, size_t slot_bytes, int slots,
+                            int box_w, int box_h) {
+    const cuuint64_t dims[3] = {(cuuint64_t)g.w, (cuuint64_t)g.h, (cuuint64_t)slots};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)slot_bytes};       // bytes, multiples of 16
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base + g.offset, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for level %dx%d box %dx%d", (int)r, g.w, g.h, box_w, box_h); return B200VO_ERR_CUDA; }
+    return B200VO_OK;
+}
 
 static bool slot_ok(const b200vo_ctx* ctx, int s) { return s >= 0 && s < ctx->store.slots; }
 
@@ -251,6 +270,18 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         }
         TRY(dev_alloc(ctx, &ctx->d_tab, (size_t)tab_total));
         TRYCUDA(cudaMemcpy(ctx->d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    {   // TMA descriptors
+        ctx->use_tma = true;
+        if (const char* v = getenv("B200VO_TMA")) ctx->use_tma = (atoi(v) != 0);
+        void* fnp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        TRYCUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qres));
+        if (!fnp || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled entry point unavailable"); b200vo_destroy(ctx); return B200VO_ERR_CUDA; }
+        for (int l = 0; l < kLevels; ++l) {
+            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_fast[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kFastBoxW, kFastBoxH));
+            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_blur[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kBlurBoxW, kBlurBoxH));
+        }
     }
     TRY(upload_brief_pattern());
     TRY(init_ransac_kernels());

@@ -10,13 +10,15 @@
 // Every rounding is written explicitly (__fmul_rn/__fmaf_rn/__fadd_rn) so the compiler's FMA
 // contraction setting cannot change the result.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace b200vo {
 
 constexpr int BL_W = 128, BL_H = 32;
-constexpr int BL_HALO = 4;                              // 3 needed; 4 keeps the staged rows word-aligned
-constexpr int BL_SWW = (BL_W + 2 * BL_HALO) / 4;        // 34 words per staged row
+constexpr int BL_HALO = 16;                             // 3 needed; 16 keeps the TMA box start 16-byte aligned
+constexpr int BL_SWW = (BL_W + 2 * BL_HALO) / 4;        // 40 words per staged row
 constexpr int BL_SH = BL_H + 6;                         // 38 staged rows
+static_assert(BL_SWW * 4 == kBlurBoxW && BL_SH == kBlurBoxH, "TMA box must match the staged tile");
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -27,8 +29,9 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // Each thread produces 4 horizontally adjacent pixels in both passes: the row pass reads 3 aligned
 // shared-memory words (10 bytes) for 4 outputs, the column pass 7 float4.
 __global__ void __launch_bounds__(256)
-blur_kernel(StoreView sv, int level, int first_slot) {
-    __shared__ uint32_t s_in[BL_SH][BL_SWW];
+blur_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+    __shared__ __align__(128) uint32_t s_in[BL_SH][BL_SWW];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) float s_row[BL_SH][BL_W];
     // kernel taps as the float32 bit patterns OpenCV's getGaussianKernel(7, 2, CV_32F) yields
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu),
@@ -40,32 +43,66 @@ blur_kernel(StoreView sv, int level, int first_slot) {
     const int ox = blockIdx.x * BL_W, oy = blockIdx.y * BL_H;
     const int tid = threadIdx.x;
 
-    // stage rows oy-3 .. oy+BL_H+2, bytes ox-4 .. ox+BL_W+3 (BORDER_REFLECT_101 at the image edges)
-    for (int i = tid; i < BL_SH * BL_SWW; i += 256) {
-        const int ty = i / BL_SWW, wx = i - ty * BL_SWW;
-        const int gy = reflect101(min(oy - 3 + ty, g.h + 2), g.h);
-        const int gx = ox - BL_HALO + 4 * wx;
-        const uint8_t* row = img + (size_t)gy * g.pitch;
-        uint32_t v;
-        if (gx >= 0 && gx + 3 < g.w) {
-            v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-        } else {
-            v = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int x = reflect101(min(gx + b, g.w + 2), g.w);
-                v |= (uint32_t)__ldg(row + x) << (8 * b);
+    // stage rows oy-3 .. oy+BL_H+2, bytes ox-16 .. ox+BL_W+15 (BORDER_REFLECT_101 at the image edges)
+    const bool border = (ox == 0) || (ox + BL_W + 3 > g.w) || (oy < 3) || (oy + BL_H + 3 > g.h);
+    if (use_tma) {
+        if (tid == 0) { tma::mbar_init(&s_bar, 1); tma::fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            tma::mbar_arrive_expect_tx(&s_bar, BL_SH * BL_SWW * 4);
+            tma::load_3d(&s_in[0][0], &tmap, &s_bar, ox - BL_HALO, oy - 3, slot);
+        }
+        tma::mbar_wait(&s_bar, 0);
+        if (border) {
+            // the hardware zero-fills outside the image; OpenCV reflects (101).  Every reflected
+            // source pixel lies inside this tile, so the halo is patched from shared memory:
+            // columns first (all staged rows), then whole rows.
+            uint8_t* sb = reinterpret_cast<uint8_t*>(&s_in[0][0]);
+            const int rowb = BL_SWW * 4;
+            __syncthreads();
+            for (int i = tid; i < BL_SH * 6; i += 256) {
+                const int ty = i / 6, k = i - ty * 6;
+                const int x = (k < 3) ? (-1 - k) : (g.w + (k - 3));
+                const int xs = (k < 3) ? (1 + k) : (g.w - 2 - (k - 3));
+                const int c = x - (ox - BL_HALO), cs = xs - (ox - BL_HALO);
+                if (c >= 0 && c < rowb && cs >= 0 && cs < rowb) sb[ty * rowb + c] = sb[ty * rowb + cs];
+            }
+            __syncthreads();
+            for (int i = tid; i < 6 * BL_SWW; i += 256) {
+                const int k = i / BL_SWW, wx = i - k * BL_SWW;
+                const int y = (k < 3) ? (-1 - k) : (g.h + (k - 3));
+                const int ys = (k < 3) ? (1 + k) : (g.h - 2 - (k - 3));
+                const int r = y - (oy - 3), rs = ys - (oy - 3);
+                if (r >= 0 && r < BL_SH && rs >= 0 && rs < BL_SH) s_in[r][wx] = s_in[rs][wx];
             }
         }
-        s_in[ty][wx] = v;
+    } else {
+        for (int i = tid; i < BL_SH * BL_SWW; i += 256) {
+            const int ty = i / BL_SWW, wx = i - ty * BL_SWW;
+            const int gy = reflect101(min(max(oy - 3 + ty, -3), g.h + 2), g.h);
+            const int gx = ox - BL_HALO + 4 * wx;
+            const uint8_t* row = img + (size_t)gy * g.pitch;
+            uint32_t v;
+            if (gx >= 0 && gx + 3 < g.w) {
+                v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+            } else {
+                v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int x = reflect101(min(max(gx + b, -3), g.w + 2), g.w);
+                    v |= (uint32_t)__ldg(row + x) << (8 * b);
+                }
+            }
+            s_in[ty][wx] = v;
+        }
     }
     __syncthreads();
 
     // row pass: s = k0*p[-3]; s = fma(p[-3+i], k[i], s), i = 1..6   (sequential, as OpenCV)
     for (int i = tid; i < BL_SH * (BL_W / 4); i += 256) {
         const int ty = i / (BL_W / 4), q = i - ty * (BL_W / 4);
-        // outputs x = 4q..4q+3 need staged bytes 4q+1 .. 4q+10 -> words q, q+1, q+2
-        const uint32_t w0 = s_in[ty][q], w1 = s_in[ty][q + 1], w2 = s_in[ty][q + 2];
+        // outputs x = 4q..4q+3 need staged bytes 4q+13 .. 4q+22 -> words q+3, q+4, q+5
+        const uint32_t w0 = s_in[ty][q + 3], w1 = s_in[ty][q + 4], w2 = s_in[ty][q + 5];
         float p[10];
         p[0] = (float)((w0 >> 8) & 0xFF); p[1] = (float)((w0 >> 16) & 0xFF); p[2] = (float)(w0 >> 24);
         p[3] = (float)(w1 & 0xFF); p[4] = (float)((w1 >> 8) & 0xFF); p[5] = (float)((w1 >> 16) & 0xFF); p[6] = (float)(w1 >> 24);
@@ -116,7 +153,7 @@ int launch_blur(b200vo_ctx* ctx, int first_slot, int n) {
     for (int l = 0; l < kLevels; ++l) {
         const LevelGeom& g = ctx->store.lv[l];
         dim3 grid(div_up(g.w, BL_W), div_up(g.h, BL_H), n);
-        blur_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot);
+        blur_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_blur[l], ctx->use_tma ? 1 : 0);
         B200VO_LAUNCH_CHECK(ctx);
     }
     return B200VO_OK;

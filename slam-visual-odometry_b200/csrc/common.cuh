@@ -1,5 +1,6 @@
 // Shared declarations of the b200vo CUDA library: context, level geometry, launch helpers.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -15,6 +16,9 @@ constexpr int kEdge = 31;          // ORB edgeThreshold (reference src/visual_od
 constexpr int kHalfPatch = 15;     // patchSize 31
 constexpr int kDescBytes = 32;
 constexpr int kMaxSolutions = 10;  // real roots of the degree-10 five-point polynomial
+// TMA boxes (bytes x rows) of the tile consumers; the inner extent must be a multiple of 16 bytes
+constexpr int kFastBoxW = 96, kFastBoxH = 38;      // fast.cu: 70x38 pixel tile + up to 15 bytes of alignment shift
+constexpr int kBlurBoxW = 160, kBlurBoxH = 38;     // blur.cu: 128+2*16 x 32+6
 
 struct LevelGeom {
     int w, h, pitch;       // pitch: bytes per row, multiple of 128 (TMA needs 16)
@@ -109,6 +113,10 @@ struct b200vo_ctx {
     uint8_t* d_stage[2]; size_t stage_bytes[2];
     cudaEvent_t stage_ready[2], stage_free[2];
     int stage_idx;
+    // TMA descriptors: one per pyramid level and consumer (the box shape is part of the descriptor)
+    CUtensorMap tmap_fast[b200vo::kLevels];
+    CUtensorMap tmap_blur[b200vo::kLevels];
+    bool use_tma;
     int64_t launches;
     bool timing;
     b200vo_stage_times times;

@@ -10,6 +10,7 @@
 // Output: an unordered candidate list per (slot, level), packed (y<<20 | x<<8 | score), plus a
 // 256-bin score histogram used by the selection kernel to find the retainBest(2 N_l) cut.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace b200vo {
 
@@ -18,8 +19,9 @@ namespace b200vo {
 // tile origin), so staging costs ~4 instructions per pixel instead of one byte load each.
 constexpr int FT_W = 62, FT_H = 30;
 constexpr int FT_CW = 64, FT_CH = 32;            // score tile
-constexpr int FT_SWW = 20, FT_SW = FT_SWW * 4;   // pixel tile row: 20 words = 80 bytes (>= 70 + 3)
+constexpr int FT_SWW = 24, FT_SW = FT_SWW * 4;   // pixel tile row: 24 words = 96 bytes (>= 70 + 15 alignment shift)
 constexpr int FT_SH = FT_CH + 6;                 // 38 rows
+static_assert(FT_SW == kFastBoxW && FT_SH == kFastBoxH, "TMA box must match the pixel tile");
 
 __device__ __forceinline__ bool has_arc9(uint32_t m) {
     uint32_t r = m | (m << 16);
@@ -46,8 +48,9 @@ __device__ __forceinline__ void load_ring(const uint8_t* p, int* v) {
 //   3. corners: corner score (max over 9-arcs of the arc minimum, minus 1) -> score tile
 //   4. corners: strict 3x3 non-max suppression + border filter -> candidate list + histogram
 __global__ void __launch_bounds__(256)
-fast_kernel(StoreView sv, int level, int first_slot) {
-    __shared__ __align__(16) uint8_t s_img[FT_SH * FT_SW];
+fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+    __shared__ __align__(128) uint8_t s_img[FT_SH * FT_SW];
+    __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(4) uint8_t s_score[FT_CH * FT_CW];
     __shared__ uint16_t s_surv[FT_CH * FT_CW];
     __shared__ uint16_t s_corn[FT_CH * FT_CW];
@@ -61,10 +64,22 @@ fast_kernel(StoreView sv, int level, int first_slot) {
     const int oy = kEdge + blockIdx.y * FT_H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px0 = ox - 4, py0 = oy - 4;           // pixel-tile origin (>= 27: always inside the image)
-    const int x0 = px0 & ~3, shift = px0 - x0;
+    // TMA needs a 16-byte aligned inner coordinate, the word-load path a 4-byte aligned one
+    const int x0 = use_tma ? (px0 & ~15) : (px0 & ~3), shift = px0 - x0;
     if (tid == 0) { s_nsurv = 0; s_ncorn = 0; s_n = 0; }
 
-    {
+    if (use_tma) {
+        // one thread issues the whole 96x38-byte box; everybody waits on the mbarrier
+        if (tid == 0) { tma::mbar_init(&s_bar, 1); tma::fence_mbar_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            tma::mbar_arrive_expect_tx(&s_bar, FT_SH * FT_SW);
+            tma::load_3d(s_img, &tmap, &s_bar, x0, py0, slot);
+        }
+        uint32_t* sc32 = reinterpret_cast<uint32_t*>(s_score);
+        for (int i = tid; i < FT_CH * FT_CW / 4; i += 256) sc32[i] = 0;
+        tma::mbar_wait(&s_bar, 0);
+    } else {
         uint32_t* s32 = reinterpret_cast<uint32_t*>(s_img);
         const int wmax = g.pitch / 4 - 1;
         for (int i = tid; i < FT_SH * FT_SWW; i += 256) {
@@ -225,7 +240,7 @@ int launch_fast(b200vo_ctx* ctx, int first_slot, int n) {
         const int iw = g.w - 2 * kEdge, ih = g.h - 2 * kEdge;
         if (iw <= 0 || ih <= 0) continue;
         dim3 grid(div_up(iw, FT_W), div_up(ih, FT_H), n);
-        fast_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot);
+        fast_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], ctx->use_tma ? 1 : 0);
         B200VO_LAUNCH_CHECK(ctx);
     }
     return B200VO_OK;
