@@ -58,6 +58,7 @@ typedef enum {
 #define B200VO_ST_E_FOUND 2         /* >= 8 matches and a model was found: R,t valid (:189,:218) */
 #define B200VO_ST_POSE_OK 4         /* valid_points >= 10 and inliers >= 12 -> scale 0.3 (:270-277,:352) */
 #define B200VO_ST_OVERFLOW 256      /* an internal list overflowed; results for this pair are not exact */
+#define B200VO_ST_ROUNDS_SHIFT 16    /* adaptive mode: bits 16..23 = number of 128-hypothesis blocks evaluated */
 
 #define B200VO_MATCH_CROSSCHECK 0   /* reference behaviour: cross-check + adaptive threshold */
 #define B200VO_MATCH_RATIO 1        /* extension: Lowe ratio test on 2-NN (no cross-check) */
@@ -73,7 +74,8 @@ typedef struct b200vo_options {
     int32_t ransac_hypotheses;      /* five-point hypotheses per pair; default 1024 (>= OpenCV maxIters 1000) */
     int32_t match_mode;             /* B200VO_MATCH_* */
     float ratio;                    /* ratio-test threshold for B200VO_MATCH_RATIO (0.75) */
-    int32_t reserved0;
+    int32_t ransac_adaptive;        /* 0 (default): evaluate all ransac_hypotheses; 1: OpenCV's adaptive stopping rule
+                                     * (confidence 0.999, reference :215), checked after every block of 128 hypotheses */
     uint64_t ransac_seed;           /* hypothesis samples are f(seed, pair id, hypothesis index) */
     double ransac_threshold_px;     /* 2.0 (:215) */
     double max_hamming;             /* 35.0 (:147) */

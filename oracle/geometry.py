@@ -186,6 +186,39 @@ def ransac_shared(x1, x2, thr, samples, solver=five_point):
     return best
 
 
+def ransac_update_num_iters(p, ep, model_points, max_iters):
+    """cv::RANSACUpdateNumIters (OpenCV calib3d/ptsetreg.cpp): iterations needed for confidence p at
+    outlier ratio ep.  findEssentialMat calls it after every improvement of the best model."""
+    import math
+    import sys
+    p = min(max(p, 0.0), 1.0)
+    ep = min(max(ep, 0.0), 1.0)
+    num = max(1.0 - p, sys.float_info.min)
+    denom = 1.0 - (1.0 - ep) ** model_points
+    if denom < sys.float_info.min:
+        return 0
+    num = math.log(num)
+    denom = math.log(denom)
+    if denom >= 0 or -num >= max_iters * (-denom):
+        return max_iters
+    return int(np.rint(num / denom))
+
+
+def adaptive_blocks(best_count_after_block, m, max_iters, block=128, conf=0.999):
+    """The product's adaptive mode: hypotheses are evaluated in blocks of `block`; after each block
+    the stopping rule above is applied to the best inlier count so far.  Returns the number of blocks
+    evaluated given the best count after each block."""
+    nb = -(-max_iters // block)
+    for k in range(nb):
+        cnt = best_count_after_block[k]
+        niters = max_iters
+        if m > 0 and cnt >= 5:
+            niters = ransac_update_num_iters(conf, (m - cnt) / m, 5, max_iters)
+        if min((k + 1) * block, max_iters) >= niters or m < 5:
+            return k + 1
+    return nb
+
+
 # ----------------------------------------------------------------------------- recoverPose
 def decompose_essential(E):
     U, _, Vt = np.linalg.svd(E)

@@ -21,7 +21,7 @@ ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_NOT_READY, ERR_ALLOC = -1, -2, -3, -4, 
 class Options(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("nfeatures", C.c_int32),
                 ("fast_threshold", C.c_int32), ("max_frames", C.c_int32), ("ransac_hypotheses", C.c_int32),
-                ("match_mode", C.c_int32), ("ratio", C.c_float), ("reserved0", C.c_int32),
+                ("match_mode", C.c_int32), ("ratio", C.c_float), ("ransac_adaptive", C.c_int32),
                 ("ransac_seed", C.c_uint64), ("ransac_threshold_px", C.c_double), ("max_hamming", C.c_double),
                 ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
                 ("min_matches_for_pose", C.c_int32), ("min_valid_points", C.c_int32), ("min_inliers", C.c_int32),

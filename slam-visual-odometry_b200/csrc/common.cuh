@@ -78,6 +78,8 @@ struct PairView {
     int* nsol;                 // [pairs][nhyp_cap]
     int* counts;               // [pairs][nhyp_cap][10] inlier counts (parity hook; may be NULL)
     uint8_t* model_ok;         // [pairs][nhyp_cap][10] 1 where models[...] holds a solution
+    int* done;                 // [pairs] adaptive RANSAC: 1 once the stopping rule is met
+    int* rounds;               // [pairs] adaptive RANSAC: blocks of 128 hypotheses evaluated
     double* pose_cand;         // [pairs][24] R1(9) R2(9) t(3) from decomposeEssentialMat
     int* pose_cnt;             // [pairs][4] cheirality votes of the four candidates
     // phased five-point solver work space (ransac.cu)
@@ -117,6 +119,7 @@ struct b200vo_ctx {
     CUtensorMap tmap_fast[b200vo::kLevels];
     CUtensorMap tmap_blur[b200vo::kLevels];
     bool use_tma;
+    int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC (default), 2: full Harley-Seal (4 POPC)
     int64_t launches;
     bool timing;
     b200vo_stage_times times;

@@ -174,8 +174,7 @@ static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_
     while (chunk > 64 && (long)row_tiles * div_up(n2max, chunk) * npairs < 4 * 148) chunk >>= 1;
     a.chunk = chunk;
     dim3 grid(div_up(n2max, chunk), row_tiles, npairs);
-    static int csa = -1;
-    if (csa < 0) { const char* v = getenv("B200VO_MATCH_CSA"); csa = v ? atoi(v) : 1; if (csa < 0 || csa > 2) csa = 1; }
+    const int csa = ctx->match_csa;
 #define LAUNCH_MATCH(RR) \
     do { if (csa == 2) match_kernel<RR, 2><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \
          else if (csa == 1) match_kernel<RR, 1><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \

@@ -27,7 +27,9 @@ struct RansacArgs {
     const int32_t* samples;     // [pairs][nhyp][5] or NULL (draw on device)
     uint64_t seed;
     int64_t first_pair_id;
-    int nhyp;
+    int nhyp;                   // total hypotheses per pair (cap in adaptive mode)
+    int h0, nround;             // this launch covers hypotheses [h0, h0 + nround)
+    int adaptive;               // 1: pairs whose stopping rule is met (pv.done) are skipped
     float thr2f;                // (float)(thr*thr), thr in normalised units
     int min_matches;            // reference kMinMatchesForPose
 };
@@ -55,8 +57,9 @@ static void read_knobs() {
 template <bool SHARED>
 __device__ __forceinline__ void fp_setup_body(const PairView& pv, const RansacArgs& ra, double* s_M) {
     const int pair = blockIdx.y;
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= ra.nhyp) return;
+    const int h = ra.h0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= ra.h0 + ra.nround) return;
+    if (ra.adaptive && pv.done[pair]) return;
     const int gid = pair * pv.nhyp_cap + h;
     const int m = pv.n_good[pair];
     if (m < ra.min_matches || m < 5) { pv.fp_ok[gid] = 0; return; }
@@ -120,8 +123,9 @@ __device__ __forceinline__ void emit_brackets(const PairView& pv, int gid, const
 __global__ void __launch_bounds__(128)
 fp_isolate_kernel(PairView pv, RansacArgs ra, bool queue_fallback) {
     const int pair = blockIdx.y;
-    const int h = blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= ra.nhyp) return;
+    const int h = ra.h0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= ra.h0 + ra.nround) return;
+    if (ra.adaptive && pv.done[pair]) return;
     const int gid = pair * pv.nhyp_cap + h;
     int nb = 0;
     geom::RootBracket br[10];
@@ -250,7 +254,7 @@ score_kernel(PairView pv, RansacArgs ra) {
 
 static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.cand_count, 0, 2 * sizeof(unsigned), ctx->stream));
-    const dim3 grid(div_up(ra.nhyp, 128), npairs);
+    const dim3 grid(div_up(ra.nround, 128), npairs);
     read_knobs();
     if (g_fp_setup_shared) fp_setup_kernel_shared<<<grid, 128, 200 * sizeof(double) * 128, ctx->stream>>>(ctx->pairs, ra);
     else fp_setup_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra);
@@ -258,11 +262,11 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
     fp_isolate_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra, g_fp_fb_queue != 0);
     B200VO_LAUNCH_CHECK(ctx);
     if (g_fp_fb_queue) {
-        const long expect_fb = std::max<long>(1, (long)npairs * ra.nhyp / 4);       // upper estimate; idle CTAs exit at once
+        const long expect_fb = std::max<long>(1, (long)npairs * ra.nround / 4);       // upper estimate; idle CTAs exit at once
         fp_isolate_fallback_kernel<<<(int)std::min<long>(148 * 16, (expect_fb + 127) / 128), 128, 0, ctx->stream>>>(ctx->pairs, npairs);
         B200VO_LAUNCH_CHECK(ctx);
     }
-    const long expect = (long)npairs * ra.nhyp * 5;               // ~4.9 roots per hypothesis
+    const long expect = (long)npairs * ra.nround * 5;             // ~4.9 roots per hypothesis
     const int blocks = (int)std::min<long>(148 * 16, std::max<long>(1, (expect + 127) / 128));
     fp_finish_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->pairs, npairs);
     B200VO_LAUNCH_CHECK(ctx);
@@ -417,7 +421,38 @@ int launch_recover_pose(b200vo_ctx* ctx, int npairs) { return launch_recover_pos
 int launch_five_point_only(b200vo_ctx* ctx, const int32_t* d_samples, int nhyp) {
     RansacArgs ra;
     ra.samples = d_samples; ra.seed = 0; ra.first_pair_id = 0; ra.nhyp = nhyp; ra.thr2f = 0.f; ra.min_matches = 5;
+    ra.h0 = 0; ra.nround = nhyp; ra.adaptive = 0;
     return launch_five_point(ctx, ra, 1);
+}
+
+// cv::RANSACUpdateNumIters (OpenCV modules/calib3d/src/ptsetreg.cpp), as findEssentialMat applies it
+// after every improvement of the best model: p = confidence, ep = outlier ratio of the best model.
+__device__ __forceinline__ int ransac_update_num_iters(double p, double ep, int model_points, int max_iters) {
+    p = fmin(fmax(p, 0.0), 1.0);
+    ep = fmin(fmax(ep, 0.0), 1.0);
+    double num = fmax(1.0 - p, 2.2250738585072014e-308);
+    double denom = 1.0 - pow(1.0 - ep, (double)model_points);
+    if (denom < 2.2250738585072014e-308) return 0;
+    num = log(num);
+    denom = log(denom);
+    return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : __double2int_rn(num / denom);
+}
+
+// adaptive mode: after each block of hypotheses decide per pair whether OpenCV's loop would have ended
+__global__ void adaptive_update_kernel(PairView pv, int npairs, int evaluated, int max_iters, double confidence) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= npairs || pv.done[pair]) return;
+    pv.rounds[pair] += 1;
+    const int m = pv.n_good[pair];
+    const int cnt = (int)(pv.best[pair] >> 32);
+    int niters = max_iters;
+    if (m > 0 && cnt >= 5) niters = ransac_update_num_iters(confidence, (double)(m - cnt) / m, 5, max_iters);
+    if (evaluated >= niters || m < 5) pv.done[pair] = 1;
+}
+
+__global__ void stamp_rounds_kernel(PairView pv, int npairs) {
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair < npairs) pv.rec[pair].status |= (pv.rounds[pair] & 0xFF) << B200VO_ST_ROUNDS_SHIFT;
 }
 
 int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int32_t* d_samples, int nhyp) {
@@ -427,16 +462,32 @@ int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int3
     const double thr = ctx->opt.ransac_threshold_px / ((ctx->K[0] + ctx->K[1]) / 2.0);
     ra.thr2f = (float)(thr * thr);
     ra.min_matches = ctx->opt.min_matches_for_pose;
+    // an explicit sample list (parity hooks) is always evaluated completely
+    ra.adaptive = (ctx->opt.ransac_adaptive != 0 && d_samples == nullptr) ? 1 : 0;
     B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.best, 0, (size_t)npairs * sizeof(unsigned long long), ctx->stream));
-    { const int rc = launch_five_point(ctx, ra, npairs); if (rc) return rc; }
-    {
-        const long expect = (long)npairs * nhyp * 5;
+    const int block = ra.adaptive ? 128 : nhyp;
+    if (ra.adaptive) {
+        B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.done, 0, (size_t)npairs * sizeof(int), ctx->stream));
+        B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.rounds, 0, (size_t)npairs * sizeof(int), ctx->stream));
+    }
+    for (int h0 = 0; h0 < nhyp; h0 += block) {
+        ra.h0 = h0; ra.nround = std::min(block, nhyp - h0);
+        { const int rc = launch_five_point(ctx, ra, npairs); if (rc) return rc; }
+        const long expect = (long)npairs * ra.nround * 5;
         const int blocks = (int)std::min<long>(148 * 8, std::max<long>(1, (expect + 7) / 8));
         score_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pairs, ra);
         B200VO_LAUNCH_CHECK(ctx);
+        if (ra.adaptive) {
+            adaptive_update_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(ctx->pairs, npairs, h0 + ra.nround, nhyp, 0.999);
+            B200VO_LAUNCH_CHECK(ctx);
+        }
     }
     finalize_kernel<<<npairs, 256, 0, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
+    if (ra.adaptive) {
+        stamp_rounds_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(ctx->pairs, npairs);
+        B200VO_LAUNCH_CHECK(ctx);
+    }
     return B200VO_OK;
 }
 

@@ -152,3 +152,20 @@ def test_noise_image_ties_and_budget(built):
         ctx.detect(0, 1)
         kp, desc = ctx.get_features(0)
     _check_features(kp, desc, O.detect_and_compute(img, 800))
+
+
+def test_tma_and_word_staging_agree(built, seq_small, monkeypatch):
+    """The TMA tile loads (FAST, blur) and the plain word-load staging must give identical features."""
+    frames = seq_small[0]
+    out = {}
+    for tma in ("1", "0"):
+        monkeypatch.setenv("B200VO_TMA", tma)
+        with built.Context(640, 240, nfeatures=1000, max_frames=4, ransac_hypotheses=64) as ctx:
+            ctx.upload_frames(frames, 0)
+            ctx.detect(0, 3)
+            out[tma] = [ctx.get_features(s) for s in range(3)] + [ctx.get_pyramid_level(1, l, blurred=True) for l in range(8)]
+    for a, b in zip(out["1"], out["0"]):
+        if isinstance(a, tuple):
+            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+        else:
+            assert np.array_equal(a, b)

@@ -157,3 +157,36 @@ def test_too_few_matches_fallback(built):
         assert np.array_equal(rec["R"].reshape(3, 3), np.eye(3)) and not rec["t"].any()
         R, t = built.chain_pose(rec, np.eye(3), np.array([1.0, 2, 3]))
         assert np.array_equal(R, np.eye(3)) and np.array_equal(t, [1, 2, 3])
+
+
+def test_adaptive_ransac_equals_truncated_fixed(built, seq_kitti):
+    """ransac_adaptive=1 applies OpenCV's stopping rule (confidence 0.999) after every block of 128
+    hypotheses: the result must equal the fixed-H evaluation of exactly the hypotheses it looked at,
+    and the number of blocks must be what the rule gives for the best inlier counts."""
+    frames = seq_kitti[0]
+    H = 1024
+    with built.Context(1241, 376, nfeatures=NF, max_frames=4, ransac_hypotheses=H, ransac_adaptive=1) as ca, \
+         built.Context(1241, 376, nfeatures=NF, max_frames=4, ransac_hypotheses=H) as cf:
+        for c in (ca, cf):
+            c.upload_frames(frames, 0)
+            c.detect(0, 2)
+        ra, Ea, _ = ca.relative_pose(0, 1, pair_id=5)
+        rounds = (int(ra["status"]) >> 16) & 0xFF
+        assert 1 <= rounds <= H // 128
+        m = int(ra["n_matches"])
+        S = built.draw_samples(42, 5, H, m)
+        rf, Ef, _ = cf.relative_pose(0, 1, pair_id=5, samples=S[:rounds * 128])
+        assert np.array_equal(Ea, Ef)
+        for k in ("R", "t", "n_matches", "n_inliers", "n_valid", "best_hyp", "best_sol"):
+            assert np.array_equal(ra[k], rf[k]), k
+        assert (int(ra["status"]) & 0xFFFF) == (int(rf["status"]) & 0xFFFF)
+        # stopping rule: best count after each block, from fixed-H runs on growing prefixes
+        best_after = []
+        for k in range(rounds):
+            r, _, _ = cf.relative_pose(0, 1, pair_id=5, samples=S[:(k + 1) * 128])
+            best_after.append(int(r["n_inliers"]))
+        assert G.adaptive_blocks(best_after + [best_after[-1]] * 8, m, H) == rounds
+        # an explicit sample list is always evaluated completely, even in adaptive mode
+        rs, Es, _ = ca.relative_pose(0, 1, pair_id=5, samples=S)
+        rfull, Efull, _ = cf.relative_pose(0, 1, pair_id=5, samples=S)
+        assert np.array_equal(Es, Efull) and ((int(rs["status"]) >> 16) & 0xFF) == 0

@@ -117,3 +117,17 @@ def test_stress_shape_properties(built):
     assert np.array_equal(vq & 0xFFFF, perm.cpu().numpy()) and (vq >> 16 == 1).all()
     inv = np.empty(n, np.int64); inv[perm.cpu().numpy()] = np.arange(n)
     assert np.array_equal(vt & 0xFFFF, inv) and (vt >> 16 == 1).all()
+
+
+def test_popcount_variants_agree(built, monkeypatch):
+    """Plain 8-POPC, 2-CSA and full Harley-Seal Hamming kernels must return identical neighbours."""
+    rng = np.random.default_rng(99)
+    q = rng.integers(0, 256, (1500, 32), dtype=np.uint8); t = rng.integers(0, 256, (1400, 32), dtype=np.uint8)
+    q[:300] = t[:300]                      # exact duplicates: distance 0 and ties
+    ref = M.nearest(q, t)
+    for v in ("0", "1", "2"):
+        monkeypatch.setenv("B200VO_MATCH_CSA", v)
+        with built.Context(640, 240, nfeatures=500, max_frames=2, ransac_hypotheses=64) as c:
+            got = c.match_descriptors(q, t)
+        for g, r in zip(got, ref):
+            assert np.array_equal(g[0], r), "variant " + v
