@@ -253,8 +253,7 @@ def run_b200(args):
         if host_input:
             stream.synchronize()
             if rank == 0:   # host-side chaining of the whole trajectory (reference visual_odometry.cpp:340-374)
-                recs = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE)
-                state["traj"] = b200vo.chain_trajectory(recs)
+                state["traj"] = b200vo.chain_trajectory(recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy())
 
     def timed(host_input, steps, warmup):
         for _ in range(warmup):
@@ -299,8 +298,9 @@ def run_b200(args):
     ms_e2e_ad, _, _ = timed(True, args.steps, max(args.warmup, 3))
     rounds_ad = None
     if rank == 0:
-        rr = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE)
+        rr = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy()
         rounds_ad = float((((rr["status"] >> 16) & 0xFF) * 128).mean())
+        del rr
     stream.synchronize()
     ad_ctx, ad_stream = ctx, stream          # closed at teardown, after the tensors that touched its stream
     ctx, stream = main_ctx, stream_main
@@ -326,7 +326,7 @@ def run_b200(args):
                 ctx.process_pairs_device(p0, np_, f0 + done_pairs)
                 done_pairs += np_
                 st = ctx.stage_times()
-                for k in ("match_ms", "filter_ms", "ransac_ms", "pose_ms"):
+                for k in ("match_ms", "filter_ms", "ransac_ms", "pose_ms", "fp_setup_ms", "fp_isolate_ms", "fp_finish_ms", "score_ms"):
                     tot[k] = tot.get(k, 0.0) + st[k]
             prev_slot = (first + n - 1) % (B + 1)
             done_frames += n
@@ -354,26 +354,32 @@ def run_b200(args):
         ms = stage.get(key, 0.0)
         gbs = alg[name] * F / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         stages_out[name] = {"ms": round(ms, 3), "bound": "hbm", "algorithmic_bytes_per_frame": alg[name], "achieved_GBps": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)}
-    # matcher: N1*N2 pairs x 8 popc32, against the measured POPC-pipe rate
+    # matcher: N1*N2 descriptor pairs; algorithmically 8 popc32 each.  The kernel executes 6 (two
+    # carry-save adders move the rest onto the LOP3 pipe), so the POPC-pipe roofline is taken on the
+    # EXECUTED population counts against the rate measured by the XOR+POPC+ADD microbenchmark.
     kp_pairs = float(NF) * NF * npairs
     mm = stage.get("match_ms", 0.0)
-    popc_ach = kp_pairs * 8 / (mm * 1e-3) if mm > 0 else 0.0
-    stages_out["match"] = {"ms": round(mm, 3), "bound": "int_pipe(popc)", "popc32_per_pair": 8, "achieved_Gpopc_s": round(popc_ach / 1e9, 1),
-                           "peak_Gpopc_s": round(popc_rate / 1e9, 1), "frac": round(popc_ach / popc_rate, 4)}
-    for name in ("select", "filter", "ransac", "pose"):
+    popc_exec = kp_pairs * 6 / (mm * 1e-3) if mm > 0 else 0.0
+    stages_out["match"] = {"ms": round(mm, 3), "bound": "int_pipe(popc)", "algorithmic_popc32_per_pair": 8, "executed_popc32_per_pair": 6,
+                           "achieved_Gpopc_s": round(popc_exec / 1e9, 1), "peak_Gpopc_s": round(popc_rate / 1e9, 1),
+                           "frac": round(popc_exec / popc_rate, 4), "descriptor_pairs_per_s": round(kp_pairs / (mm * 1e-3), 0) if mm > 0 else 0}
+    for name in ("select", "filter", "ransac", "pose", "fp_setup", "fp_isolate", "fp_finish", "score"):
         stages_out[name] = {"ms": round(stage.get(name + "_ms", 0.0), 3)}
-    total_stage_ms = sum(v for v in stage.values())
-    dom = max(stage, key=stage.get) if stage else "match_ms"
+    # FP64 work of the scoring kernel: models x points x ~20 DFMA against 64 DFMA/clk/SM
+    kernels = {k: v for k, v in stage.items() if k not in ("ransac_ms",)}
+    total_stage_ms = sum(kernels.values())
+    dom = max(kernels, key=kernels.get) if kernels else "match_ms"
     if dom == "match_ms":
-        roof = {"kernel": "match_kernel", "bound": "int_pipe", "achieved": round(popc_ach / 1e9, 1), "peak": round(popc_rate / 1e9, 1),
-                "unit": "Gpopc32/s", "frac": round(popc_ach / popc_rate, 4), "traffic": None,
-                "peak_source": "XOR+POPC+ADD microbenchmark measured in this run (b200vo_measure_popc_rate)",
+        roof = {"kernel": "match_kernel<4,1>", "bound": "int_pipe", "achieved": round(popc_exec / 1e9, 1), "peak": round(popc_rate / 1e9, 1),
+                "unit": "Gpopc32/s", "frac": round(popc_exec / popc_rate, 4), "traffic": None,
+                "peak_source": "XOR+POPC+ADD microbenchmark measured in this run (b200vo_measure_popc_rate); not an HBM- or tensor-bound kernel: "
+                               "its DRAM traffic is ~0.2 MB per 9e6 descriptor pairs (profiles/)",
                 "share_of_step": round(mm / total_stage_ms, 3)}
     else:
         nm = dom[:-3]
-        s = stages_out.get(nm, {})
-        roof = {"kernel": nm, "bound": s.get("bound", "issue"), "achieved": s.get("achieved_GBps"), "peak": hbm_peak, "unit": "GB/s",
-                "frac": s.get("frac"), "traffic": None, "peak_source": peak_src, "share_of_step": round(stage[dom] / total_stage_ms, 3)}
+        sdict = stages_out.get(nm, {})
+        roof = {"kernel": nm, "bound": sdict.get("bound", "issue"), "achieved": sdict.get("achieved_GBps"), "peak": hbm_peak, "unit": "GB/s",
+                "frac": sdict.get("frac"), "traffic": None, "peak_source": peak_src, "share_of_step": round(stage[dom] / total_stage_ms, 3)}
     hb = max(("pyramid", "fast", "blur", "brief"), key=lambda n: stages_out[n]["ms"])
     roof_hbm = {"kernel": hb, "bound": "hbm", "achieved": stages_out[hb]["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": stages_out[hb]["frac"], "traffic": None, "peak_source": peak_src}
@@ -387,7 +393,7 @@ def run_b200(args):
         try:
             ncpu = os.cpu_count() or 1
             pairs = ncpu * (args.cpu_pairs or 8)
-            fr = h_frames[:min(F, pairs + 1)].numpy()
+            fr = h_frames[:min(F, pairs + 1)].numpy().copy()      # a copy: no view may outlive the pinned tensor
             v, n, dt = cpu_reference_throughput(fr, NF, min(pairs, len(fr) - 1), ncpu)
             import cv2
             cpu = {"value": round(v, 2), "unit": "pairs/s", "cores": min(ncpu, n), "kind": "port",
@@ -396,7 +402,7 @@ def run_b200(args):
             cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
 
     traj = state["traj"]
-    ok = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE)
+    ok = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy()
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -440,4 +446,9 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    # All results are printed and every context is closed; skip interpreter-shutdown destructors
+    # (torch's caching allocators may still hold events on streams owned by the closed contexts).
+    os._exit(rc)

@@ -267,6 +267,15 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
             int* xo = tab.data() + g.tab_off; int* xc = xo + dwp; int* yo = xc + dwp; int* yc = yo + dhp;
             resize_taps(s.w, g.w, xo, xc);
             resize_taps(s.h, g.h, yo, yc);
+            // the TMA resize kernel stages the source footprint of a 128x16 output tile in a fixed box
+            for (int x0 = 0; x0 < g.w; x0 += 128) {
+                const int xl = std::min(x0 + 128, g.w) - 1;
+                if (std::min(xo[xl] + 1, s.w - 1) - (xo[x0] & ~15) + 1 > kResizeBoxW) { set_error("resize footprint exceeds the TMA box (width)"); b200vo_destroy(ctx); return B200VO_ERR_BAD_ARG; }
+            }
+            for (int y0 = 0; y0 < g.h; y0 += 16) {
+                const int yl = std::min(y0 + 16, g.h) - 1;
+                if (std::min(yo[yl] + 1, s.h - 1) - yo[y0] + 1 > kResizeBoxH) { set_error("resize footprint exceeds the TMA box (height)"); b200vo_destroy(ctx); return B200VO_ERR_BAD_ARG; }
+            }
         }
         TRY(dev_alloc(ctx, &ctx->d_tab, (size_t)tab_total));
         TRYCUDA(cudaMemcpy(ctx->d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
@@ -283,6 +292,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         for (int l = 0; l < kLevels; ++l) {
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_fast[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kFastBoxW, kFastBoxH));
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_blur[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kBlurBoxW, kBlurBoxH));
+            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_resize[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kResizeBoxW, kResizeBoxH));
         }
     }
     TRY(upload_brief_pattern());
@@ -591,6 +601,13 @@ static int run_pairs(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_ove
     if (ctx->timing) {
         B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         ctx->times.match_ms = clk.ms(0); ctx->times.filter_ms = clk.ms(1); ctx->times.ransac_ms = clk.ms(2); ctx->times.pose_ms = clk.ms(3);
+        ctx->times.fp_setup_ms = ctx->times.fp_isolate_ms = ctx->times.fp_finish_ms = ctx->times.score_ms = 0.f;
+        if (!ctx->opt.ransac_adaptive || d_samples) {
+            cudaEventElapsedTime(&ctx->times.fp_setup_ms, ctx->ev[8], ctx->ev[9]);
+            cudaEventElapsedTime(&ctx->times.fp_isolate_ms, ctx->ev[9], ctx->ev[10]);
+            cudaEventElapsedTime(&ctx->times.fp_finish_ms, ctx->ev[10], ctx->ev[11]);
+            cudaEventElapsedTime(&ctx->times.score_ms, ctx->ev[11], ctx->ev[12]);
+        }
     }
     return B200VO_OK;
 }

@@ -19,6 +19,7 @@ constexpr int kMaxSolutions = 10;  // real roots of the degree-10 five-point pol
 // TMA boxes (bytes x rows) of the tile consumers; the inner extent must be a multiple of 16 bytes
 constexpr int kFastBoxW = 96, kFastBoxH = 38;      // fast.cu: 70x38 pixel tile + up to 15 bytes of alignment shift
 constexpr int kBlurBoxW = 160, kBlurBoxH = 38;     // blur.cu: 128+2*16 x 32+6
+constexpr int kResizeBoxW = 176, kResizeBoxH = 24; // pyramid.cu: source footprint of a 128x16 output tile at scale ~1.2
 
 struct LevelGeom {
     int w, h, pitch;       // pitch: bytes per row, multiple of 128 (TMA needs 16)
@@ -118,6 +119,7 @@ struct b200vo_ctx {
     // TMA descriptors: one per pyramid level and consumer (the box shape is part of the descriptor)
     CUtensorMap tmap_fast[b200vo::kLevels];
     CUtensorMap tmap_blur[b200vo::kLevels];
+    CUtensorMap tmap_resize[b200vo::kLevels];    // [l] = level l as the SOURCE of level l+1
     bool use_tma;
     int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC (default), 2: full Harley-Seal (4 POPC)
     int64_t launches;

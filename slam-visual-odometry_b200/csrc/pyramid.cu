@@ -10,6 +10,7 @@
 // resamples level l for ALL frames of the batch (grid.z = frame), so a 1000-frame sequence costs
 // 7 launches, not 7000.
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace b200vo {
 
@@ -78,6 +79,85 @@ resize_kernel(StoreView sv, const int* __restrict__ tab, int level, int first_sl
     *reinterpret_cast<uint32_t*>(dst) = packed;
 }
 
+// TMA variant: a 128x16 output tile.  Its source footprint (<= 171 x 22 px at scale ~1.2, start aligned
+// down to 16 bytes) arrives as one cp.async.bulk.tensor box; the horizontal 8.8 pass is done once per
+// source row into shared memory (u16), the vertical 16.16 pass reads two of those rows per output.
+// Per-thread column taps live in registers for the whole tile.  Same integer arithmetic, bit-exact.
+constexpr int RZ_W = 128, RZ_H = 16;
+
+__global__ void __launch_bounds__(256)
+resize_tma_kernel(StoreView sv, const int* __restrict__ tab, int level, int first_slot, const __grid_constant__ CUtensorMap tmap) {
+    __shared__ __align__(128) uint8_t s_src[kResizeBoxH * kResizeBoxW];
+    __shared__ __align__(16) uint16_t s_h[kResizeBoxH][RZ_W];
+    __shared__ __align__(8) uint64_t s_bar;
+    const LevelGeom gs = sv.lv[level - 1];
+    const LevelGeom gd = sv.lv[level];
+    const int dwp = (gd.w + 3) & ~3, dhp = (gd.h + 3) & ~3;
+    const int* __restrict__ xofs = tab + gd.tab_off;
+    const int* __restrict__ xc1 = xofs + dwp;
+    const int* __restrict__ yofs = xc1 + dwp;
+    const int* __restrict__ yc1 = yofs + dhp;
+    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    const int x0 = blockIdx.x * RZ_W, y0 = blockIdx.y * RZ_H;
+    const int tid = threadIdx.x;
+    const int sx0 = xofs[x0] & ~15;
+    const int sy0 = yofs[y0];
+    const int ylast = min(y0 + RZ_H, gd.h) - 1;
+    const int nrows = min(min(yofs[ylast] + 1, gs.h - 1) - sy0 + 1, kResizeBoxH);
+
+    if (tid == 0) { tma::mbar_init(&s_bar, 1); tma::fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_arrive_expect_tx(&s_bar, kResizeBoxH * kResizeBoxW);
+        tma::load_3d(s_src, &tmap, &s_bar, sx0, sy0, slot);
+    }
+    // this thread's four output columns: tap offsets relative to the box, in registers
+    const int cx = (tid & 31) * 4;
+    int o0[4], o1[4], c1[4];
+    {
+        const int4 xo = *reinterpret_cast<const int4*>(xofs + x0 + cx);
+        const int4 xc = *reinterpret_cast<const int4*>(xc1 + x0 + cx);
+        const int xos[4] = {xo.x, xo.y, xo.z, xo.w}, xcs[4] = {xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool valid = (x0 + cx + i) < gd.w;
+            o0[i] = valid ? xos[i] - sx0 : 0;
+            o1[i] = valid ? min(xos[i] + 1, gs.w - 1) - sx0 : 0;
+            c1[i] = xcs[i];
+        }
+    }
+    tma::mbar_wait(&s_bar, 0);
+
+    // horizontal pass, 8.8 fixed point: h = I[s]*(256-c1) + I[s+1]*c1
+    for (int r = tid >> 5; r < nrows; r += 8) {
+        const uint8_t* row = s_src + r * kResizeBoxW;
+        ushort4 h;
+        h.x = (uint16_t)(row[o0[0]] * (256 - c1[0]) + row[o1[0]] * c1[0]);
+        h.y = (uint16_t)(row[o0[1]] * (256 - c1[1]) + row[o1[1]] * c1[1]);
+        h.z = (uint16_t)(row[o0[2]] * (256 - c1[2]) + row[o1[2]] * c1[2]);
+        h.w = (uint16_t)(row[o0[3]] * (256 - c1[3]) + row[o1[3]] * c1[3]);
+        *reinterpret_cast<ushort4*>(&s_h[r][cx]) = h;
+    }
+    __syncthreads();
+
+    // vertical pass, 16.16 fixed point, +0.5, >> 16
+    if (x0 + cx >= gd.w) return;
+#pragma unroll
+    for (int k = 0; k < RZ_H / 8; ++k) {
+        const int y = y0 + (tid >> 5) + 8 * k;
+        if (y >= gd.h) break;
+        const int ys = yofs[y];
+        const int r0 = ys - sy0, r1 = min(ys + 1, gs.h - 1) - sy0;
+        const uint32_t cy1 = yc1[y], cy0 = 256 - cy1;
+        const ushort4 a = *reinterpret_cast<const ushort4*>(&s_h[r0][cx]);
+        const ushort4 b = *reinterpret_cast<const ushort4*>(&s_h[r1][cx]);
+        const uint32_t v0 = (a.x * cy0 + b.x * cy1 + 32768u) >> 16, v1 = (a.y * cy0 + b.y * cy1 + 32768u) >> 16;
+        const uint32_t v2 = (a.z * cy0 + b.z * cy1 + 32768u) >> 16, v3 = (a.w * cy0 + b.w * cy1 + 32768u) >> 16;
+        uint8_t* dst = sv.pyr + (size_t)slot * sv.slot_bytes + gd.offset + (size_t)y * gd.pitch + x0 + cx;
+        *reinterpret_cast<uint32_t*>(dst) = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+    }
+}
+
 int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int first_slot, int n) {
     const LevelGeom& g = ctx->store.lv[0];
     dim3 block(64), grid(div_up(div_up(g.w, 4), 64), g.h, n);
@@ -89,8 +169,13 @@ int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t 
 int launch_pyramid(b200vo_ctx* ctx, int first_slot, int n) {
     for (int l = 1; l < kLevels; ++l) {
         const LevelGeom& g = ctx->store.lv[l];
-        dim3 block(32, 8), grid(div_up(g.w, 128), div_up(g.h, 8), n);
-        resize_kernel<<<grid, block, 0, ctx->stream>>>(ctx->store, ctx->d_tab, l, first_slot);
+        if (ctx->use_tma) {
+            dim3 grid(div_up(g.w, RZ_W), div_up(g.h, RZ_H), n);
+            resize_tma_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, ctx->d_tab, l, first_slot, ctx->tmap_resize[l - 1]);
+        } else {
+            dim3 block(32, 8), grid(div_up(g.w, 128), div_up(g.h, 8), n);
+            resize_kernel<<<grid, block, 0, ctx->stream>>>(ctx->store, ctx->d_tab, l, first_slot);
+        }
         B200VO_LAUNCH_CHECK(ctx);
     }
     return B200VO_OK;

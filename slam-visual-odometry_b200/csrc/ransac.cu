@@ -256,9 +256,12 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
     B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.cand_count, 0, 2 * sizeof(unsigned), ctx->stream));
     const dim3 grid(div_up(ra.nround, 128), npairs);
     read_knobs();
+    const bool tm = ctx->timing && !ra.adaptive;        // events 8..12 bracket the four kernels
+    if (tm) cudaEventRecord(ctx->ev[8], ctx->stream);
     if (g_fp_setup_shared) fp_setup_kernel_shared<<<grid, 128, 200 * sizeof(double) * 128, ctx->stream>>>(ctx->pairs, ra);
     else fp_setup_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
+    if (tm) cudaEventRecord(ctx->ev[9], ctx->stream);
     fp_isolate_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra, g_fp_fb_queue != 0);
     B200VO_LAUNCH_CHECK(ctx);
     if (g_fp_fb_queue) {
@@ -268,8 +271,10 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
     }
     const long expect = (long)npairs * ra.nround * 5;             // ~4.9 roots per hypothesis
     const int blocks = (int)std::min<long>(148 * 16, std::max<long>(1, (expect + 127) / 128));
+    if (tm) cudaEventRecord(ctx->ev[10], ctx->stream);
     fp_finish_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->pairs, npairs);
     B200VO_LAUNCH_CHECK(ctx);
+    if (tm) cudaEventRecord(ctx->ev[11], ctx->stream);
     return B200VO_OK;
 }
 
@@ -477,6 +482,7 @@ int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int3
         const int blocks = (int)std::min<long>(148 * 8, std::max<long>(1, (expect + 7) / 8));
         score_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pairs, ra);
         B200VO_LAUNCH_CHECK(ctx);
+        if (ctx->timing && !ra.adaptive) cudaEventRecord(ctx->ev[12], ctx->stream);
         if (ra.adaptive) {
             adaptive_update_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(ctx->pairs, npairs, h0 + ra.nround, nhyp, 0.999);
             B200VO_LAUNCH_CHECK(ctx);
