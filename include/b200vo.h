@@ -23,6 +23,7 @@
  * b200vo_detect                     orb_detector_->detectAndCompute   src/visual_odometry.cpp:113
  * b200vo_get_features               frame.keypoints / frame.descriptors   src/frame.h:22-23
  * b200vo_match_descriptors          matcher_->match (cross-check NN)  src/visual_odometry.cpp:153
+ * b200vo_knn_match_descriptors      [ext] BFMatcher::knnMatch(k=2) for the ratio-test mode (same call site)
  * b200vo_match                      get_good_matches_of_features      src/visual_odometry.cpp:145-180
  * b200vo_relative_pose              estimate_relative_pose: findEssentialMat + recoverPose
  *                                     src/visual_odometry.cpp:182-281
@@ -61,7 +62,9 @@ typedef enum {
 #define B200VO_ST_ROUNDS_SHIFT 16    /* adaptive mode: bits 16..23 = number of 128-hypothesis blocks evaluated */
 
 #define B200VO_MATCH_CROSSCHECK 0   /* reference behaviour: cross-check + adaptive threshold */
-#define B200VO_MATCH_RATIO 1        /* extension: Lowe ratio test on 2-NN (no cross-check) */
+#define B200VO_MATCH_RATIO 1        /* [ext] Lowe ratio test on the 2 nearest trains (no cross-check) replaces the
+                                     * matcher_->match call (:153); the sort + adaptive threshold (:155-177) still
+                                     * follow.  n_cross then counts the matches that passed the ratio test. */
 
 typedef struct b200vo_ctx b200vo_ctx;
 
@@ -169,6 +172,13 @@ int b200vo_match_descriptors(b200vo_ctx* ctx, const uint8_t* q, int n1, const ui
 /* Device-resident variant used by the matcher stress benchmark; returns elapsed kernel ms. */
 int b200vo_match_descriptors_device(b200vo_ctx* ctx, const void* q_dev, int n1, const void* t_dev, int n2, int npairs,
                                     void* nnq_packed_dev, void* nnt_packed_dev, float* kernel_ms);
+
+/* [ext] cv::BFMatcher(NORM_HAMMING, false)::knnMatch(k = 2) on caller descriptors: the two nearest trains
+ * of every query ordered by (distance, trainIdx), as OpenCV orders them.  idx/dist: [npairs][n1][2],
+ * -1 where a neighbour does not exist (n2 < 2).  This is the matcher behind B200VO_MATCH_RATIO; the
+ * reference itself only cross-checks (src/visual_odometry.cpp:87). */
+int b200vo_knn_match_descriptors(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t, int n2, int npairs,
+                                 int32_t* idx, int32_t* dist);
 
 /* get_good_matches_of_features between two slots: cross-check (or ratio test), sort by
  * (distance, queryIdx), adaptive threshold.  out may be NULL. */

@@ -22,6 +22,8 @@ public:
         uint64_t ransac_seed = 42;
         int device = 0;
         int batch_frames = 64;             // frames per launch batch in process_sequence
+        bool ratio_test = false;           // false: cross-check (reference :87); true: Lowe ratio test on 2-NN
+        float ratio = 0.75f;
     };
 
     VisualOdometry(int image_width, int image_height);

@@ -63,6 +63,20 @@ def knn2_match(q, t):
     return order.astype(np.int32), np.take_along_axis(D, order, 1)
 
 
+def ratio_test_match(q, t, ratio=0.75):
+    """Lowe ratio test on knnMatch(k=2) (the north star's second matching mode; the reference itself
+    only cross-checks, visual_odometry.cpp:87): keep m iff m.distance < ratio * n.distance, evaluated
+    on DMatch's float32 distances; a query with fewer than two neighbours is dropped.
+    Returns (queryIdx, trainIdx, distance) ascending queryIdx."""
+    if len(q) == 0 or len(t) < 2:
+        z = np.zeros(0, np.int32)
+        return z, z.copy(), z.copy()
+    idx, dist = knn2_match(q, t)
+    keep = dist[:, 0].astype(np.float32) < np.float32(ratio) * dist[:, 1].astype(np.float32)
+    i = np.arange(len(q), dtype=np.int32)
+    return i[keep], idx[keep, 0], dist[keep, 0]
+
+
 def adaptive_threshold(dist_sorted):
     """visual_odometry.cpp:160-166: thr = min(max(3*min, 0.7*median), 35); median = sorted[size/2]."""
     mn = float(dist_sorted[0])
@@ -70,11 +84,12 @@ def adaptive_threshold(dist_sorted):
     return min(max(3.0 * mn, 0.7 * med), MAX_HAMMING_THRESHOLD)
 
 
-def good_matches(q, t):
+def good_matches(q, t, ratio=None):
     """get_good_matches_of_features (visual_odometry.cpp:145-180) in the canonical order
     (distance, queryIdx) -- std::sort there is unstable, so ties have no defined order.
+    ratio=None: the reference's cross-check matcher; a float: the ratio-test matcher in its place.
     Returns (queryIdx, trainIdx, distance, threshold, n_cross)."""
-    qi, ti, d = cross_check_match(q, t)
+    qi, ti, d = cross_check_match(q, t) if ratio is None else ratio_test_match(q, t, ratio)
     if len(qi) == 0:
         return qi, ti, d, 0.0, 0
     order = np.lexsort((qi, d))

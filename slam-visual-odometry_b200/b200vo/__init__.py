@@ -15,6 +15,7 @@ HOST_LIB_PATH = os.path.join(_PKG, "lib", "libb200vo_host.so")
 
 NLEVELS = 8
 ST_MATCHED, ST_E_FOUND, ST_POSE_OK, ST_OVERFLOW = 1, 2, 4, 256
+MATCH_CROSSCHECK, MATCH_RATIO = 0, 1
 ERR_BAD_ARG, ERR_CAPACITY, ERR_CUDA, ERR_NOT_READY, ERR_ALLOC = -1, -2, -3, -4, -5
 
 
@@ -48,7 +49,7 @@ EXPORTS = [
     "b200vo_synchronize", "b200vo_level_info", "b200vo_max_keypoints", "b200vo_upload_frames",
     "b200vo_upload_frames_device", "b200vo_detect", "b200vo_get_features", "b200vo_get_pyramid_level",
     "b200vo_get_fast_candidates", "b200vo_set_features", "b200vo_match_descriptors",
-    "b200vo_match_descriptors_device", "b200vo_match", "b200vo_relative_pose", "b200vo_process_pairs",
+    "b200vo_match_descriptors_device", "b200vo_knn_match_descriptors", "b200vo_match", "b200vo_relative_pose", "b200vo_process_pairs",
     "b200vo_process_pairs_device", "b200vo_five_point", "b200vo_score_models", "b200vo_recover_pose",
     "b200vo_draw_samples", "b200vo_chain_pose", "b200vo_chain_trajectory", "b200vo_measure_popc_rate", "b200vo_fundamental_from_essential", "b200vo_enable_timing",
     "b200vo_get_stage_times", "b200vo_kernel_launches", "b200vo_stream",
@@ -237,6 +238,19 @@ class Context:
             t = np.zeros(1, np.uint8)
         self._chk(self.lib.b200vo_match_descriptors(self.h, _p(q), n1, _p(t), n2, npairs, _p(nq), _p(dq), _p(nt), _p(dt)))
         return nq, dq, nt, dt
+
+    def knn2_match_descriptors(self, q, t, npairs=1):
+        """BFMatcher(NORM_HAMMING, False).knnMatch(k=2): (idx, dist), each (npairs, n1, 2); -1 = no neighbour."""
+        q = np.ascontiguousarray(q, np.uint8); t = np.ascontiguousarray(t, np.uint8)
+        n1 = q.shape[-2] if q.size else 0
+        n2 = t.shape[-2] if t.size else 0
+        idx = np.zeros((npairs, n1, 2), np.int32); dist = np.zeros((npairs, n1, 2), np.int32)
+        if n1 == 0:
+            return idx, dist
+        if t.size == 0:
+            t = np.zeros(1, np.uint8)
+        self._chk(self.lib.b200vo_knn_match_descriptors(self.h, _p(q), n1, _p(t), n2, npairs, _p(idx), _p(dist)))
+        return idx, dist
 
     def match_descriptors_device(self, q_ptr, n1, t_ptr, n2, npairs, nnq_ptr, nnt_ptr):
         ms = C.c_float()

@@ -168,6 +168,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     if (opt->max_frames < 2) { set_error("max_frames must be >= 2"); return B200VO_ERR_BAD_ARG; }
     if (opt->ransac_hypotheses < 1) { set_error("ransac_hypotheses must be >= 1"); return B200VO_ERR_BAD_ARG; }
     if (opt->fast_threshold < 1 || opt->fast_threshold > 200) { set_error("fast_threshold out of range"); return B200VO_ERR_BAD_ARG; }
+    if (opt->match_mode != B200VO_MATCH_CROSSCHECK && opt->match_mode != B200VO_MATCH_RATIO) { set_error("unknown match_mode %d", opt->match_mode); return B200VO_ERR_BAD_ARG; }
+    if (opt->match_mode == B200VO_MATCH_RATIO && !(opt->ratio > 0.f && opt->ratio <= 1.f)) { set_error("ratio must be in (0, 1]"); return B200VO_ERR_BAD_ARG; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -307,6 +309,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     pv.nhyp_cap = opt->ransac_hypotheses;
     TRY(dev_alloc(ctx, &pv.nnq, P * C));
     TRY(dev_alloc(ctx, &pv.nnt, P * C));
+    TRY(dev_alloc(ctx, &pv.nnq2, P * C));
     TRY(dev_alloc(ctx, &pv.good, P * C));
     TRY(dev_alloc(ctx, &pv.n_good, P));
     TRY(dev_alloc(ctx, &pv.n_cross, P));
@@ -563,6 +566,34 @@ int b200vo_match_descriptors(b200vo_ctx* ctx, const uint8_t* q, int n1, const ui
             if (nn_t) nn_t[(size_t)p * n2 + i] = (int32_t)(v & 0xFFFFu);
             if (dist_t) dist_t[(size_t)p * n2 + i] = (int32_t)(v >> 16);
         }
+    }
+    return B200VO_OK;
+}
+
+int b200vo_knn_match_descriptors(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t, int n2, int npairs,
+                                 int32_t* idx, int32_t* dist) {
+    if (!ctx || !q || !t || n1 < 0 || n2 < 0 || npairs <= 0 || !idx || !dist) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
+    if (n1 > 65536 || n2 > 65536) { set_error("at most 65536 descriptors per side (16-bit packed indices)"); return B200VO_ERR_BAD_ARG; }
+    for (size_t i = 0; i < (size_t)npairs * n1 * 2; ++i) { idx[i] = -1; dist[i] = -1; }
+    if (n1 == 0 || n2 == 0) return B200VO_OK;
+    B200VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const size_t qb = (size_t)npairs * n1 * kDescBytes, tb = (size_t)npairs * n2 * kDescBytes, ob = (size_t)npairs * n1 * 4;
+    int rc = ensure_scratch(ctx, round_up(qb, 256) + round_up(tb, 256) + 2 * round_up(ob, 256));
+    if (rc) return rc;
+    uint8_t* dq = static_cast<uint8_t*>(ctx->d_scratch);
+    uint8_t* dt = dq + round_up(qb, 256);
+    uint32_t* d1 = reinterpret_cast<uint32_t*>(dt + round_up(tb, 256));
+    uint32_t* d2 = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d1) + round_up(ob, 256));
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(dq, q, qb, cudaMemcpyHostToDevice, ctx->stream));
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(dt, t, tb, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = launch_match_knn2_raw(ctx, dq, n1, dt, n2, npairs, d1, d2))) return rc;
+    std::vector<uint32_t> h1((size_t)npairs * n1), h2((size_t)npairs * n1);
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(h1.data(), d1, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(h2.data(), d2, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < (size_t)npairs * n1; ++i) {
+        if (h1[i] != 0xFFFFFFFFu) { idx[2 * i] = (int32_t)(h1[i] & 0xFFFFu); dist[2 * i] = (int32_t)(h1[i] >> 16); }
+        if (h2[i] != 0xFFFFFFFFu) { idx[2 * i + 1] = (int32_t)(h2[i] & 0xFFFFu); dist[2 * i + 1] = (int32_t)(h2[i] >> 16); }
     }
     return B200VO_OK;
 }

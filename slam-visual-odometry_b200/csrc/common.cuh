@@ -64,6 +64,7 @@ struct PairView {
     // matching
     uint32_t* nnq;             // [pairs][kp_cap] packed (dist<<16 | idx)
     uint32_t* nnt;             // [pairs][kp_cap]
+    uint32_t* nnq2;            // [pairs][kp_cap] second-nearest train of every query (ratio-test mode)
     b200vo_dmatch* good;       // [pairs][kp_cap]
     int* n_good;               // [pairs]
     int* n_cross;              // [pairs]
@@ -166,6 +167,8 @@ int launch_brief(b200vo_ctx* ctx, int first_slot, int n);
 int launch_match_slots(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_override);
 int launch_match_raw(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t, int n2, int npairs,
                      uint32_t* nnq, uint32_t* nnt);
+int launch_match_knn2_raw(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t, int n2, int npairs,
+                          uint32_t* nn1, uint32_t* nn2);
 int launch_filter(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_override);
 int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int32_t* d_samples, int nhyp);
 int launch_recover_pose(b200vo_ctx* ctx, int npairs);

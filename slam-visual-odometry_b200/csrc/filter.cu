@@ -1,4 +1,4 @@
-// K10 cross-check + K11 sort / statistics / adaptive threshold + K12 point gather & K^-1.
+// K10 cross-check (or ratio test) + K11 sort / statistics / adaptive threshold + K12 point gather & K^-1.
 //
 // What it replaces: the cross-check half of cv::BFMatcher::match and the reference's own
 // get_good_matches_of_features (src/visual_odometry.cpp:145-180): std::sort by distance,
@@ -20,6 +20,8 @@ struct FilterArgs {
     int first_slot, slot_b_override;
     double max_hamming;
     double fx, fy, cx, cy;
+    int mode;                  // B200VO_MATCH_CROSSCHECK | B200VO_MATCH_RATIO
+    float ratio;
 };
 
 __global__ void __launch_bounds__(FL_THREADS)
@@ -43,7 +45,16 @@ filter_kernel(StoreView sv, PairView pv, FilterArgs fa, int P /* pow2 >= kp_cap 
         if (i < n1 && n2 > 0) {
             const uint32_t v = nnq[i];
             const uint32_t t = v & 0xFFFFu;
-            if (v != 0xFFFFFFFFu && (nnt[t] & 0xFFFFu) == (uint32_t)i) { key = (v & 0xFFFF0000u) | (uint32_t)i; ++local; }
+            bool keep;
+            if (fa.mode == B200VO_MATCH_RATIO) {
+                // Lowe: best.distance < ratio * second.distance on DMatch's float distances (one
+                // rounded float product); a query with fewer than two neighbours is rejected
+                const uint32_t v2 = pv.nnq2[(size_t)pair * pv.kp_cap + i];
+                keep = (v != 0xFFFFFFFFu) && (v2 != 0xFFFFFFFFu) && ((float)(v >> 16) < __fmul_rn(fa.ratio, (float)(v2 >> 16)));
+            } else {
+                keep = (v != 0xFFFFFFFFu) && ((nnt[t] & 0xFFFFu) == (uint32_t)i);
+            }
+            if (keep) { key = (v & 0xFFFF0000u) | (uint32_t)i; ++local; }
         }
         keys[i] = key;
     }
@@ -124,6 +135,7 @@ int launch_filter(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_overri
     FilterArgs fa;
     fa.first_slot = first_slot; fa.slot_b_override = slot_b_override;
     fa.max_hamming = ctx->opt.max_hamming;
+    fa.mode = ctx->opt.match_mode; fa.ratio = ctx->opt.ratio;
     fa.fx = ctx->K[0]; fa.fy = ctx->K[1]; fa.cx = ctx->K[2]; fa.cy = ctx->K[3];
     filter_kernel<<<npairs, FL_THREADS, smem, ctx->stream>>>(ctx->store, ctx->pairs, fa, P);
     B200VO_LAUNCH_CHECK(ctx);

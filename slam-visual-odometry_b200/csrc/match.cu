@@ -30,6 +30,7 @@ struct MatchArgs {
     int n1, n2;                           // raw mode sizes
     int slots, first_slot, slot_b_override, kp_cap;
     uint32_t* nnq; uint32_t* nnt;         // [pairs][out_stride]
+    uint32_t* nnq2;                       // [pairs][out_stride] second neighbour (k-NN kernel only)
     int out_stride;
     int chunk;                            // train columns per CTA (<= MT_MAXCHUNK)
 };
@@ -152,6 +153,96 @@ match_kernel(MatchArgs a) {
     for (int i = tid; i < ncols; i += MT_THREADS) atomicMin(&a.nnt[(size_t)pair * a.out_stride + col0 + i], s_col[i]);
 }
 
+// K9b: the two nearest trains of every query -- cv::BFMatcher(NORM_HAMMING, false)::knnMatch(k = 2),
+// the matcher behind a Lowe ratio test (north star; the reference itself only cross-checks,
+// src/visual_odometry.cpp:87).  OpenCV orders neighbours by (distance, trainIdx) (pinned in
+// tests/test_oracle_match.py), which is again the integer order of the packed words, so
+//   second = min(second, max(best, v));  best = min(best, v)
+// keeps the exact top two in three integer min/max.  A CTA owns its query rows for ALL train
+// columns (it streams the chunks itself), so the top-2 never has to be merged across CTAs, and the
+// column minima of the cross-check kernel (redux + shared atomics) are not needed at all.
+template <int R>
+__global__ void __launch_bounds__(MT_THREADS)
+match_knn2_kernel(MatchArgs a) {
+    __shared__ __align__(16) uint32_t s_t[MT_MAXCHUNK * 8];
+    const int pair = blockIdx.z;
+    const uint8_t* q; const uint8_t* t;
+    int n1, n2;
+    if (a.counts) {
+        const int sa = (a.first_slot + pair) % a.slots;
+        const int sb = (a.slot_b_override >= 0) ? a.slot_b_override : (a.first_slot + pair + 1) % a.slots;
+        q = a.q + (size_t)sa * a.kp_cap * kDescBytes;
+        t = a.t + (size_t)sb * a.kp_cap * kDescBytes;
+        n1 = a.counts[sa]; n2 = a.counts[sb];
+    } else {
+        q = a.q + (size_t)pair * a.q_stride;
+        t = a.t + (size_t)pair * a.t_stride;
+        n1 = a.n1; n2 = a.n2;
+    }
+    const int row0 = blockIdx.y * (MT_THREADS * R);
+    if (row0 >= n1) return;
+    const int tid = threadIdx.x;
+    uint32_t qd[R][8], best[R], second[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * MT_THREADS + tid;
+        best[r] = second[r] = 0xFFFFFFFFu;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) qd[r][w] = 0;
+        if (row < n1) {
+            const uint4* p = reinterpret_cast<const uint4*>(q + (size_t)row * kDescBytes);
+            const uint4 lo = __ldg(p), hi = __ldg(p + 1);
+            qd[r][0] = lo.x; qd[r][1] = lo.y; qd[r][2] = lo.z; qd[r][3] = lo.w;
+            qd[r][4] = hi.x; qd[r][5] = hi.y; qd[r][6] = hi.z; qd[r][7] = hi.w;
+        }
+    }
+    for (int col0 = 0; col0 < n2; col0 += MT_MAXCHUNK) {
+        const int ncols = min(MT_MAXCHUNK, n2 - col0);
+        __syncthreads();                       // the previous chunk has been consumed
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(t + (size_t)col0 * kDescBytes);
+            uint4* dst = reinterpret_cast<uint4*>(s_t);
+            for (int i = tid; i < ncols * 2; i += MT_THREADS) dst[i] = __ldg(src + i);
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int j = 0; j < ncols; ++j) {
+            const uint4 t0 = *reinterpret_cast<const uint4*>(&s_t[j * 8]);
+            const uint4 t1 = *reinterpret_cast<const uint4*>(&s_t[j * 8 + 4]);
+            const uint32_t colidx = (uint32_t)(col0 + j);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t v = (hamming256<1>(qd[r], t0, t1) << 16) | colidx;
+                second[r] = min(second[r], max(best[r], v));
+                best[r] = min(best[r], v);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int row = row0 + r * MT_THREADS + tid;
+        if (row < n1) {
+            a.nnq[(size_t)pair * a.out_stride + row] = best[r];
+            a.nnq2[(size_t)pair * a.out_stride + row] = second[r];
+        }
+    }
+}
+
+static int run_match_knn2(b200vo_ctx* ctx, MatchArgs a, int n1max, int n1_expected, int npairs) {
+    if (npairs <= 0 || n1max <= 0) return B200VO_OK;
+    // rows per thread: as many as still leave >= 2 CTAs per SM (the CTA count is rows x pairs only)
+    int R = 4;
+    while (R > 1 && (long)div_up(n1_expected, MT_THREADS * R) * npairs < 2 * 148) R >>= 1;
+    dim3 grid(1, div_up(n1max, MT_THREADS * R), npairs);
+    switch (R) {
+        case 4: match_knn2_kernel<4><<<grid, MT_THREADS, 0, ctx->stream>>>(a); break;
+        case 2: match_knn2_kernel<2><<<grid, MT_THREADS, 0, ctx->stream>>>(a); break;
+        default: match_knn2_kernel<1><<<grid, MT_THREADS, 0, ctx->stream>>>(a); break;
+    }
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
 static int pick_rows_per_thread(int n1) {
     // least padding wins; prefer more rows per thread (fewer shared-memory reads per distance)
     int bestR = 1;
@@ -191,6 +282,13 @@ static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_
 
 int launch_match_slots(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_override) {
     const StoreView& sv = ctx->store;
+    if (ctx->opt.match_mode == B200VO_MATCH_RATIO) {
+        MatchArgs a{};
+        a.q = sv.desc; a.t = sv.desc; a.counts = sv.kp_count;
+        a.slots = sv.slots; a.first_slot = first_slot; a.slot_b_override = slot_b_override; a.kp_cap = sv.kp_cap;
+        a.nnq = ctx->pairs.nnq; a.nnq2 = ctx->pairs.nnq2; a.out_stride = sv.kp_cap;
+        return run_match_knn2(ctx, a, sv.kp_cap, ctx->opt.nfeatures, npairs);
+    }
     B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.nnq, 0xFF, (size_t)npairs * sv.kp_cap * sizeof(uint32_t), ctx->stream));
     B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.nnt, 0xFF, (size_t)npairs * sv.kp_cap * sizeof(uint32_t), ctx->stream));
     MatchArgs a{};
@@ -211,6 +309,15 @@ int launch_match_raw(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t
     a.counts = nullptr; a.n1 = n1; a.n2 = n2;
     a.nnq = nnq; a.nnt = nnt; a.out_stride = stride;
     return run_match(ctx, a, n1, n2, n1, npairs);
+}
+
+int launch_match_knn2_raw(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t, int n2, int npairs,
+                          uint32_t* nn1, uint32_t* nn2) {
+    MatchArgs a{};
+    a.q = q; a.t = t; a.q_stride = (size_t)n1 * kDescBytes; a.t_stride = (size_t)n2 * kDescBytes;
+    a.counts = nullptr; a.n1 = n1; a.n2 = n2;
+    a.nnq = nn1; a.nnq2 = nn2; a.out_stride = n1;
+    return run_match_knn2(ctx, a, n1, n1, npairs);
 }
 
 // ------------------------------------------------------------------ POPC-pipe microbenchmark

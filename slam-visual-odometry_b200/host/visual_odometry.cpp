@@ -51,6 +51,8 @@ void VisualOdometry::init(int w, int h, const Options& o) {
     opt.nfeatures = o.nfeatures;
     opt.ransac_hypotheses = o.ransac_hypotheses;
     opt.ransac_seed = o.ransac_seed;
+    opt.match_mode = o.ratio_test ? B200VO_MATCH_RATIO : B200VO_MATCH_CROSSCHECK;
+    opt.ratio = o.ratio;
     opt.max_frames = std::max(2, o.batch_frames + 1);
     check(b200vo_create(&opt, o.device, &ctx_), "create");
     // intrinsics synthesised from the image size (reference src/visual_odometry.cpp:90-98)

@@ -131,3 +131,65 @@ def test_popcount_variants_agree(built, monkeypatch):
             got = c.match_descriptors(q, t)
         for g, r in zip(got, ref):
             assert np.array_equal(g[0], r), "variant " + v
+
+
+# ---- ratio-test mode (north star: "cross-check and ratio test"; [ext], the reference only cross-checks)
+@pytest.mark.parametrize("n1,n2,kind", [(1, 2, "rand"), (5, 1, "rand"), (300, 7, "ties"), (257, 513, "ties"),
+                                         (1200, 1201, "rand"), (3000, 2999, "ties"), (2049, 1537, "rand")])
+def test_knn2_exact(ctx, n1, n2, kind):
+    """BFMatcher(NORM_HAMMING, False).knnMatch(k=2): both neighbours, (distance, trainIdx) order, bit-exact."""
+    rng = np.random.default_rng(n1 * 31 + n2)
+    if kind == "rand":
+        q = rng.integers(0, 256, (n1, 32), dtype=np.uint8); t = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    else:
+        q = _tie_heavy(rng, n1); t = _tie_heavy(rng, n2)
+    idx, dist = ctx.knn2_match_descriptors(q, t)
+    if n2 >= 2:
+        oi, od = M.knn2_match(q, t)
+        assert np.array_equal(idx[0], oi) and np.array_equal(dist[0], od)
+    else:
+        onq, odq, _, _ = M.nearest(q, t)
+        assert np.array_equal(idx[0][:, 0], onq) and np.array_equal(dist[0][:, 0], odq)
+        assert (idx[0][:, 1] == -1).all() and (dist[0][:, 1] == -1).all()
+
+
+def test_knn2_batched_and_live_cv2(ctx):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(21)
+    P, n1, n2 = 3, 700, 650
+    q = np.stack([_tie_heavy(rng, n1, 30) for _ in range(P)]); t = np.stack([_tie_heavy(rng, n2, 30) for _ in range(P)])
+    idx, dist = ctx.knn2_match_descriptors(q, t, npairs=P)
+    bf = cv2.BFMatcher_create(cv2.NORM_HAMMING, False)
+    for p in range(P):
+        knn = bf.knnMatch(q[p], t[p], k=2)
+        assert np.array_equal(idx[p], [[a.trainIdx for a in r] for r in knn])
+        assert np.array_equal(dist[p], [[int(a.distance) for a in r] for r in knn])
+
+
+@pytest.mark.parametrize("n1,n2,ratio", [(2000, 2100, 0.75), (40, 35, 0.8), (3000, 3000, 0.7), (50, 1, 0.75)])
+def test_ratio_mode_good_matches(built, n1, n2, ratio):
+    """get_good_matches_of_features with the ratio-test matcher in place of the cross-check matcher."""
+    rng = np.random.default_rng(n1 + 1)
+    t = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    q = t[rng.permutation(n2)[:min(n1, n2)]].copy()
+    if n1 > len(q):
+        q = np.concatenate([q, rng.integers(0, 256, (n1 - len(q), 32), dtype=np.uint8)])
+    for i, f in enumerate(rng.integers(0, 90, len(q))):
+        for b in rng.integers(0, 256, f):
+            q[i, b // 8] ^= np.uint8(1 << (b % 8))
+    with built.Context(640, 240, nfeatures=3000, max_frames=4, ransac_hypotheses=64,
+                       match_mode=built.MATCH_RATIO, ratio=ratio) as c:
+        c.set_features(0, None, q)
+        c.set_features(1, None, t)
+        good, n_pass, thr = c.match(0, 1)
+    qi, ti, d, thr_o, nc = M.good_matches(q, t, ratio=ratio)
+    assert n_pass == nc and thr == thr_o
+    assert np.array_equal(good["queryIdx"], qi) and np.array_equal(good["trainIdx"], ti)
+    assert np.array_equal(good["distance"], d.astype(np.float32))
+
+
+def test_ratio_mode_rejects_bad_options(built):
+    with pytest.raises(built.B200VOError):
+        built.Context(640, 240, match_mode=7)
+    with pytest.raises(built.B200VOError):
+        built.Context(640, 240, match_mode=built.MATCH_RATIO, ratio=1.5)

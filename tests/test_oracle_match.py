@@ -52,3 +52,29 @@ def test_cross_check_live_cv2_tie_heavy():
         qi, ti, d = M.cross_check_match(q, t)
         assert np.array_equal(qi, [x.queryIdx for x in m]) and np.array_equal(ti, [x.trainIdx for x in m])
         assert np.array_equal(d, [int(x.distance) for x in m])
+
+
+@needs_cv2
+def test_ratio_test_live_cv2():
+    """The ratio-test mode's oracle against cv2.knnMatch + Lowe's test written the usual way."""
+    import cv2
+    rng = np.random.default_rng(8)
+    bf = cv2.BFMatcher_create(cv2.NORM_HAMMING, False)
+    for trial in range(6):
+        n1, n2 = rng.integers(2, 400, 2)
+        t = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+        q = t[rng.integers(0, n2, n1)].copy()
+        for i in range(n1):
+            for b in rng.integers(0, 256, rng.integers(0, 80)):
+                q[i, b // 8] ^= np.uint8(1 << (b % 8))
+        ratio = [0.6, 0.75, 0.8][trial % 3]
+        keep = [(m.queryIdx, m.trainIdx, int(m.distance)) for m, n in bf.knnMatch(q, t, k=2)
+                if m.distance < np.float32(ratio) * n.distance]
+        qi, ti, d = M.ratio_test_match(q, t, ratio)
+        assert [tuple(x) for x in zip(qi.tolist(), ti.tolist(), d.tolist())] == keep
+
+
+def test_ratio_test_needs_two_neighbours():
+    d = np.random.default_rng(0).integers(0, 256, (5, 32), dtype=np.uint8)
+    assert len(M.ratio_test_match(d, d[:1])[0]) == 0
+    assert len(M.good_matches(d, d[:1], ratio=0.75)[0]) == 0
