@@ -326,7 +326,7 @@ def run_b200(args):
                 ctx.process_pairs_device(p0, np_, f0 + done_pairs)
                 done_pairs += np_
                 st = ctx.stage_times()
-                for k in ("match_ms", "filter_ms", "ransac_ms", "pose_ms", "fp_setup_ms", "fp_isolate_ms", "fp_finish_ms", "score_ms"):
+                for k in ("match_ms", "filter_ms", "ransac_ms", "pose_ms", "fivept_ms", "score_ms"):
                     tot[k] = tot.get(k, 0.0) + st[k]
             prev_slot = (first + n - 1) % (B + 1)
             done_frames += n
@@ -363,7 +363,7 @@ def run_b200(args):
     stages_out["match"] = {"ms": round(mm, 3), "bound": "int_pipe(popc)", "algorithmic_popc32_per_pair": 8, "executed_popc32_per_pair": 6,
                            "achieved_Gpopc_s": round(popc_exec / 1e9, 1), "peak_Gpopc_s": round(popc_rate / 1e9, 1),
                            "frac": round(popc_exec / popc_rate, 4), "descriptor_pairs_per_s": round(kp_pairs / (mm * 1e-3), 0) if mm > 0 else 0}
-    for name in ("select", "filter", "ransac", "pose", "fp_setup", "fp_isolate", "fp_finish", "score"):
+    for name in ("select", "filter", "ransac", "pose", "fivept", "score"):
         stages_out[name] = {"ms": round(stage.get(name + "_ms", 0.0), 3)}
     # FP64 work of the scoring kernel: models x points x ~20 DFMA against 64 DFMA/clk/SM
     kernels = {k: v for k, v in stage.items() if k not in ("ransac_ms",)}

@@ -125,8 +125,8 @@ typedef struct b200vo_pose_record {
 typedef struct b200vo_stage_times {
     float upload_ms, gray_ms, pyramid_ms, fast_ms, select_ms, orient_ms, blur_ms, brief_ms;
     float match_ms, filter_ms, ransac_ms, pose_ms, download_ms;
-    /* kernels inside ransac_ms (fixed-H mode: one launch each) */
-    float fp_setup_ms, fp_isolate_ms, fp_finish_ms, score_ms;
+    /* kernels inside ransac_ms (fixed-H mode: one launch each): five-point solver, Sampson scoring */
+    float fivept_ms, score_ms;
 } b200vo_stage_times;
 
 int b200vo_abi_version(void);

@@ -41,7 +41,7 @@ assert KEYPOINT_DTYPE.itemsize == 32 and DMATCH_DTYPE.itemsize == 16 and POSE_RE
 class StageTimes(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("upload_ms", "gray_ms", "pyramid_ms", "fast_ms", "select_ms", "orient_ms",
                                          "blur_ms", "brief_ms", "match_ms", "filter_ms", "ransac_ms", "pose_ms",
-                                         "download_ms", "fp_setup_ms", "fp_isolate_ms", "fp_finish_ms", "score_ms")]
+                                         "download_ms", "fivept_ms", "score_ms")]
 
 
 EXPORTS = [

@@ -330,15 +330,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     TRY(dev_alloc(ctx, &pv.rounds, P));
     TRY(dev_alloc(ctx, &pv.pose_cand, P * 24));
     TRY(dev_alloc(ctx, &pv.pose_cnt, P * 4));
-    TRY(dev_alloc(ctx, &pv.fp_setup, P * pv.nhyp_cap * 86));
-    TRY(dev_alloc(ctx, &pv.fp_ok, P * pv.nhyp_cap));
-    TRY(dev_alloc(ctx, &pv.cand_count, 4));
     TRY(dev_alloc(ctx, &pv.fb_gid, P * pv.nhyp_cap));
-    pv.cand_cap = (int)std::min<size_t>(P * pv.nhyp_cap * 10, (size_t)1 << 30);
-    TRY(dev_alloc(ctx, &pv.cand_gid, (size_t)pv.cand_cap));
-    TRY(dev_alloc(ctx, &pv.cand_tag, (size_t)pv.cand_cap));
-    TRY(dev_alloc(ctx, &pv.cand_a, (size_t)pv.cand_cap));
-    TRY(dev_alloc(ctx, &pv.cand_b, (size_t)pv.cand_cap));
+    TRY(dev_alloc(ctx, &pv.fb_count, 4));
     pv.counts = nullptr;
 #undef TRY
 #undef TRYCUDA
@@ -632,12 +625,10 @@ static int run_pairs(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_ove
     if (ctx->timing) {
         B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         ctx->times.match_ms = clk.ms(0); ctx->times.filter_ms = clk.ms(1); ctx->times.ransac_ms = clk.ms(2); ctx->times.pose_ms = clk.ms(3);
-        ctx->times.fp_setup_ms = ctx->times.fp_isolate_ms = ctx->times.fp_finish_ms = ctx->times.score_ms = 0.f;
+        ctx->times.fivept_ms = ctx->times.score_ms = 0.f;
         if (!ctx->opt.ransac_adaptive || d_samples) {
-            cudaEventElapsedTime(&ctx->times.fp_setup_ms, ctx->ev[8], ctx->ev[9]);
-            cudaEventElapsedTime(&ctx->times.fp_isolate_ms, ctx->ev[9], ctx->ev[10]);
-            cudaEventElapsedTime(&ctx->times.fp_finish_ms, ctx->ev[10], ctx->ev[11]);
-            cudaEventElapsedTime(&ctx->times.score_ms, ctx->ev[11], ctx->ev[12]);
+            cudaEventElapsedTime(&ctx->times.fivept_ms, ctx->ev[8], ctx->ev[9]);
+            cudaEventElapsedTime(&ctx->times.score_ms, ctx->ev[9], ctx->ev[10]);
         }
     }
     return B200VO_OK;

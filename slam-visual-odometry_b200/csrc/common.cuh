@@ -84,15 +84,8 @@ struct PairView {
     int* rounds;               // [pairs] adaptive RANSAC: blocks of 128 hypotheses evaluated
     double* pose_cand;         // [pairs][24] R1(9) R2(9) t(3) from decomposeEssentialMat
     int* pose_cnt;             // [pairs][4] cheirality votes of the four candidates
-    // phased five-point solver work space (ransac.cu)
-    double* fp_setup;          // [86][pairs*nhyp_cap] element-major FivePointSetup
-    uint8_t* fp_ok;            // [pairs*nhyp_cap] setup succeeded
-    unsigned int* cand_count;  // [0] number of root brackets in the compact list, [1] number of fallback hypotheses
-    int* fb_gid;               // [pairs*nhyp_cap] hypotheses whose Sturm chain was unreliable
-    int* cand_gid;             // [cand_cap] pair*nhyp_cap + hypothesis
-    int* cand_tag;             // [cand_cap] solution index | reversed << 8
-    double* cand_a; double* cand_b;   // [cand_cap] bracket
-    int cand_cap;
+    int* fb_gid;               // [pairs*nhyp_cap] hypotheses deferred to the exact root-isolation path (ransac.cu)
+    unsigned int* fb_count;    // [1] length of that queue
     int nhyp_cap;
     int kp_cap;
 };

@@ -434,51 +434,61 @@ GEOM_HD inline void polish_u(const double N[4][9], double* u) {
     int f = 3;
     for (int i = 0; i < 3; ++i) if (fabs(u[i]) > fabs(u[f])) f = i;
     if (!(fabs(u[f]) > 0.0) || !(fabs(u[f]) < 1e300)) return;
+    // The fixed component is moved to slot 3 (rows of N are addressed through offsets), so every
+    // array index below is a compile-time constant -- no run-time register indexing on the GPU.
+    double w0 = u[0], w1 = u[1], w2 = u[2], w3 = u[3];
+    int o0 = 0, o1 = 9, o2 = 18, o3 = 27;
+    if (f == 0) { const double t = w0; w0 = w3; w3 = t; o0 = 27; o3 = 0; }
+    else if (f == 1) { const double t = w1; w1 = w3; w3 = t; o1 = 27; o3 = 9; }
+    else if (f == 2) { const double t = w2; w2 = w3; w3 = t; o2 = 27; o3 = 18; }
     {
-        const double inv = 1.0 / u[f];
-        for (int i = 0; i < 4; ++i) u[i] *= inv;
-        u[f] = 1.0;
+        const double inv = 1.0 / w3;
+        w0 *= inv; w1 *= inv; w2 *= inv; w3 = 1.0;
     }
-    int fr[3];
-    { int k = 0; for (int i = 0; i < 4; ++i) if (i != f) fr[k++] = i; }
+    const double* Nf = &N[0][0];
     double E[9], r[10];
-    for (int k = 0; k < 9; ++k) E[k] = u[0] * N[0][k] + u[1] * N[1][k] + u[2] * N[2][k] + u[3] * N[3][k];
+    for (int k = 0; k < 9; ++k) E[k] = w0 * Nf[o0 + k] + w1 * Nf[o1 + k] + w2 * Nf[o2 + k] + Nf[o3 + k];
     essential_residuals(E, r);
     double ss = 0.0;
     for (int i = 0; i < 10; ++i) ss += r[i] * r[i];
     for (int it = 0; it < 4; ++it) {
-        if (ss < 1e-26) return;           // |r| ~ 1e-13: already at working precision
-        double J[3][10];
-        for (int d = 0; d < 3; ++d) essential_residual_derivative(E, N[fr[d]], J[d]);
+        if (ss < 1e-26) break;            // |r| ~ 1e-13: already at working precision
+        double J0[10], J1[10], J2[10];
+        essential_residual_derivative(E, Nf + o0, J0);
+        essential_residual_derivative(E, Nf + o1, J1);
+        essential_residual_derivative(E, Nf + o2, J2);
         // normal equations (3x3, symmetric) solved by Cramer's rule
-        double A[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+        double A0 = 0, A1 = 0, A2 = 0, A3 = 0, A4 = 0, A5 = 0, g0 = 0, g1 = 0, g2 = 0;
         for (int i = 0; i < 10; ++i) {
-            A[0] += J[0][i] * J[0][i]; A[1] += J[0][i] * J[1][i]; A[2] += J[0][i] * J[2][i];
-            A[3] += J[1][i] * J[1][i]; A[4] += J[1][i] * J[2][i]; A[5] += J[2][i] * J[2][i];
-            g[0] += J[0][i] * r[i]; g[1] += J[1][i] * r[i]; g[2] += J[2][i] * r[i];
+            A0 += J0[i] * J0[i]; A1 += J0[i] * J1[i]; A2 += J0[i] * J2[i];
+            A3 += J1[i] * J1[i]; A4 += J1[i] * J2[i]; A5 += J2[i] * J2[i];
+            g0 += J0[i] * r[i]; g1 += J1[i] * r[i]; g2 += J2[i] * r[i];
         }
-        const double c00 = A[3] * A[5] - A[4] * A[4], c01 = A[2] * A[4] - A[1] * A[5], c02 = A[1] * A[4] - A[2] * A[3];
-        const double det = A[0] * c00 + A[1] * c01 + A[2] * c02;
-        if (!(fabs(det) > 0.0)) return;
-        const double c11 = A[0] * A[5] - A[2] * A[2], c12 = A[1] * A[2] - A[0] * A[4], c22 = A[0] * A[3] - A[1] * A[1];
+        const double c00 = A3 * A5 - A4 * A4, c01 = A2 * A4 - A1 * A5, c02 = A1 * A4 - A2 * A3;
+        const double det = A0 * c00 + A1 * c01 + A2 * c02;
+        if (!(fabs(det) > 0.0)) break;
+        const double c11 = A0 * A5 - A2 * A2, c12 = A1 * A2 - A0 * A4, c22 = A0 * A3 - A1 * A1;
         const double inv = 1.0 / det;
-        double un[4];
-        for (int i = 0; i < 4; ++i) un[i] = u[i];
-        un[fr[0]] -= (c00 * g[0] + c01 * g[1] + c02 * g[2]) * inv;
-        un[fr[1]] -= (c01 * g[0] + c11 * g[1] + c12 * g[2]) * inv;
-        un[fr[2]] -= (c02 * g[0] + c12 * g[1] + c22 * g[2]) * inv;
+        const double n0 = w0 - (c00 * g0 + c01 * g1 + c02 * g2) * inv;
+        const double n1 = w1 - (c01 * g0 + c11 * g1 + c12 * g2) * inv;
+        const double n2 = w2 - (c02 * g0 + c12 * g1 + c22 * g2) * inv;
         double En[9], rn[10];
-        for (int k = 0; k < 9; ++k) En[k] = un[0] * N[0][k] + un[1] * N[1][k] + un[2] * N[2][k] + un[3] * N[3][k];
+        for (int k = 0; k < 9; ++k) En[k] = n0 * Nf[o0 + k] + n1 * Nf[o1 + k] + n2 * Nf[o2 + k] + Nf[o3 + k];
         essential_residuals(En, rn);
         double ns = 0.0;
         for (int i = 0; i < 10; ++i) ns += rn[i] * rn[i];
-        if (!(ns < ss)) return;           // no improvement (or NaN): keep the current root
-        for (int i = 0; i < 4; ++i) u[i] = un[i];
+        if (!(ns < ss)) break;            // no improvement (or NaN): keep the current root
+        w0 = n0; w1 = n1; w2 = n2;
         for (int k = 0; k < 9; ++k) E[k] = En[k];
         for (int i = 0; i < 10; ++i) r[i] = rn[i];
-        if (ss - ns < 1e-3 * ss) return;  // stalled
+        if (ss - ns < 1e-3 * ss) break;   // stalled
         ss = ns;
     }
+    // undo the permutation
+    if (f == 0) { const double t = w0; w0 = w3; w3 = t; }
+    else if (f == 1) { const double t = w1; w1 = w3; w3 = t; }
+    else if (f == 2) { const double t = w2; w2 = w3; w3 = t; }
+    u[0] = w0; u[1] = w1; u[2] = w2; u[3] = w3;
 }
 
 // One scaled row of the constraint matrix -> storage

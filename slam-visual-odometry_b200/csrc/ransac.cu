@@ -18,6 +18,7 @@
 // better), realised order-independently by the packed atomicMax.
 #include "common.cuh"
 #include "geom_core.cuh"
+#include "fivept_group.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -34,158 +35,93 @@ struct RansacArgs {
     int min_matches;            // reference kMinMatchesForPose
 };
 
-// tuning knobs (environment, read once): B200VO_FP_SETUP=shared|local, B200VO_FP_FALLBACK=inline|queue
-static int g_fp_setup_shared = -1, g_fp_fb_queue = -1;
-static void read_knobs() {
-    if (g_fp_setup_shared >= 0) return;
-    const char* a = getenv("B200VO_FP_SETUP");
-    g_fp_setup_shared = (a && a[0] == 's') ? 1 : 0;
-    const char* b = getenv("B200VO_FP_FALLBACK");
-    g_fp_fb_queue = (b && b[0] == 'q') ? 1 : 0;
-}
+// ---- cooperative five-point solver (fivept_group.cuh) ----------------------------------------
+// One hypothesis per group of 10 lanes, three groups per warp, 12 per CTA; the whole solver
+// (null space -> constraints -> elimination -> det B(z) -> Sturm isolation -> per-root finish) is ONE
+// kernel: the 10x20 matrix stays in the registers of the group, every exchange goes through the
+// group's 4.8 KB block of shared memory, nothing is staged through global or local memory.
+// (round-1 history: a thread-per-hypothesis solver ran with 10 of 32 lanes active; a three-phase
+// version with stream compaction fixed the divergence but left 5.6 KB of local memory per thread and
+// 85 % long-scoreboard stalls -- profiles/ncu_r01_final_kernels.txt.)
+constexpr int FPG_THREADS = 128;
+constexpr int FPG_GROUPS = 3 * (FPG_THREADS / 32);
 
-// ---- phased five-point solver -------------------------------------------------------------
-// A thread-per-hypothesis solver diverges badly: hypotheses have 0..10 real roots and every root
-// needs a data-dependent number of iterations (measured: 10 of 32 lanes active).  So the work is
-// re-packed between phases:
-//   fp_setup_kernel   thread / hypothesis : uniform algebra (null space, 10x20 elimination, det B(z))
-//   fp_isolate_kernel thread / hypothesis : Sturm isolation -> root brackets appended to a compact list
-//   fp_finish_kernel  thread / bracket    : refine root, back-substitute, polish, write E
-//   score_kernel      warp   / bracket    : Sampson inlier count, 64-bit atomicMax per pair
-// The compact list carries (pair, hypothesis, solution index), so "first arg-max wins" does not
-// depend on the order in which brackets were appended.
-template <bool SHARED>
-__device__ __forceinline__ void fp_setup_body(const PairView& pv, const RansacArgs& ra, double* s_M) {
-    const int pair = blockIdx.y;
-    const int h = ra.h0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= ra.h0 + ra.nround) return;
-    if (ra.adaptive && pv.done[pair]) return;
+// One hypothesis (pair, h) by the calling group.  FALLBACK = false: a hypothesis whose Sturm chain is
+// unreliable (near-multiple roots, ~2-6 %) is appended to the deferred queue instead of running the
+// long serial exact path inside this warp.
+template <bool FALLBACK>
+__device__ __forceinline__ void solve_hypothesis(const PairView& pv, const RansacArgs& ra, geom::GroupShared& gs, int r, bool in_range,
+                                                 int pair, int h) {
     const int gid = pair * pv.nhyp_cap + h;
-    const int m = pv.n_good[pair];
-    if (m < ra.min_matches || m < 5) { pv.fp_ok[gid] = 0; return; }
-    int idx[5];
-    if (ra.samples) {
+    const int m = in_range ? pv.n_good[pair] : 0;
+    const bool solve = in_range && m >= ra.min_matches && m >= 5;        // uniform over the group
+    double pts[20];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) idx[k] = ra.samples[((size_t)pair * ra.nhyp + h) * 5 + k];
-    } else {
-        geom::draw_sample(geom::pair_stream(ra.seed, ra.first_pair_id + pair), h, m, idx);
-    }
-    const size_t base = (size_t)pair * pv.kp_cap;
-    double x1[5][2], x2[5][2];
+    for (int k = 0; k < 20; ++k) pts[k] = 0.0;
+    if (solve) {
+        int idx[5];
+        if (ra.samples) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const int i = min(max(idx[k], 0), m - 1);
-        x1[k][0] = pv.x1x[base + i]; x1[k][1] = pv.x1y[base + i];
-        x2[k][0] = pv.x2x[base + i]; x2[k][1] = pv.x2y[base + i];
-    }
-    geom::FivePointSetup S;
-    bool ok;
-    if (SHARED) {
-        geom::StridedMat M{s_M + threadIdx.x, (int)blockDim.x};
-        ok = geom::five_point_setup(x1, x2, M, S);
-    } else {
-        geom::LocalMat M;
-        ok = geom::five_point_setup(x1, x2, M, S);
-    }
-    pv.fp_ok[gid] = ok ? 1 : 0;
-    if (!ok) return;
-    const size_t stride = (size_t)gridDim.y * pv.nhyp_cap;      // element-major over the hypotheses of this launch
-    const double* src = reinterpret_cast<const double*>(&S);
-    double* dst = pv.fp_setup + gid;
-#pragma unroll 2
-    for (int e = 0; e < geom::kSetupDoubles; ++e) dst[(size_t)e * stride] = src[e];
-}
-
-__global__ void __launch_bounds__(128, 4)
-fp_setup_kernel(PairView pv, RansacArgs ra) { fp_setup_body<false>(pv, ra, nullptr); }
-
-// variant with the 10x20 matrix in shared memory (element-major / thread-minor, 200 KB per CTA)
-__global__ void __launch_bounds__(128)
-fp_setup_kernel_shared(PairView pv, RansacArgs ra) {
-    extern __shared__ double s_M[];
-    fp_setup_body<true>(pv, ra, s_M);
-}
-
-__device__ __forceinline__ void emit_brackets(const PairView& pv, int gid, const geom::RootBracket* br, int nb) {
-    pv.nsol[gid] = nb;
-    if (nb == 0) return;
-    const unsigned pos = atomicAdd(pv.cand_count, (unsigned)nb);
-    for (int k = 0; k < nb; ++k) {
-        const unsigned p = pos + k;
-        if (p >= (unsigned)pv.cand_cap) break;
-        pv.cand_gid[p] = gid;
-        pv.cand_tag[p] = k | (br[k].reversed << 8);
-        pv.cand_a[p] = br[k].a;
-        pv.cand_b[p] = br[k].b;
-    }
-}
-
-__global__ void __launch_bounds__(128)
-fp_isolate_kernel(PairView pv, RansacArgs ra, bool queue_fallback) {
-    const int pair = blockIdx.y;
-    const int h = ra.h0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= ra.h0 + ra.nround) return;
-    if (ra.adaptive && pv.done[pair]) return;
-    const int gid = pair * pv.nhyp_cap + h;
-    int nb = 0;
-    geom::RootBracket br[10];
-    if (pv.fp_ok[gid]) {
-        const size_t stride = (size_t)gridDim.y * pv.nhyp_cap;
-        double c[11];
-#pragma unroll
-        for (int i = 0; i < 11; ++i) c[i] = pv.fp_setup[(size_t)(75 + i) * stride + gid];     // FivePointSetup::c
-        nb = geom::five_point_isolate(c, br, /*allow_fallback=*/!queue_fallback);
-    }
-#pragma unroll
-    for (int k = 0; k < 10; ++k) pv.model_ok[(size_t)gid * 10 + k] = 0;
-    if (nb < 0) {                       // unreliable Sturm chain: queue for the dense exact pass
-        pv.nsol[gid] = 0;
-        pv.fb_gid[atomicAdd(pv.cand_count + 1, 1u)] = gid;
-        return;
-    }
-    emit_brackets(pv, gid, br, nb);
-}
-
-// The few hypotheses whose Sturm chain failed its parity check, packed densely: every lane of these
-// warps takes the slow exact path (derivative chain), instead of one lane stalling 31 others.
-__global__ void __launch_bounds__(128)
-fp_isolate_fallback_kernel(PairView pv, int npairs) {
-    const unsigned n = pv.cand_count[1];
-    const size_t stride = (size_t)npairs * pv.nhyp_cap;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int gid = pv.fb_gid[i];
-        double c[11];
-#pragma unroll
-        for (int k = 0; k < 11; ++k) c[k] = pv.fp_setup[(size_t)(75 + k) * stride + gid];
-        geom::RootBracket br[10];
-        const int nb = geom::five_point_isolate(c, br, /*allow_fallback=*/true);
-        emit_brackets(pv, gid, br, nb);
-    }
-}
-
-__global__ void __launch_bounds__(128, 4)
-fp_finish_kernel(PairView pv, int npairs) {
-    const unsigned n = min(*pv.cand_count, (unsigned)pv.cand_cap);
-    const size_t stride = (size_t)npairs * pv.nhyp_cap;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int gid = pv.cand_gid[i];
-        const int tag = pv.cand_tag[i];
-        geom::RootBracket br;
-        br.a = pv.cand_a[i]; br.b = pv.cand_b[i]; br.reversed = tag >> 8;
-        geom::FivePointSetup S;
-        double* dst = reinterpret_cast<double*>(&S);
-        const double* src = pv.fp_setup + gid;
-#pragma unroll 2
-        for (int e = 0; e < geom::kSetupDoubles; ++e) dst[e] = src[(size_t)e * stride];
-        double E[9];
-        const bool ok = geom::five_point_finish(S, br, E);
-        const int s = tag & 0xFF;
-        if (ok) {
-            double* out = pv.models + (size_t)gid * 90 + s * 9;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) out[k] = E[k];
+            for (int k = 0; k < 5; ++k) idx[k] = ra.samples[((size_t)pair * ra.nhyp + h) * 5 + k];
+        } else {
+            geom::draw_sample(geom::pair_stream(ra.seed, ra.first_pair_id + pair), h, m, idx);
         }
-        pv.model_ok[(size_t)gid * 10 + s] = ok ? 1 : 0;
+        const size_t base = (size_t)pair * pv.kp_cap;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int i = min(max(idx[k], 0), m - 1);
+            pts[2 * k] = pv.x1x[base + i]; pts[2 * k + 1] = pv.x1y[base + i];
+            pts[10 + 2 * k] = pv.x2x[base + i]; pts[10 + 2 * k + 1] = pv.x2y[base + i];
+        }
+    }
+    double E[1][9];
+    bool ok[1] = {false};
+    geom::DeviceGroupExec ex{r, solve};
+    const int nfinal = geom::five_point_group<FALLBACK>(ex, gs, pts, E, ok);
+    if (!in_range) return;
+    pv.model_ok[(size_t)gid * 10 + r] = ok[0] ? 1 : 0;
+    if (ok[0]) {
+        double* out = pv.models + (size_t)gid * 90 + r * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) out[k] = E[0][k];
+    }
+    if (r == 0) {
+        pv.nsol[gid] = max(nfinal, 0);
+        if (!FALLBACK && nfinal < 0) pv.fb_gid[atomicAdd(pv.fb_count, 1u)] = gid;
+    }
+}
+
+__global__ void __launch_bounds__(FPG_THREADS, 4)
+five_point_group_kernel(PairView pv, RansacArgs ra) {
+    extern __shared__ __align__(16) unsigned char fpg_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / geom::kGroupLanes;               // lanes 30, 31 (g == 3) have no group: they only keep the barriers full
+    const int r = lane - geom::kGroupLanes * g;
+    const int slot = warp * 3 + min(g, 2);
+    geom::GroupShared& gs = reinterpret_cast<geom::GroupShared*>(fpg_smem)[slot];
+    const int pair = blockIdx.y;
+    const int h = ra.h0 + blockIdx.x * FPG_GROUPS + slot;
+    const bool in_range = (g < 3) && (h < ra.h0 + ra.nround) && !(ra.adaptive && pv.done[pair]);
+    solve_hypothesis<false>(pv, ra, gs, r, in_range, pair, h);
+}
+
+// the deferred hypotheses, packed densely: every group of these warps takes the exact path
+__global__ void __launch_bounds__(FPG_THREADS, 3)
+five_point_deferred_kernel(PairView pv, RansacArgs ra) {
+    extern __shared__ __align__(16) unsigned char fpg_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / geom::kGroupLanes;
+    const int r = lane - geom::kGroupLanes * g;
+    const int slot = warp * 3 + min(g, 2);
+    geom::GroupShared& gs = reinterpret_cast<geom::GroupShared*>(fpg_smem)[slot];
+    const unsigned n = *pv.fb_count;
+    for (unsigned base = blockIdx.x * FPG_GROUPS; base < n; base += gridDim.x * FPG_GROUPS) {      // uniform over the CTA
+        const unsigned i = base + slot;
+        const bool in_range = (g < 3) && (i < n);
+        const int gid = in_range ? pv.fb_gid[i] : 0;
+        const int pair = gid / pv.nhyp_cap;
+        solve_hypothesis<true>(pv, ra, gs, r, in_range, pair, gid - pair * pv.nhyp_cap);
+        __syncwarp();
     }
 }
 
@@ -193,10 +129,12 @@ fp_finish_kernel(PairView pv, int npairs) {
 // load and ~25 FFMA per point on the full-rate FP32 pipe); only points within a 0.3 % band of the
 // threshold -- where float rounding could flip the decision -- are re-evaluated with the exact
 // double-precision expression, so the count is identical to the all-double evaluation.
-__device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, int m, const double* E,
-                                                  const geom::SampsonThreshold& thr, int lane) {
+// `floor_count`: the scan stops as soon as even all remaining points could not lift the model to
+// floor_count inliers (it then can neither win nor tie; the returned count is a lower bound).
+template <bool STAGED>
+__device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, int m, const double* E, const float4* __restrict__ xf,
+                                                  const geom::SampsonThreshold& thr, int lane, int floor_count) {
     const size_t base = (size_t)pair * pv.kp_cap;
-    const float4* __restrict__ xf = pv.xf + base;
     float e[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) e[k] = (float)E[k];
@@ -221,66 +159,93 @@ __device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, 
             else in = geom::sampson_inlier_fast(E, pv.x1x[base + j], pv.x1y[base + j], pv.x2x[base + j], pv.x2y[base + j], thr);
         }
         cnt += __popc(__ballot_sync(0xffffffffu, in));
+        if (cnt + (m - i0 - 32) < floor_count) break;          // warp-uniform
     }
     return cnt;
 }
 
-// one warp per root bracket (model)
-__global__ void __launch_bounds__(256)
+// K14: one CTA per (pair, block of SC_HB hypotheses); the pair's correspondences are staged once in
+// shared memory (float4 per point) and every warp scores the valid models of the block against them.
+// K15: arg-max with "first model wins" through one 64-bit atomicMax on (count << 32 | ~model index).
+// Models are abandoned as soon as they cannot reach the pair's best count so far (exact: such a
+// model can neither win nor tie), which removes most of the work of the spurious roots.
+constexpr int SC_THREADS = 256;
+constexpr int SC_HB = 64;
+constexpr int SC_MAXPTS = 3072;                            // 48 KB of float4
+
+template <bool STAGED>
+__global__ void __launch_bounds__(SC_THREADS)
 score_kernel(PairView pv, RansacArgs ra) {
-    const unsigned n = min(*pv.cand_count, (unsigned)pv.cand_cap);
-    const int lane = threadIdx.x & 31;
-    const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
-    for (unsigned i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {
-        const int gid = pv.cand_gid[i];
-        const int s = pv.cand_tag[i] & 0xFF;
-        if (!pv.model_ok[(size_t)gid * 10 + s]) continue;
-        const int pair = gid / pv.nhyp_cap, h = gid - pair * pv.nhyp_cap;
-        const int m = pv.n_good[pair];
-        const double* mp = pv.models + (size_t)gid * 90 + s * 9;
+    extern __shared__ __align__(16) unsigned char sc_smem[];
+    const int pair = blockIdx.y;
+    if (ra.adaptive && pv.done[pair]) return;
+    const int m = pv.n_good[pair];
+    if (m < ra.min_matches || m < 5) return;
+    const int hb0 = ra.h0 + blockIdx.x * SC_HB;
+    const int hb1 = min(hb0 + SC_HB, ra.h0 + ra.nround);
+    const float4* xf = pv.xf + (size_t)pair * pv.kp_cap;
+    if (STAGED) {
+        float4* s = reinterpret_cast<float4*>(sc_smem);
+        for (int i = threadIdx.x; i < m; i += SC_THREADS) s[i] = xf[i];
+        __syncthreads();
+        xf = s;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const geom::SampsonThreshold thr = geom::make_sampson_threshold(ra.thr2f);
+    const int nslots = (hb1 - hb0) * 10;
+    for (int i = warp; i < nslots; i += SC_THREADS / 32) {
+        const int h = hb0 + i / 10, s = i - (i / 10) * 10;
+        const size_t gid = (size_t)pair * pv.nhyp_cap + h;
+        if (!pv.model_ok[gid * 10 + s]) continue;
+        const double* mp = pv.models + gid * 90 + s * 9;
         double E[9];
 #pragma unroll
         for (int k = 0; k < 9; ++k) E[k] = mp[k];
-        const geom::SampsonThreshold thr = geom::make_sampson_threshold(ra.thr2f);
-        const int cnt = warp_count_inliers(pv, pair, m, E, thr, lane);
+        const int floor_count = pv.counts ? 0 : (int)(*(volatile unsigned long long*)&pv.best[pair] >> 32);
+        const int cnt = warp_count_inliers<STAGED>(pv, pair, m, E, xf, thr, lane, floor_count);
         if (lane == 0) {
-            if (pv.counts) pv.counts[(size_t)gid * 10 + s] = cnt;
+            if (pv.counts) pv.counts[gid * 10 + s] = cnt;
             const unsigned long long packed =
                 ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(h * 10 + s));
-            atomicMax(&pv.best[pair], packed);
+            if (cnt >= floor_count) atomicMax(&pv.best[pair], packed);
         }
     }
 }
 
 static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
-    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.cand_count, 0, 2 * sizeof(unsigned), ctx->stream));
-    const dim3 grid(div_up(ra.nround, 128), npairs);
-    read_knobs();
-    const bool tm = ctx->timing && !ra.adaptive;        // events 8..12 bracket the four kernels
-    if (tm) cudaEventRecord(ctx->ev[8], ctx->stream);
-    if (g_fp_setup_shared) fp_setup_kernel_shared<<<grid, 128, 200 * sizeof(double) * 128, ctx->stream>>>(ctx->pairs, ra);
-    else fp_setup_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra);
+    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.fb_count, 0, sizeof(unsigned), ctx->stream));
+    const dim3 grid(div_up(ra.nround, FPG_GROUPS), npairs);
+    const size_t smem = FPG_GROUPS * sizeof(geom::GroupShared);
+    five_point_group_kernel<<<grid, FPG_THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
-    if (tm) cudaEventRecord(ctx->ev[9], ctx->stream);
-    fp_isolate_kernel<<<grid, 128, 0, ctx->stream>>>(ctx->pairs, ra, g_fp_fb_queue != 0);
+    // the queue length is only known on the device: a grid that covers ~1/8 of the hypotheses in one
+    // pass (measured share: 2-6 %), grid-stride beyond that; idle CTAs exit at once
+    const long expect = std::max<long>(1, (long)npairs * ra.nround / 8);
+    const int blocks = (int)std::min<long>(148 * 12, (expect + FPG_GROUPS - 1) / FPG_GROUPS);
+    five_point_deferred_kernel<<<blocks, FPG_THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
-    if (g_fp_fb_queue) {
-        const long expect_fb = std::max<long>(1, (long)npairs * ra.nround / 4);       // upper estimate; idle CTAs exit at once
-        fp_isolate_fallback_kernel<<<(int)std::min<long>(148 * 16, (expect_fb + 127) / 128), 128, 0, ctx->stream>>>(ctx->pairs, npairs);
-        B200VO_LAUNCH_CHECK(ctx);
-    }
-    const long expect = (long)npairs * ra.nround * 5;             // ~4.9 roots per hypothesis
-    const int blocks = (int)std::min<long>(148 * 16, std::max<long>(1, (expect + 127) / 128));
-    if (tm) cudaEventRecord(ctx->ev[10], ctx->stream);
-    fp_finish_kernel<<<blocks, 128, 0, ctx->stream>>>(ctx->pairs, npairs);
+    return B200VO_OK;
+}
+
+static int launch_score(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
+    const dim3 grid(div_up(ra.nround, SC_HB), npairs);
+    if (ctx->pairs.kp_cap <= SC_MAXPTS)
+        score_kernel<true><<<grid, SC_THREADS, (size_t)ctx->pairs.kp_cap * sizeof(float4), ctx->stream>>>(ctx->pairs, ra);
+    else
+        score_kernel<false><<<grid, SC_THREADS, 0, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
-    if (tm) cudaEventRecord(ctx->ev[11], ctx->stream);
     return B200VO_OK;
 }
 
 int init_ransac_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(fp_setup_kernel_shared, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * sizeof(double) * 128));
-    if (e != cudaSuccess) { set_error("fp_setup_kernel_shared smem attribute: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
+    cudaError_t e = cudaFuncSetAttribute(five_point_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(FPG_GROUPS * sizeof(geom::GroupShared)));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(five_point_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(FPG_GROUPS * sizeof(geom::GroupShared)));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_MAXPTS * sizeof(float4)));
+    if (e != cudaSuccess) { set_error("ransac kernel smem attribute: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
     return B200VO_OK;
 }
 
@@ -477,12 +442,12 @@ int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int3
     }
     for (int h0 = 0; h0 < nhyp; h0 += block) {
         ra.h0 = h0; ra.nround = std::min(block, nhyp - h0);
+        const bool tm = ctx->timing && !ra.adaptive;        // events 8..10 bracket the two kernels
+        if (tm) cudaEventRecord(ctx->ev[8], ctx->stream);
         { const int rc = launch_five_point(ctx, ra, npairs); if (rc) return rc; }
-        const long expect = (long)npairs * ra.nround * 5;
-        const int blocks = (int)std::min<long>(148 * 8, std::max<long>(1, (expect + 7) / 8));
-        score_kernel<<<blocks, 256, 0, ctx->stream>>>(ctx->pairs, ra);
-        B200VO_LAUNCH_CHECK(ctx);
-        if (ctx->timing && !ra.adaptive) cudaEventRecord(ctx->ev[12], ctx->stream);
+        if (tm) cudaEventRecord(ctx->ev[9], ctx->stream);
+        { const int rc = launch_score(ctx, ra, npairs); if (rc) return rc; }
+        if (tm) cudaEventRecord(ctx->ev[10], ctx->stream);
         if (ra.adaptive) {
             adaptive_update_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(ctx->pairs, npairs, h0 + ra.nround, nhyp, 0.999);
             B200VO_LAUNCH_CHECK(ctx);
@@ -505,7 +470,7 @@ __global__ void score_models_kernel(PairView pv, const double* models, int nmode
     double E[9];
     for (int k = 0; k < 9; ++k) E[k] = models[(size_t)w * 9 + k];
     const geom::SampsonThreshold thr = geom::make_sampson_threshold(thr2f);
-    const int cnt = warp_count_inliers(pv, 0, pv.n_good[0], E, thr, lane);      // points staged in pair 0
+    const int cnt = warp_count_inliers<false>(pv, 0, pv.n_good[0], E, pv.xf, thr, lane, 0);      // points staged in pair 0
     if (lane == 0) counts[w] = cnt;
 }
 

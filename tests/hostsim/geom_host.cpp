@@ -3,6 +3,7 @@
 // The product library never links or loads this file.
 #include <cstring>
 #include "../../slam-visual-odometry_b200/csrc/geom_core.cuh"
+#include "../../slam-visual-odometry_b200/csrc/fivept_group.cuh"
 using namespace b200vo::geom;
 extern "C" {
 int hs_five_point(const double* x1, const double* x2, double* E) {
@@ -41,4 +42,37 @@ extern "C" int hs_count_inliers_fast(const double* E, const double* x1, const do
         c += ok;
     }
     return c;
+}
+// the cooperative (10 lanes per hypothesis) solver, lanes emulated one after another
+extern "C" int hs_five_point_group(const double* x1, const double* x2, double* E) {
+    double a[5][2], b[5][2];
+    std::memcpy(a, x1, sizeof(a)); std::memcpy(b, x2, sizeof(b));
+    return five_point_group_host(a, b, reinterpret_cast<double (*)[9]>(E));
+}
+extern "C" int hs_group_shared_bytes() { return (int)sizeof(GroupShared); }
+// debug: setup polynomial + brackets of both formulations
+extern "C" int hs_dbg_thread(const double* x1, const double* x2, double* c, double* lo, double* hi, int* rev, double* N) {
+    double a[5][2], b[5][2];
+    std::memcpy(a, x1, sizeof(a)); std::memcpy(b, x2, sizeof(b));
+    LocalMat M; FivePointSetup S;
+    if (!five_point_setup(a, b, M, S)) return -1;
+    std::memcpy(c, S.c, sizeof(S.c)); std::memcpy(N, S.N, sizeof(S.N));
+    RootBracket br[10];
+    const int nb = five_point_isolate(S.c, br);
+    for (int i = 0; i < nb; ++i) { lo[i] = br[i].a; hi[i] = br[i].b; rev[i] = br[i].reversed; }
+    return nb;
+}
+extern "C" int hs_dbg_group(const double* x1, const double* x2, double* c, double* lo, double* hi, int* rev, double* N, int* flags) {
+    GroupShared gs; HostGroupExec ex;
+    double pts[20];
+    for (int i = 0; i < 5; ++i) { pts[2*i] = x1[2*i]; pts[2*i+1] = x1[2*i+1]; pts[10+2*i] = x2[2*i]; pts[10+2*i+1] = x2[2*i+1]; }
+    double Eo[kGroupLanes][9]; bool ok[kGroupLanes];
+    const int nf = five_point_group<true>(ex, gs, pts, Eo, ok);
+    std::memcpy(c, gs.S.c, sizeof(gs.S.c)); std::memcpy(N, gs.S.N, sizeof(gs.S.N));
+    for (int i = 0; i < nf; ++i) { lo[i] = gs.v.fin.a[i]; hi[i] = gs.v.fin.b[i]; rev[i] = gs.v.fin.rev[i]; }
+    flags[0] = gs.ibuf[10]; flags[1] = gs.ibuf[11]; flags[2] = gs.chain_ok[0]; flags[3] = gs.chain_ok[1];
+    { GroupShared g2; HostGroupExec e2; double E2[kGroupLanes][9]; bool o2[kGroupLanes]; flags[5] = five_point_group<false>(e2, g2, pts, E2, o2); }
+    int okc = 0; for (int i = 0; i < nf; ++i) okc += ok[i];
+    flags[4] = okc;
+    return nf;
 }
