@@ -354,13 +354,14 @@ def run_b200(args):
         ms = stage.get(key, 0.0)
         gbs = alg[name] * F / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         stages_out[name] = {"ms": round(ms, 3), "bound": "hbm", "algorithmic_bytes_per_frame": alg[name], "achieved_GBps": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)}
-    # matcher: N1*N2 descriptor pairs; algorithmically 8 popc32 each.  The kernel executes 6 (two
+    # matcher: N1*N2 descriptor pairs; algorithmically 8 popc32 each.  The kernel executes 5 (three
     # carry-save adders move the rest onto the LOP3 pipe), so the POPC-pipe roofline is taken on the
     # EXECUTED population counts against the rate measured by the XOR+POPC+ADD microbenchmark.
     kp_pairs = float(NF) * NF * npairs
     mm = stage.get("match_ms", 0.0)
-    popc_exec = kp_pairs * 6 / (mm * 1e-3) if mm > 0 else 0.0
-    stages_out["match"] = {"ms": round(mm, 3), "bound": "int_pipe(popc)", "algorithmic_popc32_per_pair": 8, "executed_popc32_per_pair": 6,
+    popc_per = {0: 8, 1: 6, 2: 4, 3: 5}[int(os.environ.get("B200VO_MATCH_CSA", "3"))]
+    popc_exec = kp_pairs * popc_per / (mm * 1e-3) if mm > 0 else 0.0
+    stages_out["match"] = {"ms": round(mm, 3), "bound": "int_pipe(popc)", "algorithmic_popc32_per_pair": 8, "executed_popc32_per_pair": popc_per,
                            "achieved_Gpopc_s": round(popc_exec / 1e9, 1), "peak_Gpopc_s": round(popc_rate / 1e9, 1),
                            "frac": round(popc_exec / popc_rate, 4), "descriptor_pairs_per_s": round(kp_pairs / (mm * 1e-3), 0) if mm > 0 else 0}
     for name in ("select", "filter", "ransac", "pose", "fivept", "score"):
@@ -370,7 +371,7 @@ def run_b200(args):
     total_stage_ms = sum(kernels.values())
     dom = max(kernels, key=kernels.get) if kernels else "match_ms"
     if dom == "match_ms":
-        roof = {"kernel": "match_kernel<4,1>", "bound": "int_pipe", "achieved": round(popc_exec / 1e9, 1), "peak": round(popc_rate / 1e9, 1),
+        roof = {"kernel": "match_kernel<4,%d>" % int(os.environ.get("B200VO_MATCH_CSA", "3")), "bound": "int_pipe", "achieved": round(popc_exec / 1e9, 1), "peak": round(popc_rate / 1e9, 1),
                 "unit": "Gpopc32/s", "frac": round(popc_exec / popc_rate, 4), "traffic": None,
                 "peak_source": "XOR+POPC+ADD microbenchmark measured in this run (b200vo_measure_popc_rate); not an HBM- or tensor-bound kernel: "
                                "its DRAM traffic is ~0.2 MB per 9e6 descriptor pairs (profiles/)",

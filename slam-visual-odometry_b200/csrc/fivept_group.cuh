@@ -49,7 +49,7 @@ constexpr int kPendSlots = 6;         // pending intervals hold >= 2 roots each 
 
 // Per-hypothesis block of shared memory.  Regions whose lifetimes do not overlap share storage:
 // `ex` (phases A-D) with the isolation work lists (phase E), the Sturm recurrence (phase E) with the
-// final bracket list (end of E, F).  2592 bytes = 32 (mod 128): the three groups of a warp touch
+// final bracket list (end of E, F).  2672 bytes = 112 (mod 128): the three groups of a warp touch
 // disjoint banks when they read the same member.
 struct GroupShared {
     FivePointSetup S;                 // N, Bx, By, B1, c -- filled by phases A-D, read by the finish phase
@@ -69,6 +69,7 @@ struct GroupShared {
     int ev_v[2][5], ev_s[2][5];
     unsigned key[16];                 // pivot keys: [0..4] null space, [5..14] elimination
     int ibuf[12];
+    int xflag[2][10];                 // exact path: which interval of the current / previous level holds a root
     int chain_ok[2];
     int fail;
     int nfinal;
@@ -245,14 +246,6 @@ GEOM_HDI int sturm_eval10(const double* p, const double* ca, const double* cb, c
     return cnt;
 }
 
-// the rare exact path (unreliable chain): one lane, generic code, kept out of line
-#if defined(__CUDA_ARCH__)
-__device__ __noinline__
-#else
-inline
-#endif
-int group_fallback_roots(const double* c, double* roots) { return real_roots_unit<10>(c, 10, roots); }
-
 // One isolated root of polynomial h.  Exact roots (lo == hi) of the reversed polynomial must lie
 // in 0 < |w| < 1: w = 0 is z = infinity, |w| = 1 belongs to p itself.
 GEOM_HDI void emit_candidate(GroupShared& gs, int h, double lo, double hi) {
@@ -279,9 +272,10 @@ GEOM_HDI void classify_interval(GroupShared& gs, int h, int nxt, double a, doubl
 
 // pts: x1[5][2] then x2[5][2] (20 doubles, identical in every lane).
 // Eout[slot][9] / okout[slot]: solution of lane r (root index r in the ordered list).  Returns the
-// number of root brackets (0 when the hypothesis is degenerate), or -1 when FALLBACK is false and the
-// hypothesis needs the exact path (nothing is written then).
-template <bool FALLBACK, class Exec>
+// number of root brackets (0 when the hypothesis is degenerate).  FINISH = false stops after the
+// ordered bracket list (gs.v.fin, gs.nfinal): the caller finishes the roots itself (the CUDA kernel
+// re-packs the roots of a whole CTA onto dense lanes).
+template <bool FINISH, class Exec>
 GEOM_HD inline int five_point_group(Exec& ex, GroupShared& gs, const double* pts, double (*Eout)[9], bool* okout) {
     // ------------------------------------------------------------------ phase A: null space
     double a_[B200VO_GRP_SLOTS][5];
@@ -701,24 +695,62 @@ GEOM_HD inline int five_point_group(Exec& ex, GroupShared& gs, const double* pts
         });
         cur = nxt;
     }
-    // Polynomials whose chain was unreliable need the exact derivative-chain method: long, serial,
-    // one lane.  The main launch does not carry it (FALLBACK = false): the hypothesis is deferred to
-    // a dense second launch where every group takes that path together.
-    bool deferred = false;
-    if (!FALLBACK) {
-        if (ex.active && (!gs.ibuf[10] || !gs.ibuf[11])) { deferred = true; ex.active = false; }
-    } else if (ex.any(ex.active && (!gs.ibuf[10] || !gs.ibuf[11]))) {
+    // Polynomials whose chain was unreliable (near-multiple roots, 2-6 % of the hypotheses) take the
+    // exact path of real_roots_unit: the roots of the k-th derivative separate those of the (k-1)-th,
+    // so level by level (linear derivative first) every interval between two consecutive roots of the
+    // previous level holds at most one root, found by its sign change.  The intervals of one level are
+    // independent: lane s takes interval s, ten levels are ten phases (the serial form needs ~55
+    // bracket solves one after another).  Scaled derivatives T[k][i] = c[i+k] C(i+k,k) live in shared
+    // memory (the work lists of the Sturm path are dead by now), so degrees can be run-time values.
+    for (int h = 0; h < 2; ++h) {
+        const bool need = ex.active && !gs.ibuf[10 + h];
+        if (!ex.any(need)) continue;
         ex.run([&](int r) {
-            const int ls = lane_slot(r);
-            const int h = r / 5, t = r - 5 * h;
-            if (t == 0 && !gs.ibuf[10 + h]) {
-                double roots[10], ctmp[11];            // a copy: cc_ itself must stay in registers
-                for (int i = 0; i < 11; ++i) ctmp[i] = cc_[ls][i];
-                const int n = group_fallback_roots(ctmp, roots);
-                gs.ncand[h] = 0;
-                for (int i = 0; i < n && i < 10; ++i) emit_candidate(gs, h, roots[i], roots[i]);
+            if (!need) return;
+            int n = 10;
+            while (n > 0 && gs.S.c[h ? 10 - n : n] == 0.0) --n;
+            if (r == 0) { gs.ibuf[0] = n; gs.ncand[h] = 0; }
+            if (r < n) {                                   // row k = r: the k-th derivative / k!
+                double* row = &gs.u.ex[r * 11 - r * (r - 1) / 2];
+                for (int i = 0; i <= n - r; ++i) {
+                    double binom = 1.0;
+                    for (int j = 1; j <= r; ++j) binom = binom * (double)(i + j) / (double)j;
+                    row[i] = gs.S.c[h ? 10 - (i + r) : i + r] * binom;
+                }
             }
         });
+        for (int k = 9; k >= 0; --k) {
+            ex.run([&](int r) {
+                if (!need) return;
+                const int n = gs.ibuf[0];
+                if (k > n - 1) return;
+                const int dk = n - k, rd = (k + 1) & 1, wr = k & 1;
+                const double* d = &gs.u.ex[k * 11 - k * (k - 1) / 2];
+                double* val = &gs.u.ex[66];                // [2][10] roots of the current / previous level
+                int cnt = 0;
+                double lo = -1.0, hi = 1.0;
+                if (k < n - 1)
+                    for (int j = 0; j < 10; ++j)
+                        if (gs.xflag[rd][j]) {
+                            if (cnt == r - 1) lo = val[rd * 10 + j];
+                            if (cnt == r) hi = val[rd * 10 + j];
+                            ++cnt;
+                        }
+                bool has = false;
+                double root = 0.0;
+                if (r <= cnt) {                            // interval r of cnt + 1
+                    const double flo = horner(d, dk, lo), fhi = horner(d, dk, hi);
+                    if (flo == 0.0) { if (r == 0) { has = true; root = lo; } }
+                    else if (fhi == 0.0) { has = true; root = hi; }
+                    else if ((flo < 0.0) != (fhi < 0.0)) { has = true; root = bracket_root_fast(d, dk, lo, hi, flo); }
+                }
+                gs.xflag[wr][r] = has ? 1 : 0;
+                if (has) {
+                    val[wr * 10 + r] = root;
+                    if (k == 0) emit_candidate(gs, h, root, root);
+                }
+            });
+        }
     }
     // ordered list: roots of p ascending, then those of the reversed polynomial ascending in w
     // (the lists were filled through atomics: ranking makes the order deterministic)
@@ -740,8 +772,8 @@ GEOM_HD inline int five_point_group(Exec& ex, GroupShared& gs, const double* pts
 
     // ------------------------------------------------------------------ phase F: one root per lane
     const int nfinal = ex.active ? gs.nfinal : 0;
-    for (int ls = 0; ls < B200VO_GRP_SLOTS; ++ls) okout[ls] = false;
-    ex.run([&](int r) {
+    if (FINISH) for (int ls = 0; ls < B200VO_GRP_SLOTS; ++ls) okout[ls] = false;
+    if (FINISH) ex.run([&](int r) {
         const int ls = lane_slot(r);
         bool ok = false;
         if (r < nfinal) {
@@ -751,7 +783,7 @@ GEOM_HD inline int five_point_group(Exec& ex, GroupShared& gs, const double* pts
         }
         okout[ls] = ok;
     });
-    return deferred ? -1 : nfinal;
+    return nfinal;
 }
 
 // host convenience (tests/hostsim): all solutions of one sample through the group algorithm

@@ -63,6 +63,12 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t* q, const uint4& t
     const uint32_t twos = tA ^ h4, fB = tA & h4;
     const uint32_t fours = fA ^ fB, eights = fA & fB;
     return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+    } else if (CSA == 3) {
+    // three carry-save adders: 5 POPC + 14 LOP3 -- POPC pipe (5/16 clk) and ALU pipe about balanced
+    const uint32_t l1 = lop3_xor3(x0, x1, x2), h1 = lop3_maj(x0, x1, x2);
+    const uint32_t l2 = lop3_xor3(x3, x4, x5), h2 = lop3_maj(x3, x4, x5);
+    const uint32_t l3 = lop3_xor3(l1, l2, x6), h3 = lop3_maj(l1, l2, x6);
+    return __popc(l3) + __popc(x7) + 2 * (__popc(h1) + __popc(h2) + __popc(h3));
     } else if (CSA == 1) {
     const uint32_t l1 = lop3_xor3(x0, x1, x2), h1 = lop3_maj(x0, x1, x2);
     const uint32_t l2 = lop3_xor3(x3, x4, x5), h2 = lop3_maj(x3, x4, x5);
@@ -212,7 +218,7 @@ match_knn2_kernel(MatchArgs a) {
             const uint32_t colidx = (uint32_t)(col0 + j);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t v = (hamming256<1>(qd[r], t0, t1) << 16) | colidx;
+                const uint32_t v = (hamming256<3>(qd[r], t0, t1) << 16) | colidx;
                 second[r] = min(second[r], max(best[r], v));
                 best[r] = min(best[r], v);
             }
@@ -267,7 +273,8 @@ static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_
     dim3 grid(div_up(n2max, chunk), row_tiles, npairs);
     const int csa = ctx->match_csa;
 #define LAUNCH_MATCH(RR) \
-    do { if (csa == 2) match_kernel<RR, 2><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \
+    do { if (csa == 3) match_kernel<RR, 3><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \
+         else if (csa == 2) match_kernel<RR, 2><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \
          else if (csa == 1) match_kernel<RR, 1><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \
          else match_kernel<RR, 0><<<grid, MT_THREADS, 0, ctx->stream>>>(a); } while (0)
     switch (R) {

@@ -43,18 +43,33 @@ struct RansacArgs {
 // (round-1 history: a thread-per-hypothesis solver ran with 10 of 32 lanes active; a three-phase
 // version with stream compaction fixed the divergence but left 5.6 KB of local memory per thread and
 // 85 % long-scoreboard stalls -- profiles/ncu_r01_final_kernels.txt.)
-constexpr int FPG_THREADS = 128;
-constexpr int FPG_GROUPS = 3 * (FPG_THREADS / 32);
-
-// One hypothesis (pair, h) by the calling group.  FALLBACK = false: a hypothesis whose Sturm chain is
-// unreliable (near-multiple roots, ~2-6 %) is appended to the deferred queue instead of running the
-// long serial exact path inside this warp.
-template <bool FALLBACK>
-__device__ __forceinline__ void solve_hypothesis(const PairView& pv, const RansacArgs& ra, geom::GroupShared& gs, int r, bool in_range,
-                                                 int pair, int h) {
+// Phases A-E run per group (fivept_group.cuh).  COMPACT: the root brackets of the whole CTA (~4.85
+// real roots per hypothesis: half of the lane slots) are re-packed onto dense lanes for the per-root
+// finish (refine, back-substitute, polish), which reads the owning group's setup data from shared
+// memory; only as many warps as there are roots keep running.  !COMPACT: every group finishes its
+// own roots (no CTA barrier, half of the lanes idle in that phase).
+template <int THREADS, int MINB, bool COMPACT>
+__global__ void __launch_bounds__(THREADS, MINB)
+five_point_group_kernel(PairView pv, RansacArgs ra) {
+    constexpr int GROUPS = 3 * (THREADS / 32);
+    extern __shared__ __align__(16) unsigned char fpg_smem[];
+    __shared__ int s_nroot;
+    __shared__ unsigned short s_root[GROUPS * 10];
+    geom::GroupShared* groups = reinterpret_cast<geom::GroupShared*>(fpg_smem);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / geom::kGroupLanes;               // lanes 30, 31 (g == 3) have no group: they only keep the barriers full
+    const int r = lane - geom::kGroupLanes * g;
+    const int slot = warp * 3 + min(g, 2);
+    geom::GroupShared& gs = groups[slot];
+    const int pair = blockIdx.y;
+    if (ra.adaptive && pv.done[pair]) return;             // uniform over the CTA
+    const int hbase = ra.h0 + blockIdx.x * GROUPS;
+    const int h = hbase + slot;
+    const bool in_range = (g < 3) && (h < ra.h0 + ra.nround);
     const int gid = pair * pv.nhyp_cap + h;
-    const int m = in_range ? pv.n_good[pair] : 0;
+    const int m = pv.n_good[pair];
     const bool solve = in_range && m >= ra.min_matches && m >= 5;        // uniform over the group
+    if (COMPACT && threadIdx.x == 0) s_nroot = 0;
     double pts[20];
 #pragma unroll
     for (int k = 0; k < 20; ++k) pts[k] = 0.0;
@@ -74,54 +89,43 @@ __device__ __forceinline__ void solve_hypothesis(const PairView& pv, const Ransa
             pts[10 + 2 * k] = pv.x2x[base + i]; pts[10 + 2 * k + 1] = pv.x2y[base + i];
         }
     }
-    double E[1][9];
-    bool ok[1] = {false};
     geom::DeviceGroupExec ex{r, solve};
-    const int nfinal = geom::five_point_group<FALLBACK>(ex, gs, pts, E, ok);
-    if (!in_range) return;
-    pv.model_ok[(size_t)gid * 10 + r] = ok[0] ? 1 : 0;
-    if (ok[0]) {
-        double* out = pv.models + (size_t)gid * 90 + r * 9;
+    if (COMPACT) {
+        __syncthreads();
+        const int nfinal = geom::five_point_group<false>(ex, gs, pts, (double (*)[9]) nullptr, (bool*)nullptr);
+        if (in_range) {
+            pv.model_ok[(size_t)gid * 10 + r] = 0;
+            if (r == 0) pv.nsol[gid] = nfinal;
+            if (r < nfinal) s_root[atomicAdd(&s_nroot, 1)] = (unsigned short)(slot * 10 + r);
+        }
+        __syncthreads();
+        const int nroot = s_nroot;
+        for (int i = threadIdx.x; i < nroot; i += THREADS) {
+            const int e = s_root[i], sl = e / 10, k = e - sl * 10;
+            const geom::GroupShared& go = groups[sl];
+            geom::RootBracket br;
+            br.a = go.v.fin.a[k]; br.b = go.v.fin.b[k]; br.reversed = go.v.fin.rev[k];
+            double E[9];
+            if (geom::five_point_finish(go.S, br, E)) {
+                const size_t gd = (size_t)pair * pv.nhyp_cap + hbase + sl;
+                double* out = pv.models + gd * 90 + k * 9;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) out[k] = E[0][k];
-    }
-    if (r == 0) {
-        pv.nsol[gid] = max(nfinal, 0);
-        if (!FALLBACK && nfinal < 0) pv.fb_gid[atomicAdd(pv.fb_count, 1u)] = gid;
-    }
-}
-
-__global__ void __launch_bounds__(FPG_THREADS, 4)
-five_point_group_kernel(PairView pv, RansacArgs ra) {
-    extern __shared__ __align__(16) unsigned char fpg_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane / geom::kGroupLanes;               // lanes 30, 31 (g == 3) have no group: they only keep the barriers full
-    const int r = lane - geom::kGroupLanes * g;
-    const int slot = warp * 3 + min(g, 2);
-    geom::GroupShared& gs = reinterpret_cast<geom::GroupShared*>(fpg_smem)[slot];
-    const int pair = blockIdx.y;
-    const int h = ra.h0 + blockIdx.x * FPG_GROUPS + slot;
-    const bool in_range = (g < 3) && (h < ra.h0 + ra.nround) && !(ra.adaptive && pv.done[pair]);
-    solve_hypothesis<false>(pv, ra, gs, r, in_range, pair, h);
-}
-
-// the deferred hypotheses, packed densely: every group of these warps takes the exact path
-__global__ void __launch_bounds__(FPG_THREADS, 3)
-five_point_deferred_kernel(PairView pv, RansacArgs ra) {
-    extern __shared__ __align__(16) unsigned char fpg_smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int g = lane / geom::kGroupLanes;
-    const int r = lane - geom::kGroupLanes * g;
-    const int slot = warp * 3 + min(g, 2);
-    geom::GroupShared& gs = reinterpret_cast<geom::GroupShared*>(fpg_smem)[slot];
-    const unsigned n = *pv.fb_count;
-    for (unsigned base = blockIdx.x * FPG_GROUPS; base < n; base += gridDim.x * FPG_GROUPS) {      // uniform over the CTA
-        const unsigned i = base + slot;
-        const bool in_range = (g < 3) && (i < n);
-        const int gid = in_range ? pv.fb_gid[i] : 0;
-        const int pair = gid / pv.nhyp_cap;
-        solve_hypothesis<true>(pv, ra, gs, r, in_range, pair, gid - pair * pv.nhyp_cap);
-        __syncwarp();
+                for (int q = 0; q < 9; ++q) out[q] = E[q];
+                pv.model_ok[gd * 10 + k] = 1;
+            }
+        }
+    } else {
+        double E[1][9];
+        bool ok[1] = {false};
+        const int nfinal = geom::five_point_group<true>(ex, gs, pts, E, ok);
+        if (!in_range) return;
+        pv.model_ok[(size_t)gid * 10 + r] = ok[0] ? 1 : 0;
+        if (ok[0]) {
+            double* out = pv.models + (size_t)gid * 90 + r * 9;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) out[k] = E[0][k];
+        }
+        if (r == 0) pv.nsol[gid] = nfinal;
     }
 }
 
@@ -212,17 +216,25 @@ score_kernel(PairView pv, RansacArgs ra) {
     }
 }
 
+template <int THREADS, int MINB, bool COMPACT>
+static void launch_fpg(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
+    constexpr int GROUPS = 3 * (THREADS / 32);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(five_point_group_kernel<THREADS, MINB, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(GROUPS * sizeof(geom::GroupShared)));
+        configured = true;
+    }
+    const dim3 grid(div_up(ra.nround, GROUPS), npairs);
+    five_point_group_kernel<THREADS, MINB, COMPACT><<<grid, THREADS, GROUPS * sizeof(geom::GroupShared), ctx->stream>>>(ctx->pairs, ra);
+}
+
 static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
-    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.fb_count, 0, sizeof(unsigned), ctx->stream));
-    const dim3 grid(div_up(ra.nround, FPG_GROUPS), npairs);
-    const size_t smem = FPG_GROUPS * sizeof(geom::GroupShared);
-    five_point_group_kernel<<<grid, FPG_THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
-    B200VO_LAUNCH_CHECK(ctx);
-    // the queue length is only known on the device: a grid that covers ~1/8 of the hypotheses in one
-    // pass (measured share: 2-6 %), grid-stride beyond that; idle CTAs exit at once
-    const long expect = std::max<long>(1, (long)npairs * ra.nround / 8);
-    const int blocks = (int)std::min<long>(148 * 12, (expect + FPG_GROUPS - 1) / FPG_GROUPS);
-    five_point_deferred_kernel<<<blocks, FPG_THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
+    // measured on B200 (1000 frames, H = 1024): 256 threads x 2 CTAs/SM with compaction 8.0 ms; without
+    // compaction 9.4; 128 x 4: 10.2; 64 x 8: 12.3; 512 x 1: 10.3 (larger CTAs keep more warps on the
+    // same instruction-cache lines; beyond 256 the register file fits only one CTA)
+    if (!ctx->fpg_compact) launch_fpg<256, 2, false>(ctx, ra, npairs);        // B200VO_FPG_COMPACT=0 (tests: identical results)
+    else launch_fpg<256, 2, true>(ctx, ra, npairs);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
@@ -238,13 +250,7 @@ static int launch_score(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
 }
 
 int init_ransac_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(five_point_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(FPG_GROUPS * sizeof(geom::GroupShared)));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(five_point_deferred_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(FPG_GROUPS * sizeof(geom::GroupShared)));
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_MAXPTS * sizeof(float4)));
+    cudaError_t e = cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_MAXPTS * sizeof(float4)));
     if (e != cudaSuccess) { set_error("ransac kernel smem attribute: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
     return B200VO_OK;
 }

@@ -190,3 +190,24 @@ def test_adaptive_ransac_equals_truncated_fixed(built, seq_kitti):
         rs, Es, _ = ca.relative_pose(0, 1, pair_id=5, samples=S)
         rfull, Efull, _ = cf.relative_pose(0, 1, pair_id=5, samples=S)
         assert np.array_equal(Es, Efull) and ((int(rs["status"]) >> 16) & 0xFF) == 0
+
+
+def test_five_point_finish_variants_agree(built, seq_kitti, monkeypatch):
+    """The five-point kernel with and without the CTA-level re-packing of roots (B200VO_FPG_COMPACT) must
+    produce byte-identical models and records."""
+    frames = seq_kitti[0]
+    out = []
+    for v in ("1", "0"):
+        monkeypatch.setenv("B200VO_FPG_COMPACT", v)
+        with built.Context(1241, 376, nfeatures=NF, max_frames=4, ransac_hypotheses=NHYP) as c:
+            c.upload_frames(frames, 0)
+            c.detect(0, 2)
+            rec, E, mask = c.relative_pose(0, 1, pair_id=3, want_mask=True)
+            f0, f1 = c.get_features(0), c.get_features(1)
+            good, _, _ = c.match(0, 1)
+            K = seq_kitti[3]
+            x1 = G.normalize_points(np.stack([f0[0]["x"][good["queryIdx"]], f0[0]["y"][good["queryIdx"]]], 1), K)
+            x2 = G.normalize_points(np.stack([f1[0]["x"][good["trainIdx"]], f1[0]["y"][good["trainIdx"]]], 1), K)
+            Es, ns = c.five_point(x1, x2, G.draw_samples(9, 0, 100, len(x1)))
+            out.append((rec.tobytes(), E.tobytes(), mask.tobytes(), Es.tobytes(), ns.tobytes()))
+    assert out[0] == out[1]

@@ -125,7 +125,7 @@ def test_popcount_variants_agree(built, monkeypatch):
     q = rng.integers(0, 256, (1500, 32), dtype=np.uint8); t = rng.integers(0, 256, (1400, 32), dtype=np.uint8)
     q[:300] = t[:300]                      # exact duplicates: distance 0 and ties
     ref = M.nearest(q, t)
-    for v in ("0", "1", "2"):
+    for v in ("0", "1", "2", "3"):
         monkeypatch.setenv("B200VO_MATCH_CSA", v)
         with built.Context(640, 240, nfeatures=500, max_frames=2, ransac_hypotheses=64) as c:
             got = c.match_descriptors(q, t)
