@@ -8,8 +8,10 @@
 //     b = (float)sin((double)theta); each of the 512 pattern points is rotated with separate float
 //     multiplies/adds (no FMA) and rounded half-to-even; bit k of byte i = I(p[16i+2k]) < I(p[16i+2k+1]).
 //
-// One warp per keypoint.  Orientation: lane = column u of the disc, loop over rows, integer
-// redux.sync reduction.  Descriptor: lane = descriptor byte; the lane keeps its 16 pattern points
+// One warp per keypoint.  Orientation: the 31 rows of the disc are read as aligned 32-bit words
+// (9 per row); a lane takes (row, word) items and folds four pixels per instruction with dp4a
+// against precomputed per-byte weights (the x offset inside the disc, 0 outside) and masks, then an
+// integer redux.sync reduction -- the moments are integers, so any summation order is exact.  Descriptor: lane = descriptor byte; the lane keeps its 16 pattern points
 // in registers for the lifetime of the warp; the 32 bytes go out as one coalesced 32-B store.
 // The kernel also assembles the frame's final keypoint array in canonical (octave, y, x) order.
 #include "common.cuh"
@@ -17,8 +19,17 @@
 
 namespace b200vo {
 
-__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
 __device__ __align__(16) int8_t d_pattern[1024];
+// intensity-centroid tables: [alignment of the row start (0..3)][item = row * 9 + word] ->
+// .x = four signed byte weights (u of each pixel, 0 outside the disc), .y = four 0/1 masks
+constexpr int kIcWords = 9, kIcItems = 31 * kIcWords;
+__device__ __align__(8) uint2 d_ic_table[4][kIcItems];
+
+__device__ __forceinline__ int dp4a_u8_s8(uint32_t a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
     const float deg = (float)(180.0 / 3.14159265358979323846);
@@ -65,25 +76,23 @@ orient_kernel(StoreView sv, int first_slot) {
     const LevelGeom g = sv.lv[level];
     const uint32_t key = sv.lkp_key[(size_t)slot * sv.lkp_total + sv.lkp_off[level] + i];
     const int x = (key >> 8) & 0xFFF, y = key >> 20;
-    const uint8_t* __restrict__ c = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset + (size_t)y * g.pitch + x;
-    const int u = lane - kHalfPatch;
-    const int au = abs(u);
+    // row v of the disc starts at byte (x - 15) of image row (y + v); rows are pitched to 128 bytes, so
+    // every row has the same misalignment al and spans words 0..8 of the aligned address below
+    const uint8_t* __restrict__ img = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset;
+    const int xs = x - kHalfPatch, al = xs & 3;
+    const uint8_t* __restrict__ wb = img + (size_t)(y - kHalfPatch) * g.pitch + (xs - al);
+    const uint2* __restrict__ tab = d_ic_table[al];
     int m10 = 0, m01 = 0;
-    if (lane < 31) {
-        // fully unrolled: the 31 row loads are independent and issue back to back (the v1 profile
-        // showed 64 % long-scoreboard stalls with one load in flight per lane)
-        constexpr int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
-        int rowsum[31];
 #pragma unroll
-        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-            const int a = v < 0 ? -v : v;
-            rowsum[v + kHalfPatch] = (au <= umax[a]) ? (int)__ldg(c + v * g.pitch + u) : 0;
+    for (int it = 0; it < (kIcItems + 31) / 32; ++it) {
+        const int item = lane + 32 * it;
+        if (item < kIcItems) {
+            const int row = item / kIcWords, k = item - row * kIcWords;
+            const uint32_t px = __ldg(reinterpret_cast<const uint32_t*>(wb + row * g.pitch) + k);
+            const uint2 wm = __ldg(tab + item);
+            m10 = dp4a_u8_s8(px, wm.x, m10);
+            m01 += (row - kHalfPatch) * dp4a_u8_s8(px, wm.y, 0);
         }
-        int s0 = 0, s1 = 0;
-#pragma unroll
-        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) { s0 += rowsum[v + kHalfPatch]; s1 += v * rowsum[v + kHalfPatch]; }
-        m10 = u * s0;
-        m01 = s1;
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
     m01 = __reduce_add_sync(0xffffffffu, m01);
@@ -140,6 +149,22 @@ brief_kernel(StoreView sv, int first_slot) {
 int upload_brief_pattern() {
     cudaError_t e = cudaMemcpyToSymbol(d_pattern, kBriefPattern31, sizeof(kBriefPattern31));
     if (e != cudaSuccess) { set_error("pattern upload failed: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
+    // intensity-centroid weights: OpenCV's umax table for patch size 31 (half-widths of the disc rows)
+    static const int umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+    static uint2 tab[4][kIcItems];
+    for (int al = 0; al < 4; ++al)
+        for (int row = 0; row < 31; ++row)
+            for (int k = 0; k < kIcWords; ++k) {
+                uint32_t w = 0, m = 0;
+                const int v = row - kHalfPatch, lim = umax[v < 0 ? -v : v];
+                for (int j = 0; j < 4; ++j) {
+                    const int u = 4 * k + j - al - kHalfPatch;
+                    if (u >= -lim && u <= lim) { w |= (uint32_t)(uint8_t)(int8_t)u << (8 * j); m |= 1u << (8 * j); }
+                }
+                tab[al][row * kIcWords + k] = make_uint2(w, m);
+            }
+    e = cudaMemcpyToSymbol(d_ic_table, tab, sizeof(tab));
+    if (e != cudaSuccess) { set_error("orientation table upload failed: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
     return B200VO_OK;
 }
 
