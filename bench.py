@@ -168,7 +168,7 @@ def run_reference(args):
             "config": {"workload": "%d-frame synthetic KITTI-shaped sequence %dx%d, %d ORB features (bounded sample)" % (args.frames, W_IMG, H_IMG, args.features)},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": min(ncpu, pairs), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -190,6 +190,20 @@ def algorithmic_bytes(ctx, nfeatures):
         "brief": sum(px) + 32 * nfeatures,
         "orient": 749 * nfeatures,
     }
+
+
+def accuracy(traj, R_gt, C_gt):
+    """Chained trajectory against the ground truth of the synthetic sequence: similarity-aligned ATE
+    (the reference applies a fixed 0.3 step scale) and mean relative rotation / translation-direction
+    error per pair.  Frame 0 is the identity pose the chain starts from."""
+    from b200vo import trajectory as T
+    poses = np.concatenate([np.concatenate([np.eye(3).ravel(), np.zeros(3)])[None], np.asarray(traj)], 0)
+    n = len(poses)
+    # ground truth relative to its own first frame (the estimate starts at identity)
+    R0, C0 = R_gt[0], C_gt[0]
+    Rg = np.stack([R0.T @ R for R in R_gt[:n]])
+    Cg = np.stack([R0.T @ (C - C0) for C in C_gt[:n]])
+    return {"vs_ground_truth": T.accuracy_report(poses, Rg, Cg)}
 
 
 def run_b200(args):
@@ -420,11 +434,12 @@ def run_b200(args):
                             "value": round(total_pairs / (ms_dev_ad * 1e-3), 1), "e2e": round(total_pairs / (ms_e2e_ad * 1e-3), 1),
                             "mean_hypotheses_per_pair": rounds_ad},
         "cpu_baseline": cpu,
-        "result_check": {"pairs_pose_ok": int(((ok["status"] & 4) != 0).sum()), "pairs_total": int(len(ok)),
-                         "trajectory_end": [round(float(x), 3) for x in traj[-1][9:12]] if traj is not None else None},
+        "result_check": dict({"pairs_pose_ok": int(((ok["status"] & 4) != 0).sum()), "pairs_total": int(len(ok)),
+                              "trajectory_end": [round(float(x), 3) for x in traj[-1][9:12]] if traj is not None else None},
+                             **(accuracy(traj, R_all, C_all) if traj is not None else {})),
         "wall_ms_per_step": round(wall_dev * 1e3, 3),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -439,8 +454,26 @@ def run_b200(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints (NCCL's version
+    banner, torchrun notices) was redirected to stderr, so stdout carries exactly this line."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                   # fd 1 -> stderr for the duration of the run (C libraries included)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

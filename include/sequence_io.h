@@ -1,0 +1,20 @@
+// Image-sequence input for the headless build: what the reference's main() does around
+// process_frame (src/main.cpp:26-49 load_image_paths, :136 cv::imread, :146-151 timestamp from the
+// file stem).  OpenCV's image codecs are not available in this build, so the reader understands the
+// binary Netpbm formats (P5 gray, P6 RGB -> BGR like cv::imread); with real OpenCV installed use
+// cv::imread instead and everything downstream is unchanged.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "vo_cv_compat.h"
+
+// png / jpg / jpeg as in the reference, plus pgm / ppm; regular files only; lexicographic order
+std::vector<std::string> load_image_paths(const std::string& dataset_path);
+// the file stem parsed as a double, or `index` when it is not a number (src/main.cpp:146-151)
+double timestamp_from_path(const std::string& path, size_t index);
+// P5 -> CV_8UC1, P6 -> CV_8UC3 in BGR order; empty Mat on failure (like cv::imread)
+cv::Mat read_pnm(const std::string& path);
+bool write_pnm(const std::string& path, const cv::Mat& image);
+// "timestamp tx ty tz r00 r01 ... r22" per line (T_wc)
+bool save_trajectory_text(const std::string& path, const std::vector<double>& timestamps, const std::vector<class Pose>& poses);

@@ -264,7 +264,8 @@ static int pick_rows_per_thread(int n1) {
 
 static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_expected, int npairs) {
     if (npairs <= 0 || n1max <= 0 || n2max <= 0) return B200VO_OK;
-    const int R = pick_rows_per_thread(n1_expected);
+    int R = pick_rows_per_thread(n1_expected);
+    if (const char* v = getenv("B200VO_MATCH_R")) { const int f = atoi(v); if (f == 1 || f == 2 || f == 3 || f == 4 || f == 6 || f == 8) R = f; }
     const int row_tiles = div_up(n1max, MT_THREADS * R);
     // enough CTAs to fill 148 SMs a few times over when the batch is small
     int chunk = MT_MAXCHUNK;
@@ -278,7 +279,10 @@ static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_
          else if (csa == 1) match_kernel<RR, 1><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \
          else match_kernel<RR, 0><<<grid, MT_THREADS, 0, ctx->stream>>>(a); } while (0)
     switch (R) {
+        case 8: LAUNCH_MATCH(8); break;
+        case 6: LAUNCH_MATCH(6); break;
         case 4: LAUNCH_MATCH(4); break;
+        case 3: LAUNCH_MATCH(3); break;
         case 2: LAUNCH_MATCH(2); break;
         default: LAUNCH_MATCH(1); break;
     }

@@ -175,11 +175,10 @@ __device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, 
 // model can neither win nor tie), which removes most of the work of the spurious roots.
 constexpr int SC_THREADS = 256;
 constexpr int SC_HB = 64;
-constexpr int SC_MAXPTS = 3072;                            // 48 KB of float4
+constexpr int SC_MAXPTS = 2048;                            // staging capacity: 32 KB of float4 (pairs with more good matches read global memory)
 
-template <bool STAGED>
 __global__ void __launch_bounds__(SC_THREADS)
-score_kernel(PairView pv, RansacArgs ra) {
+score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
     extern __shared__ __align__(16) unsigned char sc_smem[];
     const int pair = blockIdx.y;
     if (ra.adaptive && pv.done[pair]) return;
@@ -188,7 +187,8 @@ score_kernel(PairView pv, RansacArgs ra) {
     const int hb0 = ra.h0 + blockIdx.x * SC_HB;
     const int hb1 = min(hb0 + SC_HB, ra.h0 + ra.nround);
     const float4* xf = pv.xf + (size_t)pair * pv.kp_cap;
-    if (STAGED) {
+    const bool staged = m <= stage_cap;                    // uniform over the CTA
+    if (staged) {
         float4* s = reinterpret_cast<float4*>(sc_smem);
         for (int i = threadIdx.x; i < m; i += SC_THREADS) s[i] = xf[i];
         __syncthreads();
@@ -206,7 +206,8 @@ score_kernel(PairView pv, RansacArgs ra) {
 #pragma unroll
         for (int k = 0; k < 9; ++k) E[k] = mp[k];
         const int floor_count = pv.counts ? 0 : (int)(*(volatile unsigned long long*)&pv.best[pair] >> 32);
-        const int cnt = warp_count_inliers<STAGED>(pv, pair, m, E, xf, thr, lane, floor_count);
+        const int cnt = staged ? warp_count_inliers<true>(pv, pair, m, E, xf, thr, lane, floor_count)
+                               : warp_count_inliers<false>(pv, pair, m, E, xf, thr, lane, floor_count);
         if (lane == 0) {
             if (pv.counts) pv.counts[gid * 10 + s] = cnt;
             const unsigned long long packed =
@@ -241,16 +242,14 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
 
 static int launch_score(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     const dim3 grid(div_up(ra.nround, SC_HB), npairs);
-    if (ctx->pairs.kp_cap <= SC_MAXPTS)
-        score_kernel<true><<<grid, SC_THREADS, (size_t)ctx->pairs.kp_cap * sizeof(float4), ctx->stream>>>(ctx->pairs, ra);
-    else
-        score_kernel<false><<<grid, SC_THREADS, 0, ctx->stream>>>(ctx->pairs, ra);
+    const int cap = std::min(ctx->pairs.kp_cap, SC_MAXPTS);
+    score_kernel<<<grid, SC_THREADS, (size_t)cap * sizeof(float4), ctx->stream>>>(ctx->pairs, ra, cap);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
 
 int init_ransac_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(score_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_MAXPTS * sizeof(float4)));
+    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_MAXPTS * sizeof(float4)));
     if (e != cudaSuccess) { set_error("ransac kernel smem attribute: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
     return B200VO_OK;
 }

@@ -1,0 +1,62 @@
+// slam_vo_headless: the reference's slam_vo_run (src/main.cpp:51-220) without its Pangolin / highgui
+// front end -- find the dataset directory, list the images in order, and run
+//     image -> Frame(i, image) -> timestamp from the file stem -> VisualOdometry::process_frame
+// once per frame exactly as src/main.cpp:128-155 does; then write the trajectory as text instead of
+// screenshots.  `--batched` uses the process_sequence extension (same poses, launch batches).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sequence_io.h"
+#include "visual_odometry.h"
+
+int main(int argc, char** argv) {
+    std::string dir, out = "trajectory.txt";
+    bool batched = false;
+    int nfeatures = 1200;
+    for (int i = 1; i < argc; ++i) {
+        if (!std::strcmp(argv[i], "--batched")) batched = true;
+        else if (!std::strcmp(argv[i], "--features") && i + 1 < argc) nfeatures = std::atoi(argv[++i]);
+        else if (!std::strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
+        else dir = argv[i];
+    }
+    if (dir.empty()) { std::fprintf(stderr, "usage: %s <image directory> [--batched] [--features N] [--out file]\n", argv[0]); return 2; }
+    std::vector<std::string> paths;
+    try { paths = load_image_paths(dir); } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
+    if (paths.empty()) { std::fprintf(stderr, "No images found in dataset directory: %s\n", dir.c_str()); return 1; }      // main.cpp:92-95
+    const cv::Mat first = read_pnm(paths[0]);
+    if (first.empty()) { std::fprintf(stderr, "Failed to load first image: %s (this build decodes P5/P6 only)\n", paths[0].c_str()); return 1; }
+    try {
+        VisualOdometry::Options opt;
+        opt.nfeatures = nfeatures;
+        VisualOdometry vo(first.cols, first.rows, opt);
+        std::vector<double> stamps;
+        if (batched) {
+            std::vector<cv::Mat> images;
+            for (size_t i = 0; i < paths.size(); ++i) {
+                cv::Mat im = read_pnm(paths[i]);
+                if (im.empty()) { std::fprintf(stderr, "Failed to load image: %s\n", paths[i].c_str()); continue; }         // main.cpp:137-140
+                images.push_back(im);
+                stamps.push_back(timestamp_from_path(paths[i], i));
+            }
+            vo.process_sequence(images);
+        } else {
+            for (size_t i = 0; i < paths.size(); ++i) {
+                cv::Mat im = read_pnm(paths[i]);
+                if (im.empty()) { std::fprintf(stderr, "Failed to load image: %s\n", paths[i].c_str()); continue; }
+                Frame frame((int)i, im);
+                frame.timestamp = timestamp_from_path(paths[i], i);
+                stamps.push_back(frame.timestamp);
+                vo.process_frame(frame);
+            }
+        }
+        const std::vector<Pose> traj = vo.get_trajectory_poses();
+        if (!save_trajectory_text(out, stamps, traj)) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
+        std::printf("%zu frames, trajectory written to %s\n", traj.size(), out.c_str());
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}

@@ -5,6 +5,7 @@
 #include <string>
 #include <vector>
 
+#include "sequence_io.h"
 #include "visual_odometry.h"
 
 namespace { thread_local std::string g_msg; }
@@ -75,6 +76,36 @@ int vo_host_last_F(void* h, double* F) {
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) F[i * 3 + j] = f(i, j);
     return 1;
+}
+
+// ---- sequence I/O (include/sequence_io.h): listing, timestamps, Netpbm round trip
+int vo_host_list_images(const char* dir, char* out, int cap) {
+    try {
+        std::string joined;
+        const std::vector<std::string> p = load_image_paths(dir);
+        for (const std::string& s : p) { joined += s; joined += '\n'; }
+        if ((int)joined.size() + 1 > cap) return -2;
+        std::memcpy(out, joined.c_str(), joined.size() + 1);
+        return (int)p.size();
+    } catch (const std::exception& e) { g_msg = e.what(); return -1; }
+}
+
+double vo_host_timestamp(const char* path, int index) { return timestamp_from_path(path, (size_t)index); }
+
+// returns channels (1 / 3), 0 on failure; data = rows*cols*channels bytes, BGR for colour
+int vo_host_read_pnm(const char* path, unsigned char* data, int cap, int* rows, int* cols) {
+    const cv::Mat m = read_pnm(path);
+    if (m.empty()) return 0;
+    const int ch = m.channels();
+    if (cap < m.rows * m.cols * ch) return -2;
+    for (int y = 0; y < m.rows; ++y) std::memcpy(data + (size_t)y * m.cols * ch, m.ptr<uint8_t>(y), (size_t)m.cols * ch);
+    *rows = m.rows; *cols = m.cols;
+    return ch;
+}
+
+int vo_host_write_pnm(const char* path, const unsigned char* data, int rows, int cols, int channels) {
+    cv::Mat m(rows, cols, channels == 3 ? CV_8UC3 : CV_8UC1, const_cast<unsigned char*>(data));
+    return write_pnm(path, m) ? 1 : 0;
 }
 
 }  // extern "C"

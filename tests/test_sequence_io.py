@@ -1,0 +1,140 @@
+"""Sequence input and trajectory report: image listing /
+timestamps as the reference's main loop does them (src/main.cpp:26-49, :146-151), the Netpbm
+reader of the C++ headless build, TUM export, similarity-aligned ATE / RPE, epipolar residual."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def host(built):
+    lib = ctypes.CDLL(built.HOST_LIB_PATH)
+    lib.vo_host_timestamp.restype = ctypes.c_double
+    return lib
+
+
+def _touch(p):
+    open(p, "wb").close()
+
+
+def test_image_listing_matches_reference_rules(built, host, tmp_path):
+    from b200vo import dataset as D
+    names = ["000010.png", "000002.PNG", "b.jpg", "a.JPEG", "notes.txt", "000001.pgm", "c.ppm", "x.bmp"]
+    for n in names:
+        _touch(tmp_path / n)
+    os.mkdir(tmp_path / "sub.png")                       # directories are skipped (regular files only)
+    want = sorted(str(tmp_path / n) for n in names if n.lower().endswith((".png", ".jpg", ".jpeg", ".pgm", ".ppm")))
+    assert D.load_image_paths(str(tmp_path)) == want
+    buf = ctypes.create_string_buffer(1 << 16)
+    n = host.vo_host_list_images(str(tmp_path).encode(), buf, len(buf))
+    assert n == len(want) and buf.value.decode().split("\n")[:-1] == want
+
+
+def test_timestamp_from_stem(built, host):
+    from b200vo import dataset as D
+    for path, idx, want in (("/d/000123.png", 7, 123.0), ("/d/1403636579.763555.png", 0, 1403636579.763555), ("/d/frame_12.png", 5, 5.0)):
+        assert D.timestamp_from_path(path, idx) == want
+        assert host.vo_host_timestamp(path.encode(), idx) == want
+
+
+def test_pnm_round_trip_and_bgr_order(built, host, tmp_path):
+    from b200vo import dataset as D
+    rng = np.random.default_rng(0)
+    gray = rng.integers(0, 256, (37, 53), dtype=np.uint8)
+    bgr = rng.integers(0, 256, (21, 34, 3), dtype=np.uint8)
+    for arr, name in ((gray, "g.pgm"), (bgr, "c.ppm")):
+        p = str(tmp_path / name)
+        ch = 1 if arr.ndim == 2 else 3
+        assert host.vo_host_write_pnm(p.encode(), arr.ctypes.data_as(ctypes.c_void_p), arr.shape[0], arr.shape[1], ch) == 1
+        out = np.zeros(arr.size, np.uint8)
+        r, c = ctypes.c_int(), ctypes.c_int()
+        assert host.vo_host_read_pnm(p.encode(), out.ctypes.data_as(ctypes.c_void_p), out.size, ctypes.byref(r), ctypes.byref(c)) == ch
+        assert (r.value, c.value) == arr.shape[:2] and np.array_equal(out.reshape(arr.shape), arr)
+        assert np.array_equal(D.read_image(p), arr)       # Pillow path: the same pixels, BGR for colour
+    with open(tmp_path / "c.ppm", "rb") as f:             # on disk the file is RGB
+        raw = f.read()
+    assert raw[-3:] == bytes(bgr[-1, -1, ::-1])
+    # a comment line in the header is legal Netpbm
+    p = str(tmp_path / "h.pgm")
+    with open(p, "wb") as f:
+        f.write(b"P5\n# made by hand\n3 2\n255\n" + bytes(range(6)))
+    out = np.zeros(6, np.uint8); r, c = ctypes.c_int(), ctypes.c_int()
+    assert host.vo_host_read_pnm(p.encode(), out.ctypes.data_as(ctypes.c_void_p), 6, ctypes.byref(r), ctypes.byref(c)) == 1
+    assert (r.value, c.value) == (2, 3) and out.tolist() == list(range(6))
+    assert host.vo_host_read_pnm(str(tmp_path / "missing.pgm").encode(), out.ctypes.data_as(ctypes.c_void_p), 6, ctypes.byref(r), ctypes.byref(c)) == 0
+
+
+def test_tum_round_trip_and_alignment(built, tmp_path):
+    from b200vo import synth, trajectory as T
+    R, C = synth.make_trajectory(40)
+    p = str(tmp_path / "traj.txt")
+    T.save_tum(p, R, C, np.arange(40) * 0.1)
+    ts, R2, C2 = T.load_tum(p)
+    assert np.allclose(ts, np.arange(40) * 0.1) and np.abs(R2 - R).max() < 1e-8 and np.abs(C2 - C).max() < 1e-8
+    # a similarity-transformed copy has zero ATE and zero RPE
+    th = 0.3
+    Q = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    est_C = 0.3 * (Q @ C.T).T + np.array([1.0, -2.0, 0.5])
+    est_R = np.stack([Q @ r for r in R])
+    ate, s = T.ate_rmse(est_C, C)
+    assert ate < 1e-9 and abs(s - 1 / 0.3) < 1e-9
+    rr, rt = T.rpe(est_R, est_C, R, C)
+    assert rr < 1e-6 and rt < 1e-5
+    poses = np.concatenate([est_R.reshape(-1, 9), est_C], 1)
+    rep = T.accuracy_report(poses, R, C)
+    assert rep["frames"] == 40 and rep["ate_rmse_aligned"] < 1e-6
+
+
+def test_epipolar_residual_of_exact_geometry(built):
+    from b200vo import synth, trajectory as T
+    R_wc, C_w = synth.make_trajectory(2)
+    K = synth.camera_matrix(640, 240)
+    rng = np.random.default_rng(1)
+    X = np.c_[rng.uniform(-3, 3, 50), rng.uniform(-1, 1, 50), rng.uniform(4, 12, 50)]
+    def proj(i):
+        xc = (R_wc[i].T @ (X - C_w[i]).T).T
+        return (K @ (xc / xc[:, 2:]).T).T[:, :2]
+    R, t = synth.relative_pose_gt(R_wc, C_w, 0)
+    E = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]]) @ R
+    F = np.linalg.inv(K).T @ E @ np.linalg.inv(K)
+    assert T.epipolar_residual(F / np.linalg.norm(F), proj(0), proj(1)) < 1e-9
+
+
+@pytest.mark.gpu
+def test_run_directory_equals_batched_pipeline(built, seq_small, tmp_path):
+    """PNG files on disk -> run_directory must give the poses of the in-memory batched path, and the C++
+    headless driver (Netpbm input, per-frame process_frame) the same trajectory."""
+    import subprocess
+    from PIL import Image
+    from b200vo import dataset as D, trajectory as T
+    frames = seq_small[0]
+    for i, f in enumerate(frames):
+        Image.fromarray(f).save(str(tmp_path / ("%06d.png" % i)))
+    poses, recs, stamps, paths = D.run_directory(str(tmp_path), nfeatures=1000, batch_frames=2, ransac_hypotheses=256)
+    assert len(paths) == len(frames) and stamps.tolist() == [0.0, 1.0, 2.0]
+    with built.Context(640, 240, nfeatures=1000, max_frames=8, ransac_hypotheses=256) as ctx:
+        ctx.upload_frames(frames, 0)
+        ctx.detect(0, len(frames))
+        ref = ctx.process_pairs(0, len(frames) - 1, 0)
+    assert recs.tobytes() == ref.tobytes()
+    assert np.array_equal(poses[1:], built.chain_trajectory(ref))
+    # C++ headless executable on PGM copies of the same frames
+    pg = tmp_path / "pgm"
+    os.mkdir(pg)
+    for i, f in enumerate(frames):
+        with open(pg / ("%06d.pgm" % i), "wb") as fh:
+            fh.write(b"P5\n%d %d\n255\n" % (f.shape[1], f.shape[0]) + f.tobytes())
+    exe = os.path.join(os.path.dirname(built.LIB_PATH), "slam_vo_headless")
+    out = str(tmp_path / "traj.txt")
+    r = subprocess.run([exe, str(pg), "--features", "1000", "--out", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = np.array([l.split() for l in open(out) if not l.startswith("#")], float)
+    assert len(rows) == len(frames) and np.allclose(rows[:, 0], [0, 1, 2])
+    # the per-frame C++ path uses the default 1024 hypotheses; compare against that configuration
+    with built.Context(640, 240, nfeatures=1000, max_frames=8) as ctx:
+        ctx.upload_frames(frames, 0)
+        ctx.detect(0, len(frames))
+        ref2 = built.chain_trajectory(ctx.process_pairs(0, len(frames) - 1, 0))
+    assert np.allclose(rows[1:, 1:4], ref2[:, 9:12], atol=1e-8) and np.allclose(rows[1:, 4:13], ref2[:, :9], atol=1e-9)
