@@ -256,6 +256,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     TRY(dev_alloc(ctx, &sv.lkp_count, S * kLevels));
     TRY(dev_alloc(ctx, &sv.kp, S * sv.kp_cap));
     TRY(dev_alloc(ctx, &sv.desc, S * sv.kp_cap * kDescBytes));
+    TRY(dev_alloc(ctx, &sv.kp_mom, S * sv.kp_cap));
+    TRY(dev_alloc(ctx, &sv.kp_rot, S * sv.kp_cap));
     TRY(dev_alloc(ctx, &sv.kp_count, S));
     TRY(dev_alloc(ctx, &sv.flags, S));
 

@@ -54,6 +54,8 @@ struct StoreView {
     // final features
     b200vo_keypoint* kp;       // [slots][kp_cap]
     uint8_t* desc;             // [slots][kp_cap][32]
+    int2* kp_mom;              // [slots][kp_cap] intensity-centroid moments (m10, m01), canonical order
+    float2* kp_rot;            // [slots][kp_cap] (cos, sin) of the keypoint angle as the descriptor uses them
     int* kp_count;             // [slots]
     int* flags;                // [slots] overflow flags
     int kp_cap;

@@ -96,19 +96,47 @@ orient_kernel(StoreView sv, int first_slot) {
     }
     m10 = __reduce_add_sync(0xffffffffu, m10);
     m01 = __reduce_add_sync(0xffffffffu, m01);
-    if (lane == 0) {
-        b200vo_keypoint kp;
-        kp.x = __fmul_rn((float)x, g.scale);
-        kp.y = __fmul_rn((float)y, g.scale);
-        kp.size = __fmul_rn(31.0f, g.scale);
-        kp.angle = fast_atan2_deg((float)m01, (float)m10);
-        kp.response = sv.lkp_resp[(size_t)slot * sv.lkp_total + sv.lkp_off[level] + i];
-        kp.octave = level;
-        kp.class_id = -1;
-        kp.lx = (int16_t)x;
-        kp.ly = (int16_t)y;
-        sv.kp[(size_t)slot * sv.kp_cap + base + i] = kp;
+    if (lane == 0) sv.kp_mom[(size_t)slot * sv.kp_cap + base + i] = make_int2(m10, m01);
+}
+
+// One THREAD per keypoint: angle = fastAtan2(m01, m10), the rotation (cos, sin) the descriptor uses,
+// and the final keypoint record in canonical (octave, y, x) order.  (As the tail of the warp-per-
+// keypoint kernels these ~300 scalar instructions -- a division, a double-precision sincos -- cost a
+// full warp instruction stream per keypoint; here 32 keypoints share one.)
+__global__ void __launch_bounds__(256)
+keypoint_finalize_kernel(StoreView sv, int first_slot) {
+    const int slot = (first_slot + blockIdx.y) % sv.slots;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int* counts = sv.lkp_count + slot * kLevels;
+    int level = 0, base = 0, total = 0;
+#pragma unroll
+    for (int l = 0; l < kLevels; ++l) {
+        const int c = counts[l];
+        if (i >= total + c) { level = l + 1; base = total + c; }
+        total += c;
     }
+    if (i >= min(total, sv.kp_cap)) return;
+    const int li = i - base;
+    const float scale = sv.lv[level].scale;
+    const uint32_t key = sv.lkp_key[(size_t)slot * sv.lkp_total + sv.lkp_off[level] + li];
+    const int x = (key >> 8) & 0xFFF, y = key >> 20;
+    const int2 mom = sv.kp_mom[(size_t)slot * sv.kp_cap + i];
+    b200vo_keypoint kp;
+    kp.x = __fmul_rn((float)x, scale);
+    kp.y = __fmul_rn((float)y, scale);
+    kp.size = __fmul_rn(31.0f, scale);
+    kp.angle = fast_atan2_deg((float)mom.y, (float)mom.x);
+    kp.response = sv.lkp_resp[(size_t)slot * sv.lkp_total + sv.lkp_off[level] + li];
+    kp.octave = level;
+    kp.class_id = -1;
+    kp.lx = (int16_t)x;
+    kp.ly = (int16_t)y;
+    sv.kp[(size_t)slot * sv.kp_cap + i] = kp;
+    // descriptor rotation: theta = angle * (float)(pi/180); a = (float)cos((double)theta), b = (float)sin(...)
+    const float theta = __fmul_rn(kp.angle, (float)(3.14159265358979323846 / 180.0));
+    double sd, cd;
+    sincos((double)theta, &sd, &cd);
+    sv.kp_rot[(size_t)slot * sv.kp_cap + i] = make_float2((float)cd, (float)sd);
 }
 
 // grid: (ceil(kp_cap / 8), n); one warp per keypoint
@@ -128,8 +156,8 @@ brief_kernel(StoreView sv, int first_slot) {
     const b200vo_keypoint kp = sv.kp[(size_t)slot * sv.kp_cap + i];
     const LevelGeom g = sv.lv[kp.octave];
     const uint8_t* __restrict__ c = sv.blur + (size_t)slot * sv.slot_bytes + g.offset + (size_t)kp.ly * g.pitch + kp.lx;
-    const float theta = __fmul_rn(kp.angle, (float)(3.14159265358979323846 / 180.0));
-    const float a = (float)cos((double)theta), b = (float)sin((double)theta);
+    const float2 rot = sv.kp_rot[(size_t)slot * sv.kp_cap + i];       // (cos, sin) from keypoint_finalize_kernel
+    const float a = rot.x, b = rot.y;
     uint32_t byte = 0;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -173,6 +201,8 @@ int launch_orient(b200vo_ctx* ctx, int first_slot, int n) {
     for (int l = 0; l < kLevels; ++l) maxkp = max(maxkp, ctx->store.lv[l].kp_cap);
     dim3 grid(div_up(maxkp, 8), kLevels, n);
     orient_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, first_slot);
+    B200VO_LAUNCH_CHECK(ctx);
+    keypoint_finalize_kernel<<<dim3(div_up(ctx->store.kp_cap, 256), n), 256, 0, ctx->stream>>>(ctx->store, first_slot);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
