@@ -239,7 +239,11 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         tab_total += 2 * (int)(round_up(g.w, 4) + round_up(g.h, 4));
         sv.cand_off[l] = sv.cand_total; sv.cand_total += g.cand_cap;
         sv.lkp_off[l] = sv.lkp_total; sv.lkp_total += g.kp_cap;
-        if ((size_t)g.sel_cap * 12 > 200 * 1024) { set_error("nfeatures too large for the selection kernel"); b200vo_destroy(ctx); return B200VO_ERR_BAD_ARG; }
+        {   // shared memory of the selection kernel: sel_cap (key, response) + the sorted output pairs
+            size_t p2k = 64;
+            while (p2k < (size_t)g.kp_cap) p2k <<= 1;
+            if ((size_t)g.sel_cap * 8 + p2k * 8 > 220 * 1024) { set_error("nfeatures too large for the selection kernel"); b200vo_destroy(ctx); return B200VO_ERR_BAD_ARG; }
+        }
     }
     sv.slot_bytes = round_up(off, (size_t)sv.lv[0].pitch);       // frames form a regular 3-D array for batched copies
     sv.kp_cap = (int)round_up((size_t)opt->nfeatures + std::max(opt->nfeatures / 16, 64), 64);

@@ -7,10 +7,12 @@
 // (1/(4*7*255))^4, evaluated in float WITHOUT fused multiply-add, in OpenCV's operation order.
 //
 // One CTA per (slot, level).  The CTA (1) finds the FAST-score cut from the 256-bin histogram the
-// FAST kernel produced, (2) gathers the survivors into shared memory and bitonic-sorts them by
-// packed (y, x) so every later step is in raster order, (3) computes Harris, (4) finds the N_l-th
-// largest response with a second in-shared-memory sort, (5) compacts order-preservingly.
+// FAST kernel produced, (2) gathers the survivors into shared memory, (3) computes Harris, (4) finds
+// the N_l-th largest response by radix selection (four 256-bin histogram passes), (5) keeps every
+// response >= it and bitonic-sorts only those (key, response) pairs into raster order.  (v1 sorted
+// the 2 N_l survivors twice -- 79 % of the kernel's instructions.)
 #include "common.cuh"
+#include <algorithm>
 
 namespace b200vo {
 
@@ -23,13 +25,13 @@ __device__ __forceinline__ uint32_t float_key_desc(float f) {
     return ~b;
 }
 
-__device__ void bitonic_sort_u32(uint32_t* a, int n /* power of two */) {
+__device__ void bitonic_sort_u64(unsigned long long* a, int n /* power of two */) {
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
                 const int p = i ^ j;
                 if (p > i) {
-                    const uint32_t x = a[i], y = a[p];
+                    const unsigned long long x = a[i], y = a[p];
                     const bool up = (i & k) == 0;
                     if ((x > y) == up) { a[i] = y; a[p] = x; }
                 }
@@ -37,6 +39,47 @@ __device__ void bitonic_sort_u32(uint32_t* a, int n /* power of two */) {
             __syncthreads();
         }
     }
+}
+
+// k-th smallest (1-based) of the keys d_i = float_key_desc(resp[i]), i < m, by most-significant-byte-first
+// radix selection: four passes of a 256-bin shared-memory histogram instead of a full sort.
+__device__ uint32_t radix_select_kth(const float* resp, int m, int k, int* hist /* [256] shared */, int* s_pick /* [2] shared */) {
+    uint32_t prefix = 0, mask = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x) {
+            const uint32_t d = float_key_desc(resp[i]);
+            if ((d & mask) == prefix) atomicAdd(&hist[(d >> (8 * pass)) & 0xFFu], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {                       // lane L owns bins [8L, 8L+8): first bin whose running count reaches k
+            const int lane = threadIdx.x;
+            int local[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { local[i] = hist[lane * 8 + i]; sum += local[i]; }
+            int incl = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += v;
+            }
+            int run = incl - sum;                      // count in the bins below this lane's
+            if (run < k && incl >= k) {                // the k-th element falls into one of this lane's bins
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (run < k && run + local[i] >= k) { s_pick[0] = lane * 8 + i; s_pick[1] = run; }
+                    run += local[i];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (uint32_t)s_pick[0] << (8 * pass);
+        mask |= 0xFFu << (8 * pass);
+        k -= s_pick[1];
+        __syncthreads();
+    }
+    return prefix;
 }
 
 __device__ __forceinline__ float harris_at(const uint8_t* __restrict__ img, int pitch, int x, int y) {
@@ -70,17 +113,18 @@ __device__ __forceinline__ float harris_at(const uint8_t* __restrict__ img, int 
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(StoreView sv, int first_slot) {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ __align__(8) unsigned char smem_raw[];
     const int level = blockIdx.x;
     const int slot = (first_slot + blockIdx.y) % sv.slots;
     const LevelGeom g = sv.lv[level];
-    uint32_t* keys = smem;                               // [sel_cap]
-    float* resp = reinterpret_cast<float*>(smem + g.sel_cap);   // [sel_cap]
-    uint32_t* work = smem + 2 * g.sel_cap;               // [sel_cap]
-    __shared__ int s_cut, s_m, s_scan[SEL_THREADS + 1];
-    __shared__ uint32_t s_kth;
+    int P2 = 64;                                         // power of two >= kp_cap of this level
+    while (P2 < g.kp_cap) P2 <<= 1;
+    unsigned long long* pairs = reinterpret_cast<unsigned long long*>(smem_raw);       // [P2] (key << 32 | response bits)
+    uint32_t* keys = reinterpret_cast<uint32_t*>(pairs + P2);                            // [sel_cap]
+    float* resp = reinterpret_cast<float*>(keys + g.sel_cap);                            // [sel_cap]
+    __shared__ int s_cut, s_m, s_out, s_hist[256], s_pick[2];
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int total = sv.cand_count[slot * kLevels + level];
     const int cnt = min(total, g.cand_cap);
     if (tid == 0 && total > g.cand_cap) atomicOr(&sv.flags[slot], 1);
@@ -110,28 +154,29 @@ select_kernel(StoreView sv, int first_slot) {
             for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
             cut = max(best, 0);
         }
-        if (tid == 0) { s_cut = (n2 > 0) ? cut : 256; s_m = 0; }
+        if (tid == 0) { s_cut = (n2 > 0) ? cut : 256; s_m = 0; s_out = 0; }
     }
     __syncthreads();
 
-    // (2) gather survivors, sort by (y, x)
+    // (2) gather the survivors (warp-aggregated append; the order does not matter yet)
     const uint32_t* cand = sv.cand + (size_t)slot * sv.cand_total + sv.cand_off[level];
     const uint32_t cut = (uint32_t)s_cut;
-    for (int i = tid; i < cnt; i += SEL_THREADS) {
-        const uint32_t k = cand[i];
-        if ((k & 0xFFu) >= cut) {
-            const int j = atomicAdd(&s_m, 1);
-            if (j < g.sel_cap) keys[j] = k;
+    for (int i0 = 0; i0 < cnt; i0 += SEL_THREADS) {
+        const int i = i0 + tid;
+        const uint32_t k = (i < cnt) ? cand[i] : 0u;
+        const bool keep = (i < cnt) && ((k & 0xFFu) >= cut);
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_m, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int j = base + __popc(bal & ((1u << lane) - 1u));
+            if (keep && j < g.sel_cap) keys[j] = k;
         }
     }
     __syncthreads();
     int m = s_m;
     if (m > g.sel_cap) { if (tid == 0) atomicOr(&sv.flags[slot], 2); m = g.sel_cap; }
-    int P = 1;
-    while (P < m) P <<= 1;
-    for (int i = m + tid; i < P; i += SEL_THREADS) keys[i] = 0xFFFFFFFFu;
-    __syncthreads();
-    bitonic_sort_u32(keys, P);
 
     // (3) Harris
     const uint8_t* img = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset;
@@ -141,49 +186,52 @@ select_kernel(StoreView sv, int first_slot) {
     }
     __syncthreads();
 
-    // (4) N_l-th largest response (ties kept)
+    // (4) N_l-th largest response (ties kept): radix selection on the order-preserving key
     uint32_t kth = 0xFFFFFFFFu;    // keep all
-    if (m > g.nfeat) {
-        for (int i = tid; i < P; i += SEL_THREADS) work[i] = (i < m) ? float_key_desc(resp[i]) : 0xFFFFFFFFu;
-        __syncthreads();
-        bitonic_sort_u32(work, P);
-        if (tid == 0) s_kth = work[g.nfeat - 1];
-        __syncthreads();
-        kth = s_kth;
-    }
+    if (m > g.nfeat && g.nfeat > 0) kth = radix_select_kth(resp, m, g.nfeat, s_hist, s_pick);
 
-    // (5) order-preserving compaction
-    const int per = (m + SEL_THREADS - 1) / SEL_THREADS;
-    const int lo = min(tid * per, m), hi = min(lo + per, m);
-    int c = 0;
-    for (int i = lo; i < hi; ++i) c += (float_key_desc(resp[i]) <= kth);
-    s_scan[tid + 1] = c;
-    if (tid == 0) s_scan[0] = 0;
-    __syncthreads();
-    if (tid == 0) {
-        for (int i = 1; i <= SEL_THREADS; ++i) s_scan[i] += s_scan[i - 1];
-    }
-    __syncthreads();
-    int o = s_scan[tid];
-    uint32_t* okey = sv.lkp_key + (size_t)slot * sv.lkp_total + sv.lkp_off[level];
-    float* oresp = sv.lkp_resp + (size_t)slot * sv.lkp_total + sv.lkp_off[level];
-    for (int i = lo; i < hi; ++i) {
-        if (float_key_desc(resp[i]) <= kth) {
-            if (o < g.kp_cap) { okey[o] = keys[i]; oresp[o] = resp[i]; }
-            ++o;
+    // (5) keep every response >= the k-th, then sort the survivors by (y, x): raster order is the
+    //     canonical order of the keypoint list (the packed key is y << 20 | x << 8 | score)
+    for (int i0 = 0; i0 < m; i0 += SEL_THREADS) {
+        const int i = i0 + tid;
+        const bool keep = (i < m) && (float_key_desc(resp[i]) <= kth);
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_out, __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int j = base + __popc(bal & ((1u << lane) - 1u));
+            if (keep && j < P2) pairs[j] = ((unsigned long long)keys[i] << 32) | (unsigned long long)__float_as_uint(resp[i]);
         }
     }
+    __syncthreads();
+    const int outn = s_out;
+    const int nsort = min(outn, P2);
+    int P = 1;
+    while (P < nsort) P <<= 1;
+    for (int i = nsort + tid; i < P; i += SEL_THREADS) pairs[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort_u64(pairs, P);
+    uint32_t* okey = sv.lkp_key + (size_t)slot * sv.lkp_total + sv.lkp_off[level];
+    float* oresp = sv.lkp_resp + (size_t)slot * sv.lkp_total + sv.lkp_off[level];
+    for (int i = tid; i < min(nsort, g.kp_cap); i += SEL_THREADS) {
+        const unsigned long long v = pairs[i];
+        okey[i] = (uint32_t)(v >> 32);
+        oresp[i] = __uint_as_float((uint32_t)v);
+    }
     if (tid == 0) {
-        const int outn = s_scan[SEL_THREADS];
         if (outn > g.kp_cap) atomicOr(&sv.flags[slot], 4);
         sv.lkp_count[slot * kLevels + level] = min(outn, g.kp_cap);
     }
 }
 
 int launch_select(b200vo_ctx* ctx, int first_slot, int n) {
-    int max_cap = 0;
-    for (int l = 0; l < kLevels; ++l) max_cap = max(max_cap, ctx->store.lv[l].sel_cap);
-    const size_t smem = (size_t)max_cap * 12;
+    size_t smem = 0;
+    for (int l = 0; l < kLevels; ++l) {
+        int p2 = 64;
+        while (p2 < ctx->store.lv[l].kp_cap) p2 <<= 1;
+        smem = std::max(smem, (size_t)ctx->store.lv[l].sel_cap * 8 + (size_t)p2 * 8);
+    }
     static size_t configured = 0;
     if (smem > 48 * 1024 && configured < smem) {
         B200VO_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
