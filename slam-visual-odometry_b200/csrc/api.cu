@@ -291,8 +291,6 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     {   // TMA descriptors
         ctx->use_tma = true;
         if (const char* v = getenv("B200VO_TMA")) ctx->use_tma = (atoi(v) != 0);
-        ctx->fpg_compact = true;
-        if (const char* v = getenv("B200VO_FPG_COMPACT")) ctx->fpg_compact = (atoi(v) != 0);
         ctx->match_csa = 3;
         if (const char* v = getenv("B200VO_MATCH_CSA")) { const int c = atoi(v); if (c >= 0 && c <= 3) ctx->match_csa = c; }
         void* fnp = nullptr;
@@ -338,6 +336,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     TRY(dev_alloc(ctx, &pv.rounds, P));
     TRY(dev_alloc(ctx, &pv.pose_cand, P * 24));
     TRY(dev_alloc(ctx, &pv.pose_cnt, P * 4));
+    TRY(dev_alloc(ctx, &pv.fb_gid, P * pv.nhyp_cap));
+    TRY(dev_alloc(ctx, &pv.fb_count, 4));
     pv.counts = nullptr;
 #undef TRY
 #undef TRYCUDA

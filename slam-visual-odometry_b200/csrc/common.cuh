@@ -86,6 +86,8 @@ struct PairView {
     int* rounds;               // [pairs] adaptive RANSAC: blocks of 128 hypotheses evaluated
     double* pose_cand;         // [pairs][24] R1(9) R2(9) t(3) from decomposeEssentialMat
     int* pose_cnt;             // [pairs][4] cheirality votes of the four candidates
+    int* fb_gid;               // [pairs*nhyp_cap] hypotheses deferred to the exact root-isolation launch (ransac.cu)
+    unsigned int* fb_count;    // [1] length of that queue
     int nhyp_cap;
     int kp_cap;
 };
@@ -115,7 +117,6 @@ struct b200vo_ctx {
     CUtensorMap tmap_blur[b200vo::kLevels];
     CUtensorMap tmap_resize[b200vo::kLevels];    // [l] = level l as the SOURCE of level l+1
     bool use_tma;
-    bool fpg_compact;          // five-point kernel: re-pack the roots of a CTA onto dense lanes before the finish phase
     int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC, 2: full Harley-Seal (4 POPC), 3: 3 CSA + 5 POPC (default)
     int64_t launches;
     bool timing;

@@ -275,7 +275,9 @@ GEOM_HDI void classify_interval(GroupShared& gs, int h, int nxt, double a, doubl
 // number of root brackets (0 when the hypothesis is degenerate).  FINISH = false stops after the
 // ordered bracket list (gs.v.fin, gs.nfinal): the caller finishes the roots itself (the CUDA kernel
 // re-packs the roots of a whole CTA onto dense lanes).
-template <bool FINISH, class Exec>
+// EXACT = false: a hypothesis that needs the exact root path is not solved here; -1 is returned and the
+// caller queues it for a launch in which every group takes that path (no slow warp among fast ones).
+template <bool FINISH, bool EXACT, class Exec>
 GEOM_HD inline int five_point_group(Exec& ex, GroupShared& gs, const double* pts, double (*Eout)[9], bool* okout) {
     // ------------------------------------------------------------------ phase A: null space
     double a_[B200VO_GRP_SLOTS][5];
@@ -702,7 +704,9 @@ GEOM_HD inline int five_point_group(Exec& ex, GroupShared& gs, const double* pts
     // independent: lane s takes interval s, ten levels are ten phases (the serial form needs ~55
     // bracket solves one after another).  Scaled derivatives T[k][i] = c[i+k] C(i+k,k) live in shared
     // memory (the work lists of the Sturm path are dead by now), so degrees can be run-time values.
-    for (int h = 0; h < 2; ++h) {
+    bool deferred = false;
+    if (!EXACT && ex.active && (!gs.ibuf[10] || !gs.ibuf[11])) { deferred = true; ex.active = false; }
+    for (int h = 0; EXACT && h < 2; ++h) {
         const bool need = ex.active && !gs.ibuf[10 + h];
         if (!ex.any(need)) continue;
         ex.run([&](int r) {
@@ -783,7 +787,7 @@ GEOM_HD inline int five_point_group(Exec& ex, GroupShared& gs, const double* pts
         }
         okout[ls] = ok;
     });
-    return nfinal;
+    return deferred ? -1 : nfinal;
 }
 
 // host convenience (tests/hostsim): all solutions of one sample through the group algorithm
@@ -795,7 +799,7 @@ inline int five_point_group_host(const double x1[5][2], const double x2[5][2], d
     for (int i = 0; i < 5; ++i) { pts[2 * i] = x1[i][0]; pts[2 * i + 1] = x1[i][1]; pts[10 + 2 * i] = x2[i][0]; pts[10 + 2 * i + 1] = x2[i][1]; }
     double Eo[kGroupLanes][9];
     bool ok[kGroupLanes];
-    const int nf = five_point_group<true>(ex, gs, pts, Eo, ok);
+    const int nf = five_point_group<true, true>(ex, gs, pts, Eo, ok);
     int ns = 0;
     for (int r = 0; r < nf; ++r)
         if (ok[r]) { for (int k = 0; k < 9; ++k) E[ns][k] = Eo[r][k]; ++ns; }

@@ -43,33 +43,27 @@ struct RansacArgs {
 // (round-1 history: a thread-per-hypothesis solver ran with 10 of 32 lanes active; a three-phase
 // version with stream compaction fixed the divergence but left 5.6 KB of local memory per thread and
 // 85 % long-scoreboard stalls -- profiles/ncu_r01_final_kernels.txt.)
-// Phases A-E run per group (fivept_group.cuh).  COMPACT: the root brackets of the whole CTA (~4.85
-// real roots per hypothesis: half of the lane slots) are re-packed onto dense lanes for the per-root
-// finish (refine, back-substitute, polish), which reads the owning group's setup data from shared
-// memory; only as many warps as there are roots keep running.  !COMPACT: every group finishes its
-// own roots (no CTA barrier, half of the lanes idle in that phase).
-template <int THREADS, int MINB, bool COMPACT>
-__global__ void __launch_bounds__(THREADS, MINB)
-five_point_group_kernel(PairView pv, RansacArgs ra) {
-    constexpr int GROUPS = 3 * (THREADS / 32);
-    extern __shared__ __align__(16) unsigned char fpg_smem[];
-    __shared__ int s_nroot;
-    __shared__ unsigned short s_root[GROUPS * 10];
-    geom::GroupShared* groups = reinterpret_cast<geom::GroupShared*>(fpg_smem);
+// Phases A-E run per group (fivept_group.cuh).  Then the root brackets of the CTA (~4.85 real roots per
+// hypothesis: half of the lane slots) are re-packed onto dense lanes for the per-root finish (refine,
+// back-substitute, polish), which reads the owning group's setup data from shared memory; only as
+// many warps as there are roots keep running.
+// DEFERRED = false (main launch): hypothesis = blockIdx; one whose Sturm chain is unreliable (2-6 %,
+// near-multiple roots) is appended to a queue instead of taking the long exact-root path, which would
+// make its warp the straggler of the CTA (measured: 42 % of the warp time was spent waiting for it).
+// DEFERRED = true: the queued hypotheses, packed densely -- here every group takes the exact path.
+template <int THREADS, bool EXACT>
+__device__ __forceinline__ void fpg_solve(const PairView& pv, const RansacArgs& ra, geom::GroupShared* groups, int* s_nroot, int* s_gid,
+                                          unsigned short* s_root, bool in_range, int pair, int h) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / geom::kGroupLanes;               // lanes 30, 31 (g == 3) have no group: they only keep the barriers full
     const int r = lane - geom::kGroupLanes * g;
     const int slot = warp * 3 + min(g, 2);
     geom::GroupShared& gs = groups[slot];
-    const int pair = blockIdx.y;
-    if (ra.adaptive && pv.done[pair]) return;             // uniform over the CTA
-    const int hbase = ra.h0 + blockIdx.x * GROUPS;
-    const int h = hbase + slot;
-    const bool in_range = (g < 3) && (h < ra.h0 + ra.nround);
     const int gid = pair * pv.nhyp_cap + h;
-    const int m = pv.n_good[pair];
+    const int m = in_range ? pv.n_good[pair] : 0;
     const bool solve = in_range && m >= ra.min_matches && m >= 5;        // uniform over the group
-    if (COMPACT && threadIdx.x == 0) s_nroot = 0;
+    if (threadIdx.x == 0) *s_nroot = 0;
+    if (g < 3 && r == 0) s_gid[slot] = gid;
     double pts[20];
 #pragma unroll
     for (int k = 0; k < 20; ++k) pts[k] = 0.0;
@@ -90,43 +84,66 @@ five_point_group_kernel(PairView pv, RansacArgs ra) {
         }
     }
     geom::DeviceGroupExec ex{r, solve};
-    if (COMPACT) {
-        __syncthreads();
-        const int nfinal = geom::five_point_group<false>(ex, gs, pts, (double (*)[9]) nullptr, (bool*)nullptr);
-        if (in_range) {
-            pv.model_ok[(size_t)gid * 10 + r] = 0;
-            if (r == 0) pv.nsol[gid] = nfinal;
-            if (r < nfinal) s_root[atomicAdd(&s_nroot, 1)] = (unsigned short)(slot * 10 + r);
+    __syncthreads();
+    const int nfinal = geom::five_point_group<false, EXACT>(ex, gs, pts, (double (*)[9]) nullptr, (bool*)nullptr);
+    if (in_range) {
+        pv.model_ok[(size_t)gid * 10 + r] = 0;
+        if (r == 0) {
+            pv.nsol[gid] = max(nfinal, 0);
+            if (!EXACT && nfinal < 0) pv.fb_gid[atomicAdd(pv.fb_count, 1u)] = gid;
         }
-        __syncthreads();
-        const int nroot = s_nroot;
-        for (int i = threadIdx.x; i < nroot; i += THREADS) {
-            const int e = s_root[i], sl = e / 10, k = e - sl * 10;
-            const geom::GroupShared& go = groups[sl];
-            geom::RootBracket br;
-            br.a = go.v.fin.a[k]; br.b = go.v.fin.b[k]; br.reversed = go.v.fin.rev[k];
-            double E[9];
-            if (geom::five_point_finish(go.S, br, E)) {
-                const size_t gd = (size_t)pair * pv.nhyp_cap + hbase + sl;
-                double* out = pv.models + gd * 90 + k * 9;
-#pragma unroll
-                for (int q = 0; q < 9; ++q) out[q] = E[q];
-                pv.model_ok[gd * 10 + k] = 1;
-            }
-        }
-    } else {
-        double E[1][9];
-        bool ok[1] = {false};
-        const int nfinal = geom::five_point_group<true>(ex, gs, pts, E, ok);
-        if (!in_range) return;
-        pv.model_ok[(size_t)gid * 10 + r] = ok[0] ? 1 : 0;
-        if (ok[0]) {
-            double* out = pv.models + (size_t)gid * 90 + r * 9;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) out[k] = E[0][k];
-        }
-        if (r == 0) pv.nsol[gid] = nfinal;
+        if (r < nfinal) s_root[atomicAdd(s_nroot, 1)] = (unsigned short)(slot * 10 + r);
     }
+    __syncthreads();
+    const int nroot = *s_nroot;
+    for (int i = threadIdx.x; i < nroot; i += THREADS) {
+        const int e = s_root[i], sl = e / 10, k = e - sl * 10;
+        const geom::GroupShared& go = groups[sl];
+        geom::RootBracket br;
+        br.a = go.v.fin.a[k]; br.b = go.v.fin.b[k]; br.reversed = go.v.fin.rev[k];
+        double E[9];
+        if (geom::five_point_finish(go.S, br, E)) {
+            const size_t gd = (size_t)s_gid[sl];
+            double* out = pv.models + gd * 90 + k * 9;
+#pragma unroll
+            for (int q = 0; q < 9; ++q) out[q] = E[q];
+            pv.model_ok[gd * 10 + k] = 1;
+        }
+    }
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+five_point_group_kernel(PairView pv, RansacArgs ra) {
+    constexpr int GROUPS = 3 * (THREADS / 32);
+    extern __shared__ __align__(16) unsigned char fpg_smem[];
+    __shared__ int s_nroot;
+    __shared__ int s_gid[GROUPS];
+    __shared__ unsigned short s_root[GROUPS * 10];
+    const int pair = blockIdx.y;
+    if (ra.adaptive && pv.done[pair]) return;             // uniform over the CTA
+    const int lane = threadIdx.x & 31, slot = (threadIdx.x >> 5) * 3 + min(lane / geom::kGroupLanes, 2);
+    const int h = ra.h0 + blockIdx.x * GROUPS + slot;
+    const bool in_range = (lane < 3 * geom::kGroupLanes) && (h < ra.h0 + ra.nround);
+    fpg_solve<THREADS, false>(pv, ra, reinterpret_cast<geom::GroupShared*>(fpg_smem), &s_nroot, s_gid, s_root, in_range, pair, h);
+}
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+five_point_deferred_kernel(PairView pv, RansacArgs ra) {
+    constexpr int GROUPS = 3 * (THREADS / 32);
+    extern __shared__ __align__(16) unsigned char fpg_smem[];
+    __shared__ int s_nroot;
+    __shared__ int s_gid[GROUPS];
+    __shared__ unsigned short s_root[GROUPS * 10];
+    const unsigned nq = *pv.fb_count;
+    const int lane = threadIdx.x & 31, slot = (threadIdx.x >> 5) * 3 + min(lane / geom::kGroupLanes, 2);
+    const unsigned qbase = blockIdx.x * GROUPS;            // the grid covers the worst case (every hypothesis queued);
+    if (qbase >= nq) return;                               // CTAs beyond the queue exit at once
+    const bool in_range = (lane < 3 * geom::kGroupLanes) && (qbase + slot < nq);
+    const int q = in_range ? pv.fb_gid[qbase + slot] : 0;
+    const int pair = q / pv.nhyp_cap;
+    fpg_solve<THREADS, true>(pv, ra, reinterpret_cast<geom::GroupShared*>(fpg_smem), &s_nroot, s_gid, s_root, in_range, pair, q - pair * pv.nhyp_cap);
 }
 
 // Inlier count of one model by one warp.  The Sampson test is evaluated in float first (one 16-byte
@@ -217,25 +234,18 @@ score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
     }
 }
 
-template <int THREADS, int MINB, bool COMPACT>
-static void launch_fpg(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
-    constexpr int GROUPS = 3 * (THREADS / 32);
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(five_point_group_kernel<THREADS, MINB, COMPACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(GROUPS * sizeof(geom::GroupShared)));
-        configured = true;
-    }
-    const dim3 grid(div_up(ra.nround, GROUPS), npairs);
-    five_point_group_kernel<THREADS, MINB, COMPACT><<<grid, THREADS, GROUPS * sizeof(geom::GroupShared), ctx->stream>>>(ctx->pairs, ra);
-}
-
 static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
-    // measured on B200 (1000 frames, H = 1024): 256 threads x 2 CTAs/SM with compaction 8.0 ms; without
-    // compaction 9.4; 128 x 4: 10.2; 64 x 8: 12.3; 512 x 1: 10.3 (larger CTAs keep more warps on the
-    // same instruction-cache lines; beyond 256 the register file fits only one CTA)
-    if (!ctx->fpg_compact) launch_fpg<256, 2, false>(ctx, ra, npairs);        // B200VO_FPG_COMPACT=0 (tests: identical results)
-    else launch_fpg<256, 2, true>(ctx, ra, npairs);
+    // measured on B200 (1000 frames, H = 1024): 256 threads x 2 CTAs/SM 8.0 ms; 128 x 4: 10.2; 64 x 8: 12.3;
+    // 512 x 1: 10.3 (larger CTAs keep more warps on the same instruction-cache lines; beyond 256 the
+    // register file fits only one CTA)
+    constexpr int THREADS = 256, GROUPS = 3 * (THREADS / 32);
+    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.fb_count, 0, sizeof(unsigned), ctx->stream));
+    const size_t smem = GROUPS * sizeof(geom::GroupShared);
+    five_point_group_kernel<THREADS, 2><<<dim3(div_up(ra.nround, GROUPS), npairs), THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
+    B200VO_LAUNCH_CHECK(ctx);
+    // the queue length is only known on the device (measured share: 2-6 %): the grid covers the worst
+    // case, CTAs beyond the queue exit at once
+    five_point_deferred_kernel<THREADS, 2><<<div_up(npairs * ra.nround, GROUPS), THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
@@ -250,6 +260,9 @@ static int launch_score(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
 
 int init_ransac_kernels() {
     cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_MAXPTS * sizeof(float4)));
+    const int fpg_smem = 3 * (256 / 32) * (int)sizeof(geom::GroupShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(five_point_group_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpg_smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(five_point_deferred_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpg_smem);
     if (e != cudaSuccess) { set_error("ransac kernel smem attribute: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
     return B200VO_OK;
 }

@@ -67,11 +67,11 @@ extern "C" int hs_dbg_group(const double* x1, const double* x2, double* c, doubl
     double pts[20];
     for (int i = 0; i < 5; ++i) { pts[2*i] = x1[2*i]; pts[2*i+1] = x1[2*i+1]; pts[10+2*i] = x2[2*i]; pts[10+2*i+1] = x2[2*i+1]; }
     double Eo[kGroupLanes][9]; bool ok[kGroupLanes];
-    const int nf = five_point_group<true>(ex, gs, pts, Eo, ok);
+    const int nf = five_point_group<true, true>(ex, gs, pts, Eo, ok);
     std::memcpy(c, gs.S.c, sizeof(gs.S.c)); std::memcpy(N, gs.S.N, sizeof(gs.S.N));
     for (int i = 0; i < nf; ++i) { lo[i] = gs.v.fin.a[i]; hi[i] = gs.v.fin.b[i]; rev[i] = gs.v.fin.rev[i]; }
     flags[0] = gs.ibuf[10]; flags[1] = gs.ibuf[11]; flags[2] = gs.chain_ok[0]; flags[3] = gs.chain_ok[1];
-    { GroupShared g2; HostGroupExec e2; double E2[kGroupLanes][9]; bool o2[kGroupLanes]; flags[5] = five_point_group<false>(e2, g2, pts, E2, o2); }
+    { GroupShared g2; HostGroupExec e2; double E2[kGroupLanes][9]; bool o2[kGroupLanes]; flags[5] = five_point_group<true, false>(e2, g2, pts, E2, o2); }
     int okc = 0; for (int i = 0; i < nf; ++i) okc += ok[i];
     flags[4] = okc;
     return nf;

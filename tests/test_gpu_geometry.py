@@ -192,22 +192,23 @@ def test_adaptive_ransac_equals_truncated_fixed(built, seq_kitti):
         assert np.array_equal(Es, Efull) and ((int(rs["status"]) >> 16) & 0xFF) == 0
 
 
-def test_five_point_finish_variants_agree(built, seq_kitti, monkeypatch):
-    """The five-point kernel with and without the CTA-level re-packing of roots (B200VO_FPG_COMPACT) must
-    produce byte-identical models and records."""
-    frames = seq_kitti[0]
-    out = []
-    for v in ("1", "0"):
-        monkeypatch.setenv("B200VO_FPG_COMPACT", v)
-        with built.Context(1241, 376, nfeatures=NF, max_frames=4, ransac_hypotheses=NHYP) as c:
-            c.upload_frames(frames, 0)
-            c.detect(0, 2)
-            rec, E, mask = c.relative_pose(0, 1, pair_id=3, want_mask=True)
-            f0, f1 = c.get_features(0), c.get_features(1)
-            good, _, _ = c.match(0, 1)
-            K = seq_kitti[3]
-            x1 = G.normalize_points(np.stack([f0[0]["x"][good["queryIdx"]], f0[0]["y"][good["queryIdx"]]], 1), K)
-            x2 = G.normalize_points(np.stack([f1[0]["x"][good["trainIdx"]], f1[0]["y"][good["trainIdx"]]], 1), K)
-            Es, ns = c.five_point(x1, x2, G.draw_samples(9, 0, 100, len(x1)))
-            out.append((rec.tobytes(), E.tobytes(), mask.tobytes(), Es.tobytes(), ns.tobytes()))
-    assert out[0] == out[1]
+def test_five_point_gpu_equals_host_emulation(scene, built):
+    """The cooperative solver is one source for device and host (csrc/fivept_group.cuh; on the host the
+    lanes of a group are executed one after another, tests/hostsim).  Same samples -> the same solution
+    sets up to floating-point contraction differences (the host build disables FMA contraction)."""
+    import ctypes, os
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim", "libgeom_host.so"))
+    x1, x2 = scene["x1"], scene["x2"]
+    S = G.draw_samples(77, 3, 200, len(x1))
+    E, ns = scene["ctx"].five_point(x1, x2, S)
+    same, errs = 0, []
+    for h, s in enumerate(S):
+        a, b = np.ascontiguousarray(x1[s]), np.ascontiguousarray(x2[s])
+        Eh = np.zeros((10, 9))
+        n = lib.hs_five_point_group(a.ctypes.data_as(ctypes.c_void_p), b.ctypes.data_as(ctypes.c_void_p), Eh.ctypes.data_as(ctypes.c_void_p))
+        same += (n == ns[h])
+        for e in Eh[:n]:
+            errs.append(min([_set_err(e, g) for g in E[h, :ns[h]]], default=1.0))
+    errs = np.array(errs)
+    assert same >= 0.97 * len(S), same
+    assert (errs <= 1e-8).mean() >= 0.97, (errs <= 1e-8).mean()
