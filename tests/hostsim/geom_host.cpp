@@ -3,6 +3,7 @@
 // The product library never links or loads this file.
 #include <cstring>
 #include "../../slam-visual-odometry_b200/csrc/geom_core.cuh"
+#include "five_point_thread.h"
 #include "../../slam-visual-odometry_b200/csrc/fivept_group.cuh"
 using namespace b200vo::geom;
 extern "C" {
