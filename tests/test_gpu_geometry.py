@@ -212,3 +212,17 @@ def test_five_point_gpu_equals_host_emulation(scene, built):
     errs = np.array(errs)
     assert same >= 0.97 * len(S), same
     assert (errs <= 1e-8).mean() >= 0.97, (errs <= 1e-8).mean()
+
+
+def test_five_point_is_deterministic(scene):
+    """The cooperative solver exchanges data through shared memory under phase barriers; a missing
+    barrier would show up as run-to-run differences (compute-sanitizer is not available on this pool).
+    Same samples, repeated launches -> byte-identical solution sets."""
+    x1, x2 = scene["x1"], scene["x2"]
+    S = G.draw_samples(5, 11, NHYP, len(x1))
+    ref = None
+    for _ in range(4):
+        E, ns = scene["ctx"].five_point(x1, x2, S)
+        cur = (E.tobytes(), ns.tobytes())
+        assert ref is None or cur == ref
+        ref = cur
