@@ -31,6 +31,7 @@ for p in (ROOT, os.path.join(ROOT, "slam-visual-odometry_b200")):
         sys.path.insert(0, p)
 
 W_IMG, H_IMG = 1241, 376
+MATCH_DRAM_BYTES_PER_LAUNCH = 30005760      # profiles/ncu_r01_match_fullconfig.txt (30.0 MB read, 0 written)
 METRIC = "frame-pairs/sec (detect+match+E-RANSAC+pose)"
 
 
@@ -386,9 +387,13 @@ def run_b200(args):
     dom = max(kernels, key=kernels.get) if kernels else "match_ms"
     if dom == "match_ms":
         roof = {"kernel": "match_kernel<4,%d>" % int(os.environ.get("B200VO_MATCH_CSA", "3")), "bound": "int_pipe", "achieved": round(popc_exec / 1e9, 1), "peak": round(popc_rate / 1e9, 1),
-                "unit": "Gpopc32/s", "frac": round(popc_exec / popc_rate, 4), "traffic": None,
-                "peak_source": "XOR+POPC+ADD microbenchmark measured in this run (b200vo_measure_popc_rate); not an HBM- or tensor-bound kernel: "
-                               "its DRAM traffic is ~0.2 MB per 9e6 descriptor pairs (profiles/)",
+                "unit": "Gpopc32/s", "frac": round(popc_exec / popc_rate, 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (250-frame batch) from the ncu --set full
+                # capture profiles/ncu_r01_match_fullconfig.txt; algorithmic: 2 x 250 x 3001 x 32 B descriptors = 48 MB
+                # if nothing were shared, 24 MB with every descriptor read once
+                "traffic": MATCH_DRAM_BYTES_PER_LAUNCH if (F, NF, B) == (1000, 3000, 250) else None, "traffic_unit": "bytes/launch",
+                "peak_source": "XOR+POPC+ADD microbenchmark measured in this run (b200vo_measure_popc_rate); not an HBM- or tensor-bound kernel "
+                               "(30 MB of DRAM traffic per 2.9 ms launch)",
                 "share_of_step": round(mm / total_stage_ms, 3)}
     else:
         nm = dom[:-3]

@@ -35,6 +35,8 @@ def main():
                 u = units[ix[c]]
                 try:
                     f = float(v.replace(",", ""))
+                    if label == "us":                      # ncu picks the time unit per report
+                        f *= {"s": 1e6, "second": 1e6, "ms": 1e3, "msecond": 1e3, "us": 1.0, "usecond": 1.0, "ns": 1e-3, "nsecond": 1e-3}.get(u, 1.0)
                     v = ("%.3g" % f)
                 except ValueError:
                     pass
