@@ -298,7 +298,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         TRYCUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qres));
         if (!fnp || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled entry point unavailable"); b200vo_destroy(ctx); return B200VO_ERR_CUDA; }
         for (int l = 0; l < kLevels; ++l) {
-            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_fast[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kFastBoxW, kFastBoxH));
+            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_fast[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, fast_level_is_wide(l) ? kFastBoxWideW : kFastBoxW, kFastBoxH));
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_blur[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kBlurBoxW, kBlurBoxH));
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_resize[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kResizeBoxW, kResizeBoxH));
         }

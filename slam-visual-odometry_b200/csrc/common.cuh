@@ -18,6 +18,8 @@ constexpr int kDescBytes = 32;
 constexpr int kMaxSolutions = 10;  // real roots of the degree-10 five-point polynomial
 // TMA boxes (bytes x rows) of the tile consumers; the inner extent must be a multiple of 16 bytes
 constexpr int kFastBoxW = 96, kFastBoxH = 38;      // fast.cu: 70x38 pixel tile + up to 15 bytes of alignment shift
+constexpr int kFastBoxWideW = 160;                 // fast.cu: the 134-pixel-wide tile of the large levels
+inline bool fast_level_is_wide(int level) { return level <= 4; }
 constexpr int kBlurBoxW = 160, kBlurBoxH = 38;     // blur.cu: 128+2*16 x 32+6
 constexpr int kResizeBoxW = 176, kResizeBoxH = 24; // pyramid.cu: source footprint of a 128x16 output tile at scale ~1.2
 

@@ -17,11 +17,19 @@ namespace b200vo {
 // Tile geometry: 62x30 outputs -> a 64x32 score tile (1-px NMS halo) -> a 70x38 pixel tile (+3 ring).
 // The pixel tile is fetched as aligned 32-bit words (row of 20 words; `shift` = misalignment of the
 // tile origin), so staging costs ~4 instructions per pixel instead of one byte load each.
-constexpr int FT_W = 62, FT_H = 30;
-constexpr int FT_CW = 64, FT_CH = 32;            // score tile
-constexpr int FT_SWW = 24, FT_SW = FT_SWW * 4;   // pixel tile row: 24 words = 96 bytes (>= 70 + 15 alignment shift)
-constexpr int FT_SH = FT_CH + 6;                 // 38 rows
-static_assert(FT_SW == kFastBoxW && FT_SH == kFastBoxH, "TMA box must match the pixel tile");
+// Two tile widths: the wide one (126 outputs) for the large levels -- its survivor / corner lists are
+// four and two 256-thread passes long instead of 1.4 and 0.5, so phases 2-4 run on full warps -- the
+// narrow one (62) where a wide tile would mostly overhang the level.
+template <int CW>
+struct FastTile {
+    static constexpr int FT_CW = CW, FT_CH = 32;                 // score tile
+    static constexpr int FT_W = CW - 2, FT_H = FT_CH - 2;        // outputs
+    static constexpr int FT_SW = (CW + 6 + 15 + 15) / 16 * 16;   // pixel tile row bytes: CW + 6 ring + <= 15 alignment shift, x16
+    static constexpr int FT_SWW = FT_SW / 4;
+    static constexpr int FT_SH = FT_CH + 6;                      // 38 rows
+};
+static_assert(FastTile<64>::FT_SW == kFastBoxW && FastTile<128>::FT_SW == kFastBoxWideW && FastTile<64>::FT_SH == kFastBoxH,
+              "TMA boxes must match the pixel tiles");
 
 __device__ __forceinline__ bool has_arc9(uint32_t m) {
     uint32_t r = m | (m << 16);
@@ -33,8 +41,8 @@ __device__ __forceinline__ bool has_arc9(uint32_t m) {
     return (r & 0xFFFFu) != 0;
 }
 
+template <int S>
 __device__ __forceinline__ void load_ring(const uint8_t* p, int* v) {
-    const int S = FT_SW;
     v[0] = p[3 * S];       v[1] = p[3 * S + 1];   v[2] = p[2 * S + 2];   v[3] = p[S + 3];
     v[4] = p[3];           v[5] = p[-S + 3];      v[6] = p[-2 * S + 2];  v[7] = p[-3 * S + 1];
     v[8] = p[-3 * S];      v[9] = p[-3 * S - 1];  v[10] = p[-2 * S - 2]; v[11] = p[-S - 3];
@@ -47,8 +55,11 @@ __device__ __forceinline__ void load_ring(const uint8_t* p, int* v) {
 //   2. survivors: full 16-pixel segment test -> corners appended to a second list
 //   3. corners: corner score (max over 9-arcs of the arc minimum, minus 1) -> score tile
 //   4. corners: strict 3x3 non-max suppression + border filter -> candidate list + histogram
+template <int CW>
 __global__ void __launch_bounds__(256)
 fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+    using T = FastTile<CW>;
+    constexpr int FT_CW = T::FT_CW, FT_CH = T::FT_CH, FT_W = T::FT_W, FT_H = T::FT_H, FT_SW = T::FT_SW, FT_SWW = T::FT_SWW, FT_SH = T::FT_SH;
     __shared__ __align__(128) uint8_t s_img[FT_SH * FT_SW];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(4) uint8_t s_score[FT_CH * FT_CW];
@@ -160,7 +171,7 @@ fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUt
             const uint8_t* p = s_org + cy * FT_SW + cx;
             const int c = p[0], hi = c + t, lo = c - t;
             int v[16];
-            load_ring(p, v);
+            load_ring<FT_SW>(p, v);
             uint32_t mb = 0, md = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
@@ -190,7 +201,7 @@ fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUt
         const uint8_t* p = s_org + cy * FT_SW + cx;
         const int c = p[0];
         int v[16];
-        load_ring(p, v);
+        load_ring<FT_SW>(p, v);
         // exactly one polarity can hold a 9-arc; its arc-min maximum is the corner's best threshold
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = bright ? (v[i] - c) : (c - v[i]);
@@ -267,8 +278,13 @@ int launch_fast(b200vo_ctx* ctx, int first_slot, int n) {
         const LevelGeom& g = ctx->store.lv[l];
         const int iw = g.w - 2 * kEdge, ih = g.h - 2 * kEdge;
         if (iw <= 0 || ih <= 0) continue;
-        dim3 grid(div_up(iw, FT_W), div_up(ih, FT_H), n);
-        fast_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], ctx->use_tma ? 1 : 0);
+        if (fast_level_is_wide(l)) {
+            dim3 grid(div_up(iw, FastTile<128>::FT_W), div_up(ih, FastTile<128>::FT_H), n);
+            fast_kernel<128><<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], ctx->use_tma ? 1 : 0);
+        } else {
+            dim3 grid(div_up(iw, FastTile<64>::FT_W), div_up(ih, FastTile<64>::FT_H), n);
+            fast_kernel<64><<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], ctx->use_tma ? 1 : 0);
+        }
         B200VO_LAUNCH_CHECK(ctx);
     }
     return B200VO_OK;
