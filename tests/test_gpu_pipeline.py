@@ -133,3 +133,45 @@ def test_python_reference_chain_equals_library(built, records):
     for i, r in enumerate(batched):
         R, t = PL.chain_pose(R, t, dict(status=int(r["status"]), R=r["R"], t=r["t"]))
         assert np.allclose(traj[i][:9].reshape(3, 3), R, atol=1e-14) and np.allclose(traj[i][9:], t, atol=1e-14)
+
+
+def test_flat_frame_in_sequence_takes_reference_fallback(built, seq, records):
+    """A frame without texture yields no keypoints: both pairs touching it have < 10 good matches, the
+    pose stays unchanged (reference fallback (a), visual_odometry.cpp:340-345), the other pairs are
+    unaffected (byte-identical to the undisturbed run)."""
+    frames = seq[0].copy()
+    frames[3] = 128
+    batched, _ = records
+    with built.Context(W, H, nfeatures=NF, max_frames=NFRAMES + 1, ransac_hypotheses=NHYP) as ctx:
+        ctx.upload_frames(frames, 0)
+        ctx.detect(0, NFRAMES)
+        recs = ctx.process_pairs(0, NFRAMES - 1, 0)
+    for i in (2, 3):
+        assert recs[i]["status"] == 0 and recs[i]["n_matches"] == 0
+    for i in (0, 1, 4, 5):
+        assert recs[i].tobytes() == batched[i].tobytes()
+    poses = built.chain_trajectory(recs)
+    assert np.array_equal(poses[2], poses[1]) and np.array_equal(poses[3], poses[1])      # frames 3 and 4 keep frame 2's pose
+
+
+def test_ratio_mode_pipeline(built, seq):
+    """The whole pair path with the ratio-test matcher: its good-match list equals the oracle's on the
+    GPU's own descriptors, and the poses are as accurate as in cross-check mode."""
+    from oracle import match as M
+    frames, R_wc, C_w, K = seq
+    with built.Context(W, H, nfeatures=NF, max_frames=NFRAMES + 1, ransac_hypotheses=NHYP,
+                       match_mode=built.MATCH_RATIO, ratio=0.8) as ctx:
+        ctx.upload_frames(frames, 0)
+        ctx.detect(0, NFRAMES)
+        recs = ctx.process_pairs(0, NFRAMES - 1, 0)
+        d0, d1 = ctx.get_features(0)[1], ctx.get_features(1)[1]
+        good, n_pass, thr = ctx.match(0, 1)
+    qi, ti, d, thr_o, nc = M.good_matches(d0, d1, ratio=0.8)
+    assert n_pass == nc and thr == thr_o and np.array_equal(good["queryIdx"], qi) and np.array_equal(good["trainIdx"], ti)
+    assert recs[0]["n_matches"] == len(qi)
+    from b200vo import synth
+    for i, r in enumerate(recs):
+        assert r["status"] & 4, "pair %d has no valid pose in ratio mode" % i
+        Rg, tg = synth.relative_pose_gt(R_wc, C_w, i)
+        # minimal-sample model without refit on a differently composed match list: 2 degrees
+        assert G.rotation_angle_deg(r["R"].reshape(3, 3), Rg) < 2.0
