@@ -27,6 +27,7 @@
  * b200vo_match                      get_good_matches_of_features      src/visual_odometry.cpp:145-180
  * b200vo_relative_pose              estimate_relative_pose: findEssentialMat + recoverPose
  *                                     src/visual_odometry.cpp:182-281
+ * b200vo_process_frame              one whole streaming step of process_frame    src/visual_odometry.cpp:323-378
  * b200vo_process_pairs              the batched detect-free remainder of process_frame for a
  *                                     contiguous range of frame pairs  src/visual_odometry.cpp:340-366
  * b200vo_chain_pose                 invert_relative_... + compose_next_...  src/visual_odometry.cpp:292-314,350-360
@@ -189,6 +190,13 @@ int b200vo_match(b200vo_ctx* ctx, int slot1, int slot2, b200vo_dmatch* out, int 
  * (NULL: drawn on the device from (seed, pair_id)).  essential (9 doubles, may be NULL) gets E. */
 int b200vo_relative_pose(b200vo_ctx* ctx, int slot1, int slot2, int64_t pair_id, const int32_t* samples, int nhyp,
                          b200vo_pose_record* rec, double* essential, uint8_t* inlier_mask, int mask_cap);
+
+/* One streaming step, i.e. what VisualOdometry::process_frame does per frame (src/visual_odometry.cpp:323-378):
+ * upload + detect the frame into `slot`, run the pair (prev_slot, slot) when prev_slot >= 0, and return the
+ * frame's features, the pose record and E -- with ONE host synchronisation (the separate calls above
+ * synchronise four times).  kp / desc / essential may be NULL; rec is required when prev_slot >= 0. */
+int b200vo_process_frame(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int channels, int slot, int prev_slot, int64_t pair_id,
+                         b200vo_keypoint* kp, uint8_t* desc, int cap, int* n, b200vo_pose_record* rec, double* essential);
 
 /* Batched: pairs (first_slot+i, first_slot+i+1), i < npairs, with pair ids first_pair_id+i.
  * Features of all touched slots must exist (b200vo_detect).  Records are copied to `out`. */

@@ -67,4 +67,6 @@ private:
     int previous_slot_ = 0;
     int64_t frame_counter_ = 0;
     bool initialized_ = false;
+    std::vector<struct b200vo_keypoint> kp_buf_;      // reused per frame (no allocation in process_frame)
+    std::vector<uint8_t> desc_buf_;
 };

@@ -49,7 +49,7 @@ EXPORTS = [
     "b200vo_synchronize", "b200vo_level_info", "b200vo_max_keypoints", "b200vo_upload_frames",
     "b200vo_upload_frames_device", "b200vo_detect", "b200vo_get_features", "b200vo_get_pyramid_level",
     "b200vo_get_fast_candidates", "b200vo_set_features", "b200vo_match_descriptors",
-    "b200vo_match_descriptors_device", "b200vo_knn_match_descriptors", "b200vo_match", "b200vo_relative_pose", "b200vo_process_pairs",
+    "b200vo_match_descriptors_device", "b200vo_knn_match_descriptors", "b200vo_match", "b200vo_relative_pose", "b200vo_process_frame", "b200vo_process_pairs",
     "b200vo_process_pairs_device", "b200vo_five_point", "b200vo_score_models", "b200vo_recover_pose",
     "b200vo_draw_samples", "b200vo_chain_pose", "b200vo_chain_trajectory", "b200vo_measure_popc_rate", "b200vo_fundamental_from_essential", "b200vo_enable_timing",
     "b200vo_get_stage_times", "b200vo_kernel_launches", "b200vo_stream",
@@ -277,6 +277,21 @@ class Context:
                                                 _p(mask), self.kp_cap if want_mask else 0))
         r = rec[0]
         return r, E.reshape(3, 3), (mask[:r["n_matches"]].copy() if want_mask else None)
+
+    def process_frame(self, image, slot, prev_slot=-1, pair_id=0):
+        """One streaming step (b200vo_process_frame): returns (keypoints, descriptors, record or None, E or None)."""
+        im = np.ascontiguousarray(image, np.uint8)
+        ch = 3 if im.ndim == 3 else 1
+        kp = np.zeros(self.kp_cap, KEYPOINT_DTYPE)
+        desc = np.zeros((self.kp_cap, 32), np.uint8)
+        n = C.c_int()
+        rec = np.zeros(1, POSE_RECORD_DTYPE)
+        E = np.zeros(9)
+        self._chk(self.lib.b200vo_process_frame(self.h, _p(im), C.c_size_t(im.shape[1] * ch), ch, int(slot), int(prev_slot), C.c_int64(pair_id),
+                                                _p(kp), _p(desc), self.kp_cap, C.byref(n), _p(rec), _p(E)))
+        if prev_slot < 0:
+            return kp[:n.value].copy(), desc[:n.value].copy(), None, None
+        return kp[:n.value].copy(), desc[:n.value].copy(), rec[0], E.reshape(3, 3)
 
     def process_pairs(self, first_slot, npairs, first_pair_id=0):
         out = np.zeros(npairs, POSE_RECORD_DTYPE)

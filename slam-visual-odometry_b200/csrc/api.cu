@@ -665,6 +665,44 @@ int b200vo_relative_pose(b200vo_ctx* ctx, int slot1, int slot2, int64_t pair_id,
     return B200VO_OK;
 }
 
+// One streaming step of VisualOdometry::process_frame (reference src/visual_odometry.cpp:323-378) with a
+// single host synchronisation: upload + detect of the new frame, the pair (prev_slot, slot) if
+// prev_slot >= 0, and every result the reference's per-frame code reads -- features, pose record, E.
+int b200vo_process_frame(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int channels, int slot, int prev_slot, int64_t pair_id,
+                         b200vo_keypoint* kp, uint8_t* desc, int cap, int* n, b200vo_pose_record* rec, double* essential) {
+    if (!ctx || !host || !slot_ok(ctx, slot) || prev_slot >= ctx->store.slots || !n || (prev_slot >= 0 && !rec)) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
+    const StoreView& sv = ctx->store;
+    int rc;
+    if ((rc = b200vo_upload_frames(ctx, host, 1, pitch, pitch * sv.lv[0].h, channels, slot))) return rc;
+    if ((rc = b200vo_detect(ctx, slot, 1))) return rc;
+    // results travel through one pinned block: [count, flags | keypoints | descriptors | record | E]
+    const size_t kb = (size_t)sv.kp_cap * sizeof(b200vo_keypoint), db = (size_t)sv.kp_cap * kDescBytes;
+    const size_t off_kp = 64, off_desc = off_kp + kb, off_rec = round_up(off_desc + db, 64), off_E = off_rec + sizeof(b200vo_pose_record);
+    if ((rc = ensure_pinned(ctx, off_E + 9 * sizeof(double)))) return rc;
+    uint8_t* hp = static_cast<uint8_t*>(ctx->h_pinned);
+    int* cnt_flags = reinterpret_cast<int*>(hp);
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(&cnt_flags[0], sv.kp_count + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(&cnt_flags[1], sv.flags + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (kp) B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_kp, sv.kp + (size_t)slot * sv.kp_cap, kb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc) B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_desc, sv.desc + (size_t)slot * sv.kp_cap * kDescBytes, db, cudaMemcpyDeviceToHost, ctx->stream));
+    if (prev_slot >= 0) {
+        if ((rc = run_pairs(ctx, prev_slot, 1, slot, pair_id, nullptr, ctx->opt.ransac_hypotheses))) return rc;
+        B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_rec, ctx->pairs.rec, sizeof(b200vo_pose_record), cudaMemcpyDeviceToHost, ctx->stream));
+        B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_E, ctx->pairs.E, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    *n = cnt_flags[0];
+    if (cnt_flags[1]) { set_error("slot %d: internal list overflow (flags=%d)", slot, cnt_flags[1]); return B200VO_ERR_CAPACITY; }
+    if ((kp || desc) && cap < cnt_flags[0]) { set_error("capacity %d < %d keypoints", cap, cnt_flags[0]); return B200VO_ERR_CAPACITY; }
+    if (kp) std::memcpy(kp, hp + off_kp, (size_t)cnt_flags[0] * sizeof(b200vo_keypoint));
+    if (desc) std::memcpy(desc, hp + off_desc, (size_t)cnt_flags[0] * kDescBytes);
+    if (prev_slot >= 0) {
+        std::memcpy(rec, hp + off_rec, sizeof(b200vo_pose_record));
+        if (essential) std::memcpy(essential, hp + off_E, 9 * sizeof(double));
+    }
+    return B200VO_OK;
+}
+
 int b200vo_process_pairs_device(b200vo_ctx* ctx, int first_slot, int npairs, int64_t first_pair_id, void** records_dev) {
     if (!ctx || !slot_ok(ctx, first_slot) || npairs <= 0 || npairs > ctx->max_pairs - 1) { set_error("bad arguments (npairs must be in 1..max_frames-1)"); return B200VO_ERR_BAD_ARG; }
     B200VO_CUDA_CHECK(cudaSetDevice(ctx->device));

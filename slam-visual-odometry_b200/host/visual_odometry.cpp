@@ -73,15 +73,17 @@ cv::Mat VisualOdometry::process_frame(Frame& frame) {
     const int slots = std::max(2, options_.batch_frames + 1);
     const int cur = initialized_ ? (previous_slot_ + 1) % slots : 0;
     const ImageView v = view_of(frame.image, width_, height_);
-    check(b200vo_upload_frames(ctx_, v.data, 1, v.pitch, v.pitch * height_, v.channels, cur), "upload_frames");
-    check(b200vo_detect(ctx_, cur, 1), "detect");
-
-    // detect_features(): fill frame.keypoints / frame.descriptors (reference :103-117)
+    // one call, one synchronisation: upload + detect + (if there is a previous frame) match / RANSAC / pose
     const int cap = b200vo_max_keypoints(ctx_);
-    std::vector<b200vo_keypoint> kps((size_t)cap);
-    cv::Mat desc(cap, 32, CV_8UC1);
+    kp_buf_.resize((size_t)cap);
+    desc_buf_.resize((size_t)cap * 32);
     int n = 0;
-    check(b200vo_get_features(ctx_, cur, kps.data(), desc.data, cap, &n), "get_features");
+    b200vo_pose_record rec;
+    double E[9];
+    check(b200vo_process_frame(ctx_, v.data, v.pitch, v.channels, cur, initialized_ ? previous_slot_ : -1, frame_counter_ - 1,
+                               kp_buf_.data(), desc_buf_.data(), cap, &n, &rec, E), "process_frame");
+    const b200vo_keypoint* kps = kp_buf_.data();
+    // detect_features(): fill frame.keypoints / frame.descriptors (reference :103-117)
     frame.keypoints.resize((size_t)n);
     for (int i = 0; i < n; ++i) {
         cv::KeyPoint& k = frame.keypoints[(size_t)i];
@@ -89,7 +91,7 @@ cv::Mat VisualOdometry::process_frame(Frame& frame) {
         k.response = kps[i].response; k.octave = kps[i].octave; k.class_id = kps[i].class_id;
     }
     cv::Mat d(n, 32, CV_8UC1);
-    for (int i = 0; i < n; ++i) std::copy(desc.data + (size_t)i * 32, desc.data + (size_t)(i + 1) * 32, d.data + (size_t)i * d.step);
+    for (int i = 0; i < n; ++i) std::copy(desc_buf_.data() + (size_t)i * 32, desc_buf_.data() + (size_t)(i + 1) * 32, d.data + (size_t)i * d.step);
     frame.descriptors = d;
     frame.processed = true;
     const cv::Mat display_image = frame.image.clone();
@@ -106,9 +108,6 @@ cv::Mat VisualOdometry::process_frame(Frame& frame) {
 
     // Default to the last known pose; the record's status bits encode the reference's fallbacks.
     frame.pose = Pose(previous_frame_.pose.R_wc, previous_frame_.pose.t_wc);
-    b200vo_pose_record rec;
-    double E[9];
-    check(b200vo_relative_pose(ctx_, previous_slot_, cur, frame_counter_ - 1, nullptr, 0, &rec, E, nullptr, 0), "relative_pose");
     if (rec.status & B200VO_ST_E_FOUND) {
         double F[9];
         check(b200vo_fundamental_from_essential(ctx_, E, F), "fundamental");
