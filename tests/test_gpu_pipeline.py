@@ -175,3 +175,26 @@ def test_ratio_mode_pipeline(built, seq):
         Rg, tg = synth.relative_pose_gt(R_wc, C_w, i)
         # minimal-sample model without refit on a differently composed match list: 2 degrees
         assert G.rotation_angle_deg(r["R"].reshape(3, 3), Rg) < 2.0
+
+
+def test_streaming_entry_point_equals_separate_calls(built, seq, records):
+    """b200vo_process_frame (one synchronisation) returns what upload + detect + get_features +
+    relative_pose return."""
+    frames = seq[0]
+    batched, _ = records
+    with built.Context(W, H, nfeatures=NF, max_frames=2, ransac_hypotheses=NHYP) as ctx, \
+         built.Context(W, H, nfeatures=NF, max_frames=2, ransac_hypotheses=NHYP) as ref:
+        prev = -1
+        for i in range(4):
+            cur = i & 1
+            kp, desc, rec, E = ctx.process_frame(frames[i], cur, prev, i - 1)
+            ref.upload_frames(frames[i:i + 1], cur)
+            ref.detect(cur, 1)
+            rkp, rdesc = ref.get_features(cur)
+            assert kp.tobytes() == rkp.tobytes() and np.array_equal(desc, rdesc)
+            if i == 0:
+                assert rec is None
+            else:
+                rrec, rE, _ = ref.relative_pose(prev, cur, pair_id=i - 1)
+                assert rec.tobytes() == rrec.tobytes() == batched[i - 1].tobytes() and np.array_equal(E, rE)
+            prev = cur
