@@ -128,7 +128,7 @@ int launch_filter(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_overri
     while (P < ctx->store.kp_cap) P <<= 1;
     const size_t smem = (size_t)P * sizeof(uint32_t);
     static size_t configured = 0;
-    if (smem > 48 * 1024 && configured < smem) {
+    if (configured < smem) {          // static shared memory counts against the 48 KB default too: always opt in
         B200VO_CUDA_CHECK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }

@@ -233,7 +233,7 @@ int launch_select(b200vo_ctx* ctx, int first_slot, int n) {
         smem = std::max(smem, (size_t)ctx->store.lv[l].sel_cap * 8 + (size_t)p2 * 8);
     }
     static size_t configured = 0;
-    if (smem > 48 * 1024 && configured < smem) {
+    if (configured < smem) {          // static shared memory counts against the 48 KB default too: always opt in
         B200VO_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }

@@ -169,3 +169,24 @@ def test_tma_and_word_staging_agree(built, seq_small, monkeypatch):
             assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
         else:
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("W,H,NF", [(100, 80, 300), (333, 222, 700), (1999, 1001, 5000), (64, 64, 100), (4095, 300, 2000)])
+def test_odd_sizes_bit_exact(built, W, H, NF):
+    """Widths that are not multiples of 4 / 16, the smallest and the widest supported images, a level
+    smaller than the border, and a feature budget whose selection kernel needs exactly 48 KB of dynamic
+    shared memory (a launch failure found with this case)."""
+    from b200vo import synth
+    frames = synth.make_sequence(W, H, 2, device="cuda")[0].cpu().numpy()
+    with built.Context(W, H, nfeatures=NF, max_frames=3, ransac_hypotheses=64) as ctx:
+        ctx.upload_frames(frames, 0)
+        ctx.detect(0, 2)
+        for s in (0, 1):
+            kp, desc = ctx.get_features(s)
+            ref = O.detect_and_compute(frames[s], NF)
+            assert len(kp) == len(ref["x"])
+            assert np.array_equal(kp["lx"], ref["x"]) and np.array_equal(kp["ly"], ref["y"]) and np.array_equal(kp["octave"], ref["level"])
+            assert np.array_equal(kp["angle"], ref["angle"]) and np.array_equal(kp["response"], ref["response"])
+            assert np.array_equal(desc, ref["desc"])
+        rec = ctx.process_pairs(0, 1, 0)[0]
+        assert rec["n_matches"] >= 0
