@@ -190,3 +190,21 @@ def test_odd_sizes_bit_exact(built, W, H, NF):
             assert np.array_equal(desc, ref["desc"])
         rec = ctx.process_pairs(0, 1, 0)[0]
         assert rec["n_matches"] >= 0
+
+
+@pytest.mark.parametrize("thr", [1, 40, 127, 128, 200])
+def test_fast_threshold_range(built, seq_small, thr):
+    """FAST corners for thresholds across the supported range (the byte-SIMD pre-test switches formula at
+    t >= 128), against the oracle's score map and live cv2."""
+    frames = seq_small[0]
+    with built.Context(640, 240, nfeatures=500, max_frames=2, fast_threshold=thr) as ctx:
+        ctx.upload_frames(frames[:1], 0)
+        ctx.detect(0, 1)
+        pyr = O.build_pyramid(frames[0])
+        for level in (0, 3):
+            x, y, sc = ctx.get_fast_candidates(0, level)
+            xs, ys, ss = O.fast_detect(pyr[level], thr)
+            h, w = pyr[level].shape
+            keep = (xs >= 31) & (xs < w - 31) & (ys >= 31) & (ys < h - 31)
+            ref = sorted(zip(ys[keep].tolist(), xs[keep].tolist(), ss[keep].tolist()))
+            assert sorted(zip(y.tolist(), x.tolist(), sc.tolist())) == ref, "threshold %d level %d" % (thr, level)
