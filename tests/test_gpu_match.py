@@ -193,3 +193,16 @@ def test_ratio_mode_rejects_bad_options(built):
         built.Context(640, 240, match_mode=7)
     with pytest.raises(built.B200VOError):
         built.Context(640, 240, match_mode=built.MATCH_RATIO, ratio=1.5)
+
+
+def test_knn2_large_batch_uses_wide_row_tiles(ctx):
+    """A batch large enough that the 2-NN kernel runs with 4 query rows per thread (the CTA count
+    decides): every 50th pair checked against the oracle."""
+    rng = np.random.default_rng(31)
+    P, n1, n2 = 300, 700, 650
+    q = rng.integers(0, 256, (P, n1, 32), dtype=np.uint8); t = rng.integers(0, 256, (P, n2, 32), dtype=np.uint8)
+    q[:, :40] = t[:, :40]                     # exact duplicates: distance 0, ties with their neighbours
+    idx, dist = ctx.knn2_match_descriptors(q, t, npairs=P)
+    for p in range(0, P, 50):
+        oi, od = M.knn2_match(q[p], t[p])
+        assert np.array_equal(idx[p], oi) and np.array_equal(dist[p], od), p
