@@ -89,3 +89,37 @@ def test_scoring_decomposition_cheirality_vs_golden(hs, golden):
             best = (int(ok.sum()), R.reshape(3, 3).copy(), tt.copy(), ok.copy())
     assert best[0] == int(golden["rp_count"]) and np.array_equal(best[3], golden["rp_mask"])
     assert np.abs(best[1] - golden["rp_R"]).max() < 1e-9 and np.abs(best[2] - golden["rp_t"]).max() < 1e-9
+
+
+def test_cooperative_five_point_vs_cv2_golden(hs, golden):
+    """The product's solver (csrc/fivept_group.cuh, 10 lanes per hypothesis) executed on the host with the
+    lanes of every phase run one after another, against cv2's solution sets (findEssentialMat on exactly
+    five points returns all solutions) and against the independent thread-per-hypothesis form."""
+    x1, x2, K = _pts(golden)
+    S = golden["samples"]; ns = golden["fivept_nsol"]; Eg = golden["fivept_E"].reshape(-1, 3, 3)
+    off, errs, same, res, cross = 0, [], 0, [], []
+    for h, s in enumerate(S):
+        ref = Eg[off:off + ns[h]]; off += ns[h]
+        a, b = np.ascontiguousarray(x1[s]), np.ascontiguousarray(x2[s])
+        E = np.zeros((10, 9)); Et = np.zeros((10, 9))
+        n = hs.hs_five_point_group(P(a), P(b), P(E))
+        nt = hs.hs_five_point(P(a), P(b), P(Et))
+        got = E[:n].reshape(-1, 3, 3)
+        same += n == len(ref)
+        for e in ref:
+            errs.append(min([min(np.abs(e - g).max(), np.abs(e + g).max()) for g in got], default=1.0))
+        for g in got:
+            assert abs(np.linalg.norm(g) - 1.0) < 1e-12
+            res.append(max(abs(np.linalg.det(g)), np.abs(2 * g @ g.T @ g - np.trace(g @ g.T) * g).max()))
+        for e in Et[:nt]:
+            cross.append(min([min(np.abs(e - g.ravel()).max(), np.abs(e + g.ravel()).max()) for g in got], default=1.0))
+    assert same >= 0.93 * len(S) and (np.array(errs) <= 1e-6).mean() >= 0.95
+    assert np.percentile(res, 95) < 1e-12
+    assert (np.array(cross) <= 1e-8).mean() >= 0.97          # the two forms agree on (almost) every root
+
+
+def test_cooperative_solver_shared_block_layout(hs):
+    """2672 bytes: a multiple of 16 (array of blocks stays aligned) and 112 mod 128 (the three groups of a
+    warp touch disjoint banks when they read the same member)."""
+    n = hs.hs_group_shared_bytes()
+    assert n % 16 == 0 and n % 128 == 112 and n <= 4096
