@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Stage times and launch-sequence wall time of ONE frame / ONE pair (the streaming regime of
+VisualOdometry::process_frame): python tools/single_frame_times.py"""
 import sys, time, numpy as np
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/slam-visual-odometry_b200')
 import b200vo
