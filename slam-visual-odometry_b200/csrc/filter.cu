@@ -127,8 +127,11 @@ int launch_filter(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_overri
     int P = 1;
     while (P < ctx->store.kp_cap) P <<= 1;
     const size_t smem = (size_t)P * sizeof(uint32_t);
-    static size_t configured = 0;
-    if (configured < smem) {          // static shared memory counts against the 48 KB default too: always opt in
+    // the attribute is per function AND per device and the last value set wins, so it only ever grows;
+    // static shared memory counts against the 48 KB default too: always opt in
+    static size_t configured_per_device[64] = {};
+    size_t& configured = configured_per_device[ctx->device & 63];
+    if (configured < smem) {
         B200VO_CUDA_CHECK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }

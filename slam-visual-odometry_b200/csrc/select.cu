@@ -232,8 +232,11 @@ int launch_select(b200vo_ctx* ctx, int first_slot, int n) {
         while (p2 < ctx->store.lv[l].kp_cap) p2 <<= 1;
         smem = std::max(smem, (size_t)ctx->store.lv[l].sel_cap * 8 + (size_t)p2 * 8);
     }
-    static size_t configured = 0;
-    if (configured < smem) {          // static shared memory counts against the 48 KB default too: always opt in
+    // the attribute is per function AND per device and the last value set wins, so it only ever grows;
+    // static shared memory counts against the 48 KB default too: always opt in
+    static size_t configured_per_device[64] = {};
+    size_t& configured = configured_per_device[ctx->device & 63];
+    if (configured < smem) {
         B200VO_CUDA_CHECK(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }

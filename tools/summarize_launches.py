@@ -23,8 +23,12 @@ def main(path):
         d = agg.setdefault(k, [0, 0.0])
         d[0] += 1
         d[1] += v
-    ours = {k: v for k, v in agg.items() if "b200vo::" in k}
-    other = {k: v for k, v in agg.items() if "b200vo::" not in k}
+    # ncu prints the namespace only in some modes (not with -k filters): recognise the library's kernels by name too
+    lib = re.compile(r"b200vo::|^(resize_tma|resize|bgr2gray|fast|select|orient|keypoint_finalize|blur|brief|match|match_knn2|filter|"
+                     r"five_point_group|five_point_deferred|score|score_models|finalize|pose_decompose|pose_vote|pose_select|pose_mask|"
+                     r"clear_detect_state|adaptive_update|stamp_rounds|popc_rate)_kernel")
+    ours = {k: v for k, v in agg.items() if lib.search(k)}
+    other = {k: v for k, v in agg.items() if not lib.search(k)}
     tot = sum(v[1] for v in ours.values())
     print("# ncu launch list summary: %s\n" % path)
     print("Library kernels (namespace b200vo): %d launches, %.1f us total under ncu\n" % (sum(v[0] for v in ours.values()), tot))
