@@ -181,6 +181,31 @@ class DevView:
         self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPU cores NVML reports as local to its GPU BEFORE the pinned frame buffer is
+    allocated (first touch decides the NUMA node): with eight ranks uploading 467 MB per step each, host
+    memory on the wrong socket makes the e2e path PCIe/UPI-bound.  Best effort; silently skipped."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = None
+        try:                                   # CUDA ordinal -> NVML handle through the UUID (CUDA_VISIBLE_DEVICES may reorder)
+            import torch
+            uuid = str(torch.cuda.get_device_properties(index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def algorithmic_bytes(ctx, nfeatures):
     """algorithmic bytes per frame of the HBM-bound stages."""
     px = [ctx.level_info(l)[0] * ctx.level_info(l)[1] for l in range(8)]
@@ -217,6 +242,7 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     F, NF, B = args.frames, args.features, min(args.batch, args.frames)
