@@ -78,15 +78,9 @@ __device__ __forceinline__ uint32_t hamming256(const uint32_t* q, const uint4& t
     }
 }
 
-template <int R, int CSA>
-__global__ void __launch_bounds__(MT_THREADS)
-match_kernel(MatchArgs a) {
-    __shared__ __align__(16) uint32_t s_t[MT_MAXCHUNK * 8];
-    __shared__ uint32_t s_col[MT_MAXCHUNK];
-
-    const int pair = blockIdx.z;
-    const uint8_t* q; const uint8_t* t;
-    int n1, n2;
+// query / train descriptor arrays and their sizes of pair `pair`: ring slots of the frame store, or
+// back-to-back raw arrays
+__device__ __forceinline__ void resolve_pair(const MatchArgs& a, int pair, const uint8_t*& q, const uint8_t*& t, int& n1, int& n2) {
     if (a.counts) {
         const int sa = (a.first_slot + pair) % a.slots;
         const int sb = (a.slot_b_override >= 0) ? a.slot_b_override : (a.first_slot + pair + 1) % a.slots;
@@ -98,6 +92,18 @@ match_kernel(MatchArgs a) {
         t = a.t + (size_t)pair * a.t_stride;
         n1 = a.n1; n2 = a.n2;
     }
+}
+
+template <int R, int CSA>
+__global__ void __launch_bounds__(MT_THREADS)
+match_kernel(MatchArgs a) {
+    __shared__ __align__(16) uint32_t s_t[MT_MAXCHUNK * 8];
+    __shared__ uint32_t s_col[MT_MAXCHUNK];
+
+    const int pair = blockIdx.z;
+    const uint8_t* q; const uint8_t* t;
+    int n1, n2;
+    resolve_pair(a, pair, q, t, n1, n2);
     const int row0 = blockIdx.y * (MT_THREADS * R);
     const int col0 = blockIdx.x * a.chunk;
     if (row0 >= n1 || col0 >= n2) return;
@@ -174,17 +180,7 @@ match_knn2_kernel(MatchArgs a) {
     const int pair = blockIdx.z;
     const uint8_t* q; const uint8_t* t;
     int n1, n2;
-    if (a.counts) {
-        const int sa = (a.first_slot + pair) % a.slots;
-        const int sb = (a.slot_b_override >= 0) ? a.slot_b_override : (a.first_slot + pair + 1) % a.slots;
-        q = a.q + (size_t)sa * a.kp_cap * kDescBytes;
-        t = a.t + (size_t)sb * a.kp_cap * kDescBytes;
-        n1 = a.counts[sa]; n2 = a.counts[sb];
-    } else {
-        q = a.q + (size_t)pair * a.q_stride;
-        t = a.t + (size_t)pair * a.t_stride;
-        n1 = a.n1; n2 = a.n2;
-    }
+    resolve_pair(a, pair, q, t, n1, n2);
     const int row0 = blockIdx.y * (MT_THREADS * R);
     if (row0 >= n1) return;
     const int tid = threadIdx.x;

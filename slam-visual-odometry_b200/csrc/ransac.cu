@@ -7,13 +7,14 @@
 //
 // OpenCV draws its samples from a private RNG and stops adaptively; here every pair evaluates a
 // fixed, seeded set of H hypotheses (a pure function of (seed, pair id, hypothesis index), never
-// of the rank or batch), all in one launch:
-//   five_point_kernel : one thread per hypothesis -> up to 10 essential matrices
-//   score_kernel      : one warp per hypothesis; lanes stride over the correspondences, ballot +
-//                       popc counts inliers of each model; the best (count, first index) of the
-//                       pair is kept with one 64-bit atomicMax on (count << 32 | ~model_index)
-//   finalize_kernel   : winning E, its inlier mask, record fields
-//   recover_pose_kernel: one CTA per pair; the four (R,t) candidates are voted on by all points.
+// of the rank or batch), the whole batch of pairs per launch:
+//   five_point_group_kernel    : 10 lanes per hypothesis (fivept_group.cuh) -> up to 10 essential matrices
+//   five_point_deferred_kernel : the few hypotheses that need the exact root path, densely packed
+//   score_kernel               : CTA per (pair, 64 hypotheses), correspondences staged in shared memory,
+//                                one warp per model; ballot + popc counts inliers; the best (count, first
+//                                index) of the pair is kept with one 64-bit atomicMax on (count << 32 | ~index)
+//   finalize_kernel            : winning E, its inlier mask, record fields
+//   pose_decompose / pose_vote / pose_select : recoverPose; the four (R,t) candidates are voted on by all points
 // "First arg-max wins" is exactly OpenCV's rule (a model replaces the best only if strictly
 // better), realised order-independently by the packed atomicMax.
 #include "common.cuh"
@@ -36,10 +37,10 @@ struct RansacArgs {
 };
 
 // ---- cooperative five-point solver (fivept_group.cuh) ----------------------------------------
-// One hypothesis per group of 10 lanes, three groups per warp, 12 per CTA; the whole solver
+// One hypothesis per group of 10 lanes, three groups per warp, 24 per CTA; the whole solver
 // (null space -> constraints -> elimination -> det B(z) -> Sturm isolation -> per-root finish) is ONE
 // kernel: the 10x20 matrix stays in the registers of the group, every exchange goes through the
-// group's 4.8 KB block of shared memory, nothing is staged through global or local memory.
+// group's 2.7 KB block of shared memory, nothing is staged through global or local memory.
 // (round-1 history: a thread-per-hypothesis solver ran with 10 of 32 lanes active; a three-phase
 // version with stream compaction fixed the divergence but left 5.6 KB of local memory per thread and
 // 85 % long-scoreboard stalls -- profiles/ncu_r01_final_kernels.txt.)
@@ -47,10 +48,10 @@ struct RansacArgs {
 // hypothesis: half of the lane slots) are re-packed onto dense lanes for the per-root finish (refine,
 // back-substitute, polish), which reads the owning group's setup data from shared memory; only as
 // many warps as there are roots keep running.
-// DEFERRED = false (main launch): hypothesis = blockIdx; one whose Sturm chain is unreliable (2-6 %,
+// EXACT = false (main launch): hypothesis = blockIdx; one whose Sturm chain is unreliable (2-6 %,
 // near-multiple roots) is appended to a queue instead of taking the long exact-root path, which would
 // make its warp the straggler of the CTA (measured: 42 % of the warp time was spent waiting for it).
-// DEFERRED = true: the queued hypotheses, packed densely -- here every group takes the exact path.
+// EXACT = true (deferred launch): the queued hypotheses, packed densely -- every group takes the exact path.
 template <int THREADS, bool EXACT>
 __device__ __forceinline__ void fpg_solve(const PairView& pv, const RansacArgs& ra, geom::GroupShared* groups, int* s_nroot, int* s_gid,
                                           unsigned short* s_root, bool in_range, int pair, int h) {
