@@ -74,10 +74,12 @@ def test_accuracy_vs_ground_truth_and_cv2(built, seq, records):
         R = r["R"].reshape(3, 3)
         assert abs(np.linalg.det(R) - 1) < 1e-9 and abs(np.linalg.norm(r["t"]) - 1) < 1e-9
         assert G.rotation_angle_deg(R, Rg) < 1.0, "pair %d rotation error vs GT" % i
-        # same correspondences as the cv2 pipeline (identical good-match count), and a rotation
-        # within a degree of it (cv2 draws its own hypotheses: parity is by tolerance)
+        # same correspondences as the cv2 pipeline (identical good-match count).  cv2 draws its own
+        # hypotheses (parity is by tolerance): both results are minimal-sample models
+        # within a degree of the ground truth, hence within two degrees of each other
         assert r["n_matches"] == cv_recs[i]["n_matches"]
-        assert G.rotation_angle_deg(R, cv_recs[i]["R"]) < 1.0
+        assert G.rotation_angle_deg(cv_recs[i]["R"], Rg) < 1.0, "pair %d: cv2 rotation error vs GT" % i
+        assert G.rotation_angle_deg(R, cv_recs[i]["R"]) < 2.0
 
 
 def _host(built):
