@@ -51,7 +51,7 @@ typedef enum {
     B200VO_ERR_BAD_ARG = -1,
     B200VO_ERR_CAPACITY = -2,       /* a caller buffer or an internal fixed-capacity list is too small */
     B200VO_ERR_CUDA = -3,
-    B200VO_ERR_NOT_READY = -4,      /* e.g. matching a slot that has no features */
+    B200VO_ERR_NOT_READY = -4,      /* reserved; a slot without features is a soft failure (0 matches, status 0), as in the reference */
     B200VO_ERR_ALLOC = -5
 } b200vo_status;
 
