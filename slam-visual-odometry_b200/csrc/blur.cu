@@ -28,19 +28,22 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 // Each thread produces 4 horizontally adjacent pixels in both passes: the row pass reads 3 aligned
 // shared-memory words (10 bytes) for 4 outputs, the column pass 7 float4.
+template <bool MERGED>
 __global__ void __launch_bounds__(256)
-blur_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+blur_kernel(StoreView sv, const __grid_constant__ LevelTiles lt, int level_arg, int first_slot, const __grid_constant__ LevelMaps maps, int use_tma) {
     __shared__ __align__(128) uint32_t s_in[BL_SH][BL_SWW];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) float s_row[BL_SH][BL_W];
     // kernel taps as the float32 bit patterns OpenCV's getGaussianKernel(7, 2, CV_32F) yields
     const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu),
                 k2 = __uint_as_float(0x3e434a39u), k3 = __uint_as_float(0x3e5d4ae0u);
+    int level = level_arg, bx = blockIdx.x, by = blockIdx.y, frame = blockIdx.z;
+    if (MERGED) { const TileCoord tc = tile_coord(lt, blockIdx.x); level = tc.level; bx = tc.bx; by = tc.by; frame = tc.frame; }
     const LevelGeom g = sv.lv[level];
-    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    const int slot = (first_slot + frame) % sv.slots;
     const uint8_t* __restrict__ img = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset;
     uint8_t* out = sv.blur + (size_t)slot * sv.slot_bytes + g.offset;
-    const int ox = blockIdx.x * BL_W, oy = blockIdx.y * BL_H;
+    const int ox = bx * BL_W, oy = by * BL_H;
     const int tid = threadIdx.x;
 
     // stage rows oy-3 .. oy+BL_H+2, bytes ox-16 .. ox+BL_W+15 (BORDER_REFLECT_101 at the image edges)
@@ -50,7 +53,7 @@ blur_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUt
         __syncthreads();
         if (tid == 0) {
             tma::mbar_arrive_expect_tx(&s_bar, BL_SH * BL_SWW * 4);
-            tma::load_3d(&s_in[0][0], &tmap, &s_bar, ox - BL_HALO, oy - 3, slot);
+            tma::load_3d(&s_in[0][0], &maps.m[level], &s_bar, ox - BL_HALO, oy - 3, slot);
         }
         tma::mbar_wait(&s_bar, 0);
         if (border) {
@@ -150,10 +153,20 @@ blur_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUt
 }
 
 int launch_blur(b200vo_ctx* ctx, int first_slot, int n) {
+    const LevelMaps& maps = *reinterpret_cast<const LevelMaps*>(ctx->tmap_blur);
+    LevelTiles lt;
+    lt.first[0] = 0;
+    for (int l = 0; l < kLevels; ++l) level_tiles_add(lt, l, div_up(ctx->store.lv[l].w, BL_W), div_up(ctx->store.lv[l].h, BL_H), n);
+    if (n <= kMergedLevelsMaxFrames) {
+        // one launch for all eight levels
+        blur_kernel<true><<<lt.first[kLevels], 256, 0, ctx->stream>>>(ctx->store, lt, 0, first_slot, maps, ctx->use_tma ? 1 : 0);
+        B200VO_LAUNCH_CHECK(ctx);
+        return B200VO_OK;
+    }
     for (int l = 0; l < kLevels; ++l) {
         const LevelGeom& g = ctx->store.lv[l];
         dim3 grid(div_up(g.w, BL_W), div_up(g.h, BL_H), n);
-        blur_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_blur[l], ctx->use_tma ? 1 : 0);
+        blur_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->store, lt, l, first_slot, maps, ctx->use_tma ? 1 : 0);
         B200VO_LAUNCH_CHECK(ctx);
     }
     return B200VO_OK;

@@ -56,8 +56,7 @@ __device__ __forceinline__ void load_ring(const uint8_t* p, int* v) {
 //   3. corners: corner score (max over 9-arcs of the arc minimum, minus 1) -> score tile
 //   4. corners: strict 3x3 non-max suppression + border filter -> candidate list + histogram
 template <int CW>
-__global__ void __launch_bounds__(256)
-fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+__device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx, int by, int frame, int first_slot, const CUtensorMap* tmap, int use_tma) {
     using T = FastTile<CW>;
     constexpr int FT_CW = T::FT_CW, FT_CH = T::FT_CH, FT_W = T::FT_W, FT_H = T::FT_H, FT_SW = T::FT_SW, FT_SWW = T::FT_SWW, FT_SH = T::FT_SH;
     __shared__ __align__(128) uint8_t s_img[FT_SH * FT_SW];
@@ -70,10 +69,10 @@ fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUt
     __shared__ int s_hist[256];                     // score histogram of this tile, flushed once (one global atomic per non-empty bin)
 
     const LevelGeom g = sv.lv[level];
-    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    const int slot = (first_slot + frame) % sv.slots;
     const uint8_t* __restrict__ img = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset;
-    const int ox = kEdge + blockIdx.x * FT_W;       // first output pixel of the tile
-    const int oy = kEdge + blockIdx.y * FT_H;
+    const int ox = kEdge + bx * FT_W;       // first output pixel of the tile
+    const int oy = kEdge + by * FT_H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int px0 = ox - 4, py0 = oy - 4;           // pixel-tile origin (>= 27: always inside the image)
     // TMA needs a 16-byte aligned inner coordinate, the word-load path a 4-byte aligned one
@@ -87,7 +86,7 @@ fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUt
         __syncthreads();
         if (tid == 0) {
             tma::mbar_arrive_expect_tx(&s_bar, FT_SH * FT_SW);
-            tma::load_3d(s_img, &tmap, &s_bar, x0, py0, slot);
+            tma::load_3d(s_img, tmap, &s_bar, x0, py0, slot);
         }
         uint32_t* sc32 = reinterpret_cast<uint32_t*>(s_score);
         for (int i = tid; i < FT_CH * FT_CW / 4; i += 256) sc32[i] = 0;
@@ -249,6 +248,21 @@ fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUt
         if (base + i < g.cand_cap) out[base + i] = s_list[i];
 }
 
+// one pyramid level per launch (large batches): the level is a kernel parameter
+template <int CW>
+__global__ void __launch_bounds__(256)
+fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+    fast_tile<CW>(sv, level, blockIdx.x, blockIdx.y, blockIdx.z, first_slot, &tmap, use_tma);
+}
+
+// several levels per launch (small batches, see LevelTiles)
+template <int CW>
+__global__ void __launch_bounds__(256, 6)
+fast_levels_kernel(StoreView sv, const __grid_constant__ LevelTiles lt, int first_slot, const __grid_constant__ LevelMaps maps, int use_tma) {
+    const TileCoord tc = tile_coord(lt, blockIdx.x);
+    fast_tile<CW>(sv, tc.level, tc.bx, tc.by, tc.frame, first_slot, &maps.m[tc.level], use_tma);
+}
+
 __global__ void clear_detect_state_kernel(StoreView sv, int first_slot, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int per = kLevels * 256;
@@ -274,16 +288,39 @@ int launch_fast(b200vo_ctx* ctx, int first_slot, int n) {
         clear_detect_state_kernel<<<div_up(total, 256), 256, 0, ctx->stream>>>(ctx->store, first_slot, n);
         B200VO_LAUNCH_CHECK(ctx);
     }
+    const LevelMaps& maps = *reinterpret_cast<const LevelMaps*>(ctx->tmap_fast);
+    const int tma = ctx->use_tma ? 1 : 0;
+    LevelTiles wide, narrow;
+    wide.first[0] = narrow.first[0] = 0;
+    for (int l = 0; l < kLevels; ++l) {
+        const LevelGeom& g = ctx->store.lv[l];
+        const int iw = g.w - 2 * kEdge, ih = g.h - 2 * kEdge;
+        const bool w = fast_level_is_wide(l), any = iw > 0 && ih > 0;
+        level_tiles_add(wide, l, any ? div_up(iw, FastTile<128>::FT_W) : 0, (any && w) ? div_up(ih, FastTile<128>::FT_H) : 0, n);
+        level_tiles_add(narrow, l, any ? div_up(iw, FastTile<64>::FT_W) : 0, (any && !w) ? div_up(ih, FastTile<64>::FT_H) : 0, n);
+    }
+    if (n <= kMergedLevelsMaxFrames) {
+        // two launches: the wide-tile levels (0..4) and the narrow-tile levels (5..7)
+        if (wide.first[kLevels] > 0) {
+            fast_levels_kernel<128><<<wide.first[kLevels], 256, 0, ctx->stream>>>(ctx->store, wide, first_slot, maps, tma);
+            B200VO_LAUNCH_CHECK(ctx);
+        }
+        if (narrow.first[kLevels] > 0) {
+            fast_levels_kernel<64><<<narrow.first[kLevels], 256, 0, ctx->stream>>>(ctx->store, narrow, first_slot, maps, tma);
+            B200VO_LAUNCH_CHECK(ctx);
+        }
+        return B200VO_OK;
+    }
     for (int l = 0; l < kLevels; ++l) {
         const LevelGeom& g = ctx->store.lv[l];
         const int iw = g.w - 2 * kEdge, ih = g.h - 2 * kEdge;
         if (iw <= 0 || ih <= 0) continue;
         if (fast_level_is_wide(l)) {
             dim3 grid(div_up(iw, FastTile<128>::FT_W), div_up(ih, FastTile<128>::FT_H), n);
-            fast_kernel<128><<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], ctx->use_tma ? 1 : 0);
+            fast_kernel<128><<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], tma);
         } else {
             dim3 grid(div_up(iw, FastTile<64>::FT_W), div_up(ih, FastTile<64>::FT_H), n);
-            fast_kernel<64><<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], ctx->use_tma ? 1 : 0);
+            fast_kernel<64><<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], tma);
         }
         B200VO_LAUNCH_CHECK(ctx);
     }

@@ -134,6 +134,31 @@ def test_ring_wraparound_and_batch_invariance(built, seq_small):
     assert np.array_equal(b[1], ref["desc"])
 
 
+def test_merged_and_per_level_launches_agree(built, seq_small):
+    """Batches of up to 16 frames run FAST and the blur with one launch over all pyramid levels, larger
+    batches with one launch per level (common.cuh kMergedLevelsMaxFrames): the same frames through both
+    give byte-identical keypoints, descriptors, FAST candidates and blurred levels."""
+    frames = np.concatenate([seq_small[0]] * 8)[:20]              # 20 frames: > 16 -> per-level launches
+    frames = np.ascontiguousarray(frames)
+    frames[3:] = np.roll(frames[3:], 5, axis=2)                    # not all copies identical
+    with built.Context(640, 240, nfeatures=1000, max_frames=20, ransac_hypotheses=64) as big, \
+         built.Context(640, 240, nfeatures=1000, max_frames=20, ransac_hypotheses=64) as small:
+        big.upload_frames(frames, 0)
+        big.detect(0, 20)
+        small.upload_frames(frames, 0)
+        for s in range(0, 20, 5):
+            small.detect(s, 5)                                     # <= 16 -> merged launches
+        for s in (0, 3, 7, 19):
+            a, b = big.get_features(s), small.get_features(s)
+            assert a[0].tobytes() == b[0].tobytes() and np.array_equal(a[1], b[1])
+            for lv in (0, 4, 5, 7):
+                assert np.array_equal(big.get_pyramid_level(s, lv, blurred=True), small.get_pyramid_level(s, lv, blurred=True))
+                ca, cb = big.get_fast_candidates(s, lv), small.get_fast_candidates(s, lv)
+                assert all(np.array_equal(x, y) for x, y in zip(ca, cb))
+        ref = O.detect_and_compute(frames[19], 1000)
+        assert np.array_equal(big.get_features(19)[1], ref["desc"])
+
+
 def test_flat_image_has_no_features(built):
     with built.Context(640, 240, nfeatures=500, max_frames=2, ransac_hypotheses=64) as ctx:
         ctx.upload_frames(np.full((1, 240, 640), 77, np.uint8), 0)
