@@ -292,6 +292,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         ctx->use_tma = true;
         if (const char* v = getenv("B200VO_TMA")) ctx->use_tma = (atoi(v) != 0);
         ctx->match_csa = 3;
+        ctx->filter_fast_cap = 1 << 30;
+        if (const char* v = getenv("B200VO_FILTER_FAST_CAP")) ctx->filter_fast_cap = atoi(v);
         if (const char* v = getenv("B200VO_MATCH_CSA")) { const int c = atoi(v); if (c >= 0 && c <= 3) ctx->match_csa = c; }
         void* fnp = nullptr;
         cudaDriverEntryPointQueryResult qres;

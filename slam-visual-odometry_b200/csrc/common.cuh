@@ -152,6 +152,7 @@ struct b200vo_ctx {
     CUtensorMap tmap_resize[b200vo::kLevels];    // [l] = level l as the SOURCE of level l+1
     bool use_tma;
     int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC, 2: full Harley-Seal (4 POPC), 3: 3 CSA + 5 POPC (default)
+    int filter_fast_cap;       // filter.cu: survivors the compacted sort may hold (B200VO_FILTER_FAST_CAP, tests set 0)
     int64_t launches;
     bool timing;
     b200vo_stage_times times;

@@ -206,3 +206,35 @@ def test_knn2_large_batch_uses_wide_row_tiles(ctx):
     for p in range(0, P, 50):
         oi, od = M.knn2_match(q[p], t[p])
         assert np.array_equal(idx[p], oi) and np.array_equal(dist[p], od), p
+
+
+@pytest.mark.parametrize("max_hamming", [35.0, 256.0])
+def test_filter_compacted_and_full_sort_agree(built, monkeypatch, max_hamming):
+    """The filter kernel reads minimum / median / survivor count off the distance histogram and sorts only
+    the survivors; with B200VO_FILTER_FAST_CAP=0 (or a cap below the survivor count) it sorts the whole
+    list as its first version did.  Same good-match list, count and threshold, and equal to the oracle;
+    max_hamming = 256 makes most matches survive (long sorted lists, distances up to ~100)."""
+    rng = np.random.default_rng(5)
+    t = rng.integers(0, 256, (2500, 32), dtype=np.uint8)
+    q = t[rng.permutation(2500)[:2300]].copy()
+    for i, f in enumerate(rng.integers(20, 60, len(q))):
+        for b in rng.integers(0, 256, f):
+            q[i, b // 8] ^= np.uint8(1 << (b % 8))
+    outs = []
+    for cap in ("4096", "0", "64"):
+        monkeypatch.setenv("B200VO_FILTER_FAST_CAP", cap)
+        with built.Context(640, 240, nfeatures=3000, max_frames=4, ransac_hypotheses=64, max_hamming=max_hamming) as c:
+            c.set_features(0, None, q)
+            c.set_features(1, None, t)
+            good, n_cross, thr = c.match(0, 1)
+            outs.append((good.tobytes(), n_cross, thr))
+    assert outs[0] == outs[1] == outs[2]
+    good = np.frombuffer(outs[0][0], built.DMATCH_DTYPE)
+    qi, ti, d, thr_o, nc = M.good_matches(q, t) if max_hamming == 35.0 else (None,) * 5
+    if qi is not None:
+        assert outs[0][1] == nc and outs[0][2] == thr_o
+        assert np.array_equal(good["queryIdx"], qi) and np.array_equal(good["trainIdx"], ti)
+    else:
+        assert len(good) > 1000                                    # the long-list case really is long
+        key = good["distance"].astype(np.int64) * 65536 + good["queryIdx"]
+        assert np.all(np.diff(key) > 0)                            # (distance, queryIdx) order
