@@ -72,7 +72,7 @@ typedef struct b200vo_ctx b200vo_ctx;
 typedef struct b200vo_options {
     int32_t struct_size;            /* sizeof(b200vo_options), set by b200vo_default_options */
     int32_t width, height;          /* level-0 image size */
-    int32_t nfeatures;              /* ORB nfeatures; reference default 1200 (:65) */
+    int32_t nfeatures;              /* ORB nfeatures; reference default 1200 (:65); 1..30841 */
     int32_t fast_threshold;         /* 10 (:73) */
     int32_t max_frames;             /* slots in the device-resident frame store (ring) */
     int32_t ransac_hypotheses;      /* five-point hypotheses per pair; default 1024 (>= OpenCV maxIters 1000) */

@@ -164,7 +164,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     if (opt->struct_size != (int32_t)sizeof(b200vo_options)) { set_error("options struct_size mismatch (ABI)"); return B200VO_ERR_BAD_ARG; }
     if (opt->width < 64 || opt->height < 64 || opt->width > 4095 || opt->height > 4095) {
         set_error("image size %dx%d unsupported (64..4095)", opt->width, opt->height); return B200VO_ERR_BAD_ARG; }
-    if (opt->nfeatures < 1 || opt->nfeatures > 60000) { set_error("nfeatures out of range"); return B200VO_ERR_BAD_ARG; }
+    if (opt->nfeatures < 1 || opt->nfeatures > 30841) { set_error("nfeatures out of range (1..30841: the match filter keeps one 32-bit key per keypoint in shared memory)"); return B200VO_ERR_BAD_ARG; }
     if (opt->max_frames < 2) { set_error("max_frames must be >= 2"); return B200VO_ERR_BAD_ARG; }
     if (opt->ransac_hypotheses < 1) { set_error("ransac_hypotheses must be >= 1"); return B200VO_ERR_BAD_ARG; }
     if (opt->fast_threshold < 1 || opt->fast_threshold > 200) { set_error("fast_threshold out of range"); return B200VO_ERR_BAD_ARG; }
@@ -248,6 +248,12 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     sv.slot_bytes = round_up(off, (size_t)sv.lv[0].pitch);       // frames form a regular 3-D array for batched copies
     sv.kp_cap = (int)round_up((size_t)opt->nfeatures + std::max(opt->nfeatures / 16, 64), 64);
     if (sv.kp_cap > 65535) { set_error("nfeatures too large for 16-bit match indices"); b200vo_destroy(ctx); return B200VO_ERR_BAD_ARG; }
+    {   // filter.cu keeps pow2(kp_cap) + kFilterFastCap 32-bit keys in shared memory
+        size_t p2 = 1;
+        while (p2 < (size_t)sv.kp_cap) p2 <<= 1;
+        if ((p2 + kFilterFastCap) * sizeof(uint32_t) > 227 * 1024) {
+            set_error("nfeatures %d too large for the shared-memory match filter (at most 30841)", opt->nfeatures); b200vo_destroy(ctx); return B200VO_ERR_BAD_ARG; }
+    }
 
     const size_t S = (size_t)sv.slots;
     TRY(dev_alloc(ctx, &sv.pyr, S * sv.slot_bytes));

@@ -41,6 +41,7 @@ struct LevelGeom {
 // with the level as a kernel parameter (fast_kernel, blur_kernel<false>): the kernels measured 2-4 %
 // faster that way at 500 frames per launch.
 constexpr int kMergedLevelsMaxFrames = 16;
+constexpr int kFilterFastCap = 4096;               // filter.cu: survivors the compacted sort holds (16 KB of shared memory)
 struct LevelTiles {
     int first[kLevels + 1];
     int tiles[kLevels];

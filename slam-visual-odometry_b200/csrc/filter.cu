@@ -19,7 +19,7 @@
 namespace b200vo {
 
 constexpr int FL_THREADS = 512;
-constexpr int FL_FAST_CAP = 4096;      // survivors the compacted sort holds (16 KB of shared memory)
+constexpr int FL_FAST_CAP = kFilterFastCap;
 
 struct FilterArgs {
     int first_slot, slot_b_override;

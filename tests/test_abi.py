@@ -63,7 +63,7 @@ def test_bad_options_rejected(built):
     h = ctypes.c_void_p()
     assert lib.b200vo_create(ctypes.byref(o), 0, ctypes.byref(h)) == built.ERR_BAD_ARG
     assert b"struct_size" in lib.b200vo_last_error()
-    for kw in (dict(width=32), dict(nfeatures=0), dict(max_frames=1), dict(ransac_hypotheses=0)):
+    for kw in (dict(width=32), dict(nfeatures=0), dict(nfeatures=30842), dict(max_frames=1), dict(ransac_hypotheses=0)):
         o = built.default_options(640, 240)
         for k, v in kw.items():
             setattr(o, k, v)
