@@ -2,7 +2,7 @@
 
 Nothing like this exists in the reference (its data/ directory is untracked); it is the input
 generator for tests and bench.py, not part of the hot path.  A textured corridor (ground, ceiling,
-two side walls) is rendered by per-pixel ray/plane intersection with the intrinsics the reference
+two side walls, boards at staggered depths) is rendered by per-pixel ray/plane intersection with the intrinsics the reference
 synthesises from the image size, fx = fy = W, cx = W/2, cy = H/2
 (/root/reference/src/visual_odometry.cpp:90-98).  torch is used only as an array library so the
 same code renders on the CPU (tests, golden fixtures) and on the GPU (bench).
@@ -35,7 +35,7 @@ def camera_matrix(width, height):
     return np.array([[float(width), 0, width / 2.0], [0, float(width), height / 2.0], [0, 0, 1.0]])
 
 
-def make_trajectory(nframes, seed=5678, step=0.45):
+def make_trajectory(nframes, seed=5678, step=1.0):
     """Smooth forward motion with gentle yaw/pitch and sway.  Returns R_wc (n,3,3), C_w (n,3)."""
     rng = np.random.default_rng(seed)
     ph = rng.uniform(0, 2 * math.pi, 4)
@@ -44,7 +44,7 @@ def make_trajectory(nframes, seed=5678, step=0.45):
     for i in range(nframes):
         yaw = 0.10 * math.sin(0.045 * i + ph[0]) + 0.04 * math.sin(0.21 * i + ph[1])
         pitch = 0.015 * math.sin(0.13 * i + ph[2])
-        x = 0.9 * math.sin(0.03 * i + ph[3])
+        x = 0.45 * math.sin(0.03 * i + ph[3])
         y = 0.05 * math.sin(0.17 * i + ph[0])
         z += step * (1.0 + 0.2 * math.sin(0.07 * i + ph[1]))
         cy, sy = math.cos(yaw), math.sin(yaw)
@@ -64,8 +64,16 @@ def relative_pose_gt(R_wc, C_w, i):
     return R, t / np.linalg.norm(t)
 
 
-# planes: (normal axis, offset, texture axes); camera: x right, y down, z forward
-_PLANES = ((1, 1.65, (0, 2)), (1, -2.6, (0, 2)), (0, -4.5, (2, 1)), (0, 5.5, (2, 1)))
+# Scene (camera: x right, y down, z forward).  Four textured planes form a corridor narrow enough that
+# structure starts ~5 m ahead -- (normal axis, offset, texture axes) -- and three families of
+# fronto-parallel boards repeat along z at staggered periods: (z0, period, x range, y range).  The boards
+# give the depth discontinuities and near-range parallax that make the translation direction of a
+# monocular pair observable to a degree or two (round-1 scene: everything >= 9 m away, 10-20 deg).
+_PLANES = ((1, 1.5, (0, 2)), (1, -2.0, (0, 2)), (0, -2.5, (2, 1)), (0, 3.0, (2, 1)))
+_BOARDS = ((2.0, 7.0, (0.9, 1.9), (-0.9, 1.5)), (5.5, 7.0, (-1.9, -0.9), (-0.6, 1.5)), (4.0, 11.0, (-0.5, 0.5), (-2.0, -0.7)))
+_BOARDS_AHEAD = 6          # boards of each family tested per ray (visible range ~ 40 m)
+_BOARD_NEAR = 2.0          # the nearest board is at least this far ahead (closer ones only blur the frame)
+_DETAIL_GAIN, _DETAIL_FREQ, _DETAIL_RANGE_M = 0.7, 4.3, 9.0     # fine texture layer, faded out with distance (a crude LOD)
 
 
 @torch.no_grad()
@@ -76,6 +84,7 @@ def render_frames(width, height, R_wc, C_w, texture, device="cpu", texels_per_m=
     tex = torch.as_tensor(texture, device=dev).float()
     ts = tex.shape[0]
     fx = float(width)
+    detail_range = _DETAIL_RANGE_M * fx / 1241.0        # the detail layer aliases beyond ~fx/260 m
     u = (torch.arange(width, device=dev, dtype=torch.float32) - width / 2.0) / fx
     v = (torch.arange(height, device=dev, dtype=torch.float32) - height / 2.0) / fx
     dc = torch.stack([u[None, :].expand(height, width), v[:, None].expand(height, width),
@@ -83,6 +92,19 @@ def render_frames(width, height, R_wc, C_w, texture, device="cpu", texels_per_m=
     out = torch.empty((n, height, width), dtype=torch.uint8, device=dev)
     Rt = torch.as_tensor(R_wc, device=dev, dtype=torch.float32)
     Ct = torch.as_tensor(C_w, device=dev, dtype=torch.float32)
+
+    def sample(tu, tv):                                                     # bilinear, tiled
+        u0 = torch.floor(tu); v0 = torch.floor(tv)
+        fu = tu - u0; fv = tv - v0
+        iu0 = torch.remainder(u0, ts).long(); iv0 = torch.remainder(v0, ts).long()
+        iu1 = (iu0 + 1) % ts; iv1 = (iv0 + 1) % ts
+        return (tex[iv0, iu0] * (1 - fu) * (1 - fv) + tex[iv0, iu1] * fu * (1 - fv)
+                + tex[iv1, iu0] * (1 - fu) * fv + tex[iv1, iu1] * fu * fv)
+
+    def shade(t, tu, tv, du, dv):                                           # base layer + near-range detail layer
+        wd = (_DETAIL_GAIN * (1.0 - t / detail_range)).clamp(min=0.0)
+        return sample(tu, tv) + wd * (sample(tu * _DETAIL_FREQ + du, tv * _DETAIL_FREQ + dv) - 128.0)
+
     for s in range(0, n, chunk):
         R = Rt[s:s + chunk]
         C = Ct[s:s + chunk]
@@ -93,19 +115,27 @@ def render_frames(width, height, R_wc, C_w, texture, device="cpu", texels_per_m=
             denom = dw[..., ax]
             t = (off - C[:, ax])[:, None, None] / torch.where(denom.abs() < 1e-9, torch.full_like(denom, 1e-9), denom)
             hit = C[:, None, None, :] + t[..., None] * dw
-            tu = hit[..., ta] * texels_per_m + 137.0 * pi
-            tv = hit[..., tb] * texels_per_m + 71.0 * pi
-            u0 = torch.floor(tu); v0 = torch.floor(tv)
-            fu = tu - u0; fv = tv - v0
-            iu0 = torch.remainder(u0, ts).long(); iv0 = torch.remainder(v0, ts).long()
-            iu1 = (iu0 + 1) % ts; iv1 = (iv0 + 1) % ts
-            val = (tex[iv0, iu0] * (1 - fu) * (1 - fv) + tex[iv0, iu1] * fu * (1 - fv)
-                   + tex[iv1, iu0] * (1 - fu) * fv + tex[iv1, iu1] * fu * fv)
-            fade = torch.exp(-torch.clamp(t - 18.0, min=0.0) / 10.0)
-            val = 128.0 + (val - 128.0) * fade
+            val = shade(t, hit[..., ta] * texels_per_m + 137.0 * pi, hit[..., tb] * texels_per_m + 71.0 * pi, 31.0 * pi, 17.0 * pi)
             ok = (t > 0.05) & (t < best_t)
             best_t = torch.where(ok, t, best_t)
             best_val = torch.where(ok, val, best_val)
+        dz = dw[..., 2].clamp(min=1e-3)
+        for bi, (z0, per, (xa, xb), (ya, yb)) in enumerate(_BOARDS):
+            k0 = torch.ceil((C[:, 2] + _BOARD_NEAR - z0) / per)
+            for j in range(_BOARDS_AHEAD):
+                k = k0 + j
+                t = (z0 + k * per - C[:, 2])[:, None, None] / dz
+                hx = C[:, 0, None, None] + t * dw[..., 0]
+                hy = C[:, 1, None, None] + t * dw[..., 1]
+                jx = ((torch.remainder(k * 0.6180339887, 1.0) - 0.5) * 0.6)[:, None, None]    # per-board lateral jitter
+                inside = (hx - jx > xa) & (hx - jx < xb) & (hy > ya) & (hy < yb)
+                kk = k[:, None, None]
+                val = shade(t, hx * texels_per_m + 211.0 * bi + 97.0 * kk, hy * texels_per_m + 59.0 * bi + 31.0 * kk, 13.0 * bi + 7.0 * kk, 5.0 * bi)
+                ok = inside & (t > 0.05) & (t < best_t)
+                best_t = torch.where(ok, t, best_t)
+                best_val = torch.where(ok, val, best_val)
+        fade = torch.exp(-torch.clamp(best_t - 18.0, min=0.0) / 10.0)
+        best_val = 128.0 + (best_val - 128.0) * fade
         out[s:s + chunk] = best_val.round().clamp(0, 255).to(torch.uint8)
     return out
 
