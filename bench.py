@@ -11,7 +11,7 @@ One STEP = one pass of the hot path over the whole synthetic sequence of this ra
            read of the pose records + host-side pose chaining inside the timed region.
 Multi-GPU (torchrun, one process per GPU): the global sequence is partitioned into contiguous
 frame-pair ranges (weak scaling: each rank gets its own F-1 pairs); the only exchange is one NCCL
-all_gather of the 128-byte pose records, then rank 0 chains the trajectory on the host.
+all_gather of the 160-byte pose records, then rank 0 chains the trajectory on the host.
 --impl reference: the reference's own CPU path (the same OpenCV calls through cv2, oracle/pipeline.py)
 on the host cores, one worker process per core over contiguous pair ranges.
 """
@@ -146,12 +146,8 @@ def run_reference(args):
     tex = synth.make_texture()
     R_wc, C_w = synth.make_trajectory(args.frames)
     nfr = min(args.frames, pairs + 1)
-    try:
-        import torch
-        dev = "cuda" if torch.cuda.is_available() else "cpu"
-    except Exception:
-        dev = "cpu"
-    frames = synth.render_frames(W_IMG, H_IMG, R_wc[:nfr], C_w[:nfr], tex, device=dev).cpu().numpy()
+    # rendered on the CPU: nothing of this arm touches a GPU
+    frames = synth.render_frames(W_IMG, H_IMG, R_wc[:nfr], C_w[:nfr], tex, device="cpu").numpy()
     pairs = min(pairs, nfr - 1)
     vals = []
     for i in range(args.warmup + args.steps):
@@ -258,9 +254,10 @@ def run_b200(args):
 
     ctx = b200vo.Context(W_IMG, H_IMG, device=local, nfeatures=NF, max_frames=B + 1, ransac_hypotheses=args.hypotheses)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    recs_dev = torch.zeros(npairs * 128, dtype=torch.uint8, device="cuda:%d" % local)
-    recs_all = torch.zeros(world * npairs * 128, dtype=torch.uint8, device="cuda:%d" % local) if world > 1 else recs_dev
-    recs_host = torch.empty(world * npairs * 128, dtype=torch.uint8, pin_memory=True)
+    RB = b200vo.RECORD_BYTES
+    recs_dev = torch.zeros(npairs * RB, dtype=torch.uint8, device="cuda:%d" % local)
+    recs_all = torch.zeros(world * npairs * RB, dtype=torch.uint8, device="cuda:%d" % local) if world > 1 else recs_dev
+    recs_host = torch.empty(world * npairs * RB, dtype=torch.uint8, pin_memory=True)
     frame_bytes = W_IMG * H_IMG
     state = {"traj": None}
 
@@ -283,14 +280,14 @@ def run_b200(args):
             if np_ > 0:
                 ptr = ctx.process_pairs_device(p0, np_, f0 + done_pairs)
                 with torch.cuda.stream(stream):
-                    src = torch.as_tensor(DevView(ptr, np_ * 128), device="cuda:%d" % local)
-                    recs_dev[done_pairs * 128:(done_pairs + np_) * 128].copy_(src, non_blocking=True)
+                    src = torch.as_tensor(DevView(ptr, np_ * RB), device="cuda:%d" % local)
+                    recs_dev[done_pairs * RB:(done_pairs + np_) * RB].copy_(src, non_blocking=True)
             prev_slot = (first + n - 1) % (B + 1)
             done_frames += n
             done_pairs += np_
         with torch.cuda.stream(stream):
             if world > 1:
-                dist.all_gather_into_tensor(recs_all, recs_dev)     # the one exchange step: 128 B per pair
+                dist.all_gather_into_tensor(recs_all, recs_dev)     # the one exchange step: 160 B per pair
             if host_input:
                 recs_host.copy_(recs_all, non_blocking=True)
         if host_input:
@@ -457,9 +454,9 @@ def run_b200(args):
         "dtype": "u8/i32 (features, matching), f64 (geometry)", "data": "synthetic",
         "config": {"workload": "%d-frame synthetic KITTI-shaped sequence %dx%d per GPU, %d ORB features, %d five-point hypotheses/pair, launch batches of %d frames" % (F, W_IMG, H_IMG, NF, args.hypotheses, B),
                    "pairs_per_step": total_pairs, "cache": "inputs larger than L2 (%.0f MB of frames per step)" % (F * frame_bytes / 1e6),
-                   "partition": "contiguous frame-pair ranges, one per GPU; one NCCL all_gather of 128-B pose records" if world > 1 else "single GPU"},
+                   "partition": "contiguous frame-pair ranges, one per GPU; one NCCL all_gather of 160-B pose records" if world > 1 else "single GPU"},
         "e2e": {"value": round(e2e, 1), "unit": "pairs/s", "ms_per_step": round(ms_e2e, 3), "h2d_bytes_per_step": world * F * frame_bytes,
-                "d2h_bytes_per_step": world * npairs * 128, "wall_ms_per_step": round(wall_e2e * 1e3, 3)},
+                "d2h_bytes_per_step": world * npairs * RB, "wall_ms_per_step": round(wall_e2e * 1e3, 3)},
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
         "roofline": roof, "roofline_hbm": roof_hbm, "stages": stages_out,
@@ -516,6 +513,4 @@ if __name__ == "__main__":
     rc = main()
     sys.stdout.flush()
     sys.stderr.flush()
-    # All results are printed and every context is closed; skip interpreter-shutdown destructors
-    # (torch's caching allocators may still hold events on streams owned by the closed contexts).
-    os._exit(rc)
+    sys.exit(rc)

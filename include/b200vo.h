@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define B200VO_ABI_VERSION 1
+#define B200VO_ABI_VERSION 2
 #define B200VO_NLEVELS 8            /* reference src/visual_odometry.cpp:67 */
 
 typedef enum {
@@ -59,7 +59,9 @@ typedef enum {
 #define B200VO_ST_MATCHED 1         /* >= 10 good matches: pose estimation attempted (:344-345) */
 #define B200VO_ST_E_FOUND 2         /* >= 8 matches and a model was found: R,t valid (:189,:218) */
 #define B200VO_ST_POSE_OK 4         /* valid_points >= 10 and inliers >= 12 -> scale 0.3 (:270-277,:352) */
-#define B200VO_ST_OVERFLOW 256      /* an internal list overflowed; results for this pair are not exact */
+#define B200VO_ST_OVERFLOW 256      /* an internal fixed-capacity list of one of the two frames overflowed (only possible
+                                     * through score ties); its feature set was truncated deterministically, so the
+                                     * pair's results are reproducible but not the reference's */
 #define B200VO_ST_ROUNDS_SHIFT 16    /* adaptive mode: bits 16..23 = number of 128-hypothesis blocks evaluated */
 
 #define B200VO_MATCH_CROSSCHECK 0   /* reference behaviour: cross-check + adaptive threshold */
@@ -108,8 +110,10 @@ typedef struct b200vo_dmatch {
     float distance;
 } b200vo_dmatch;
 
-/* 128-byte relative-pose record: the wire format gathered across GPUs.  (R,t) is OpenCV's
- * recoverPose convention: x_c2 = R x_c1 + t, |t| = 1. */
+/* 160-byte relative-pose record: the wire format gathered across GPUs.  (R,t) is OpenCV's
+ * recoverPose convention: x_c2 = R x_c1 + t, |t| = 1.  The tail carries what the reference prints per
+ * pair: the [MatchDebug] statistics of the unfiltered match list (src/visual_odometry.cpp:119-143,
+ * 160-168) and the mean algebraic epipolar residual over the RANSAC inliers (:248-263). */
 typedef struct b200vo_pose_record {
     double R[9];                    /* row-major */
     double t[3];
@@ -121,6 +125,12 @@ typedef struct b200vo_pose_record {
     int32_t best_hyp;               /* index of the winning hypothesis, -1 if none */
     int32_t best_sol;               /* which of its solutions */
     float threshold;                /* adaptive Hamming threshold used */
+    double dist_mean;               /* mean distance of the n_cross matches (get_mean_dist_ham, :130-134); 0 if none */
+    double epi_residual;            /* mean |x2^T F x1| over the inliers of findEssentialMat, pixel coordinates, F = K^-T E K^-1
+                                     * with E as returned here (|E|_F = 1; the residual is algebraic, so it scales with E); 0 when no E (:248-263) */
+    float dist_min, dist_max;       /* matches.front() / matches.back() after the sort (:160-161) */
+    float dist_median;              /* element size/2 of the sorted list (get_median_dist, :136-143) */
+    int32_t reserved;
 } b200vo_pose_record;
 
 typedef struct b200vo_stage_times {

@@ -274,6 +274,18 @@ def fundamental_from_essential(E, K):
     return Kinv.T @ E @ Kinv
 
 
+def epipolar_residual(E, K, p1, p2, mask):
+    """visual_odometry.cpp:248-263: mean |x2^T F x1| over the inliers of findEssentialMat, homogeneous
+    PIXEL coordinates, F = K^-T E K^-1 (:225-246).  0 when the mask is empty."""
+    F = fundamental_from_essential(E, K)
+    p1 = np.asarray(p1, np.float64).reshape(-1, 2); p2 = np.asarray(p2, np.float64).reshape(-1, 2)
+    m = np.asarray(mask).astype(bool).ravel()
+    if not m.any():
+        return 0.0
+    x1 = np.c_[p1, np.ones(len(p1))][m]; x2 = np.c_[p2, np.ones(len(p2))][m]
+    return float(np.abs(np.einsum("ij,jk,ik->i", x2, F, x1)).mean())
+
+
 def compose_pose(R_wc, t_wc, R, t, scale):
     """visual_odometry.cpp:292-314: invert (R,t) then T_w_c2 = T_w_c1 * T_c1_c2 with scaled t."""
     R_inv = R.T

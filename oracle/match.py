@@ -84,6 +84,16 @@ def adaptive_threshold(dist_sorted):
     return min(max(3.0 * mn, 0.7 * med), MAX_HAMMING_THRESHOLD)
 
 
+def match_statistics(dist):
+    """The [MatchDebug] values of the unfiltered match list (visual_odometry.cpp:119-143,160-168):
+    min = sorted.front(), max = sorted.back(), mean = sum/size in double, median = element size/2.
+    Returns dict(min, max, mean, median); all 0 for an empty list (the reference returns before printing)."""
+    d = np.sort(np.asarray(dist, np.float64))
+    if len(d) == 0:
+        return {"min": 0.0, "max": 0.0, "mean": 0.0, "median": 0.0}
+    return {"min": float(d[0]), "max": float(d[-1]), "mean": float(d.sum() / len(d)), "median": float(d[len(d) // 2])}
+
+
 def good_matches(q, t, ratio=None):
     """get_good_matches_of_features (visual_odometry.cpp:145-180) in the canonical order
     (distance, queryIdx) -- std::sort there is unstable, so ties have no defined order.

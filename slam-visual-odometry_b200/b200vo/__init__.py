@@ -34,8 +34,12 @@ KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle"
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
 POSE_RECORD_DTYPE = np.dtype([("R", "<f8", (9,)), ("t", "<f8", (3,)), ("n_matches", "<i4"), ("n_inliers", "<i4"),
                               ("n_valid", "<i4"), ("status", "<i4"), ("n_cross", "<i4"), ("best_hyp", "<i4"),
-                              ("best_sol", "<i4"), ("threshold", "<f4")])
-assert KEYPOINT_DTYPE.itemsize == 32 and DMATCH_DTYPE.itemsize == 16 and POSE_RECORD_DTYPE.itemsize == 128
+                              ("best_sol", "<i4"), ("threshold", "<f4"),
+                              ("dist_mean", "<f8"), ("epi_residual", "<f8"), ("dist_min", "<f4"), ("dist_max", "<f4"),
+                              ("dist_median", "<f4"), ("reserved", "<i4")])
+RECORD_BYTES = POSE_RECORD_DTYPE.itemsize
+ABI_VERSION = 2
+assert KEYPOINT_DTYPE.itemsize == 32 and DMATCH_DTYPE.itemsize == 16 and RECORD_BYTES == 160
 
 
 class StageTimes(C.Structure):

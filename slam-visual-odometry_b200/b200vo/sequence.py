@@ -3,7 +3,7 @@
 The reference processes a sequence strictly in order on one thread (src/main.cpp:128-194).  Frame
 pairs are independent until pose chaining, so rank r of G owns a contiguous range of pairs, runs the
 whole per-pair path on its own GPU, and the only exchange is one all_gather of the fixed-size
-128-byte pose records (b200vo_pose_record); rank 0 then chains them on the host exactly as
+160-byte pose records (b200vo_pose_record); rank 0 then chains them on the host exactly as
 process_frame would (src/visual_odometry.cpp:340-374).  torch.distributed is plumbing only: NCCL
 over NVLink on GPUs, gloo in the CPU tests.
 """

@@ -101,24 +101,27 @@ def render_frames(width, height, R_wc, C_w, texture, device="cpu", texels_per_m=
         return (tex[iv0, iu0] * (1 - fu) * (1 - fv) + tex[iv0, iu1] * fu * (1 - fv)
                 + tex[iv1, iu0] * (1 - fu) * fv + tex[iv1, iu1] * fu * fv)
 
-    def shade(t, tu, tv, du, dv):                                           # base layer + near-range detail layer
-        wd = (_DETAIL_GAIN * (1.0 - t / detail_range)).clamp(min=0.0)
-        return sample(tu, tv) + wd * (sample(tu * _DETAIL_FREQ + du, tv * _DETAIL_FREQ + dv) - 128.0)
-
     for s in range(0, n, chunk):
         R = Rt[s:s + chunk]
         C = Ct[s:s + chunk]
         dw = torch.einsum("nij,hwj->nhwi", R, dc)                          # (b,H,W,3)
+        # pass 1: the nearest surface of every ray and its texture coordinates (no texture access yet)
         best_t = torch.full(dw.shape[:3], 1e9, device=dev)
-        best_val = torch.full(dw.shape[:3], 128.0, device=dev)
+        b_tu = torch.zeros_like(best_t); b_tv = torch.zeros_like(best_t)
+        b_du = torch.zeros_like(best_t); b_dv = torch.zeros_like(best_t)
+
+        def take(ok, t, tu, tv, du, dv):
+            nonlocal best_t, b_tu, b_tv, b_du, b_dv
+            best_t = torch.where(ok, t, best_t)
+            b_tu = torch.where(ok, tu, b_tu); b_tv = torch.where(ok, tv, b_tv)
+            b_du = torch.where(ok, du, b_du); b_dv = torch.where(ok, dv, b_dv)
+
         for pi, (ax, off, (ta, tb)) in enumerate(_PLANES):
             denom = dw[..., ax]
             t = (off - C[:, ax])[:, None, None] / torch.where(denom.abs() < 1e-9, torch.full_like(denom, 1e-9), denom)
             hit = C[:, None, None, :] + t[..., None] * dw
-            val = shade(t, hit[..., ta] * texels_per_m + 137.0 * pi, hit[..., tb] * texels_per_m + 71.0 * pi, 31.0 * pi, 17.0 * pi)
-            ok = (t > 0.05) & (t < best_t)
-            best_t = torch.where(ok, t, best_t)
-            best_val = torch.where(ok, val, best_val)
+            take((t > 0.05) & (t < best_t), t, hit[..., ta] * texels_per_m + 137.0 * pi, hit[..., tb] * texels_per_m + 71.0 * pi,
+                 torch.full_like(t, 31.0 * pi), torch.full_like(t, 17.0 * pi))
         dz = dw[..., 2].clamp(min=1e-3)
         for bi, (z0, per, (xa, xb), (ya, yb)) in enumerate(_BOARDS):
             k0 = torch.ceil((C[:, 2] + _BOARD_NEAR - z0) / per)
@@ -130,13 +133,14 @@ def render_frames(width, height, R_wc, C_w, texture, device="cpu", texels_per_m=
                 jx = ((torch.remainder(k * 0.6180339887, 1.0) - 0.5) * 0.6)[:, None, None]    # per-board lateral jitter
                 inside = (hx - jx > xa) & (hx - jx < xb) & (hy > ya) & (hy < yb)
                 kk = k[:, None, None]
-                val = shade(t, hx * texels_per_m + 211.0 * bi + 97.0 * kk, hy * texels_per_m + 59.0 * bi + 31.0 * kk, 13.0 * bi + 7.0 * kk, 5.0 * bi)
-                ok = inside & (t > 0.05) & (t < best_t)
-                best_t = torch.where(ok, t, best_t)
-                best_val = torch.where(ok, val, best_val)
+                take(inside & (t > 0.05) & (t < best_t), t, hx * texels_per_m + 211.0 * bi + 97.0 * kk,
+                     hy * texels_per_m + 59.0 * bi + 31.0 * kk, (13.0 * bi + 7.0 * kk).expand_as(t), torch.full_like(t, 5.0 * bi))
+        # pass 2: one texture lookup per pixel -- base layer + near-range detail layer, faded with distance
+        wd = (_DETAIL_GAIN * (1.0 - best_t / detail_range)).clamp(min=0.0)
+        val = sample(b_tu, b_tv) + wd * (sample(b_tu * _DETAIL_FREQ + b_du, b_tv * _DETAIL_FREQ + b_dv) - 128.0)
         fade = torch.exp(-torch.clamp(best_t - 18.0, min=0.0) / 10.0)
-        best_val = 128.0 + (best_val - 128.0) * fade
-        out[s:s + chunk] = best_val.round().clamp(0, 255).to(torch.uint8)
+        val = torch.where(best_t < 1e8, 128.0 + (val - 128.0) * fade, torch.full_like(val, 128.0))
+        out[s:s + chunk] = val.round().clamp(0, 255).to(torch.uint8)
     return out
 
 

@@ -328,6 +328,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     TRY(dev_alloc(ctx, &pv.n_good, P));
     TRY(dev_alloc(ctx, &pv.n_cross, P));
     TRY(dev_alloc(ctx, &pv.thr, P));
+    TRY(dev_alloc(ctx, &pv.mstat, P * 4));
+    TRY(dev_alloc(ctx, &pv.ovf, P));
     TRY(dev_alloc(ctx, &pv.x1x, P * C));
     TRY(dev_alloc(ctx, &pv.x1y, P * C));
     TRY(dev_alloc(ctx, &pv.x2x, P * C));
@@ -700,7 +702,8 @@ int b200vo_process_frame(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int
     }
     B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     *n = cnt_flags[0];
-    if (cnt_flags[1]) { set_error("slot %d: internal list overflow (flags=%d)", slot, cnt_flags[1]); return B200VO_ERR_CAPACITY; }
+    // an overflowed internal list (score ties) is a soft failure here, as everything on the per-frame path of the
+    // reference is: the truncation is deterministic and the pair record carries B200VO_ST_OVERFLOW
     if ((kp || desc) && cap < cnt_flags[0]) { set_error("capacity %d < %d keypoints", cap, cnt_flags[0]); return B200VO_ERR_CAPACITY; }
     if (kp) std::memcpy(kp, hp + off_kp, (size_t)cnt_flags[0] * sizeof(b200vo_keypoint));
     if (desc) std::memcpy(desc, hp + off_desc, (size_t)cnt_flags[0] * kDescBytes);

@@ -106,6 +106,8 @@ struct PairView {
     int* n_good;               // [pairs]
     int* n_cross;              // [pairs]
     double* thr;               // [pairs]
+    double* mstat;             // [pairs][4] min, max, median, mean of the unfiltered match distances ([MatchDebug], reference :119-168)
+    int* ovf;                  // [pairs] OR of the overflow flags of the pair's two slots
     // geometry (normalised coordinates of the good matches, SoA)
     double* x1x; double* x1y; double* x2x; double* x2y;   // [pairs][kp_cap]
     float4* xf;                // [pairs][kp_cap] the same four coordinates rounded to float (scoring prefilter)

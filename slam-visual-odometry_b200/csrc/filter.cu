@@ -95,22 +95,33 @@ filter_kernel(StoreView sv, PairView pv, FilterArgs fa, int P /* pow2 >= kp_cap 
         for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off); if (lane >= off) incl += v; }
         const int excl = incl - sum;
         const int m = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        double thr = 0.0;
+        double thr = 0.0, mn = 0.0, mx = 0.0, med = 0.0, mean = 0.0;
         if (m > 0) {
             const unsigned nz = __ballot_sync(0xFFFFFFFFu, sum > 0);
             const int rank = m / 2;
             const unsigned md = __ballot_sync(0xFFFFFFFFu, excl <= rank && rank < incl);
-            int first = 0, at_rank = 0, cum = excl;
+            int first = 0, last = 0, at_rank = 0, cum = excl, wsum = 0;
             bool found_first = false, found_rank = false;
 #pragma unroll
             for (int k = 0; k < 9; ++k) {
                 if (!found_first && c[k] > 0) { first = lane * 9 + k; found_first = true; }
+                if (c[k] > 0) last = lane * 9 + k;
+                wsum += (lane * 9 + k) * c[k];
                 cum += c[k];
                 if (!found_rank && cum > rank) { at_rank = lane * 9 + k; found_rank = true; }
             }
-            const double mn = (double)__shfl_sync(0xFFFFFFFFu, first, __ffs(nz) - 1);
-            const double med = (double)__shfl_sync(0xFFFFFFFFu, at_rank, __ffs(md) - 1);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, off);
+            mn = (double)__shfl_sync(0xFFFFFFFFu, first, __ffs(nz) - 1);
+            mx = (double)__shfl_sync(0xFFFFFFFFu, last, 31 - __clz(nz));
+            med = (double)__shfl_sync(0xFFFFFFFFu, at_rank, __ffs(md) - 1);
+            mean = (double)wsum / (double)m;                   // the distances are integers: the sum is exact in any order
             thr = fmin(fmax(3.0 * mn, 0.7 * med), fa.max_hamming);
+        }
+        if (lane == 0) {                                        // [MatchDebug] statistics (reference :119-129,160-168)
+            double* st = pv.mstat + (size_t)pair * 4;
+            st[0] = mn; st[1] = mx; st[2] = med; st[3] = mean;
+            pv.ovf[pair] = sv.flags[sa] | sv.flags[sb];
         }
         int gl = 0;
 #pragma unroll

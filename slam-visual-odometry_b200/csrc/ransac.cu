@@ -288,10 +288,27 @@ finalize_kernel(PairView pv, RansacArgs ra) {
         for (int k = 0; k < 9; ++k) E[k] = 0.0;
     }
     const size_t base = (size_t)pair * pv.kp_cap;
-    for (int i = tid; i < m; i += blockDim.x)
-        pv.inl[base + i] = found ? (uint8_t)geom::sampson_inlier(E, pv.x1x[base + i], pv.x1y[base + i], pv.x2x[base + i],
-                                                                 pv.x2y[base + i], ra.thr2f)
-                                 : (uint8_t)0;
+    // inlier mask of the winner, and the reference's self-check: mean |x2^T F x1| over the inliers in pixel
+    // coordinates (src/visual_odometry.cpp:248-263).  With F = K^-T E K^-1 that is x2n^T E x1n on the
+    // normalised points.  Fixed summation order (strided partial sums, then a tree): the record is byte-identical
+    // whatever the batch.
+    __shared__ double s_sum[256];
+    double part = 0.0;
+    for (int i = tid; i < m; i += blockDim.x) {
+        bool in = false;
+        if (found) {
+            const double x1 = pv.x1x[base + i], y1 = pv.x1y[base + i], x2 = pv.x2x[base + i], y2 = pv.x2y[base + i];
+            in = geom::sampson_inlier(E, x1, y1, x2, y2, ra.thr2f);
+            if (in) part += fabs(x2 * (E[0] * x1 + E[1] * y1 + E[2]) + y2 * (E[3] * x1 + E[4] * y1 + E[5]) + (E[6] * x1 + E[7] * y1 + E[8]));
+        }
+        pv.inl[base + i] = in ? (uint8_t)1 : (uint8_t)0;
+    }
+    s_sum[tid] = part;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) s_sum[tid] += s_sum[tid + o];
+        __syncthreads();
+    }
     if (tid == 0) {
         for (int k = 0; k < 9; ++k) pv.E[(size_t)pair * 9 + k] = E[k];
         b200vo_pose_record r;
@@ -300,11 +317,16 @@ finalize_kernel(PairView pv, RansacArgs ra) {
         r.n_matches = m;
         r.n_inliers = found ? cnt : 0;
         r.n_valid = 0;
-        r.status = ((m >= ra.min_matches) ? B200VO_ST_MATCHED : 0) | (found ? B200VO_ST_E_FOUND : 0);
+        r.status = ((m >= ra.min_matches) ? B200VO_ST_MATCHED : 0) | (found ? B200VO_ST_E_FOUND : 0) |
+                   (pv.ovf[pair] ? B200VO_ST_OVERFLOW : 0);
         r.n_cross = pv.n_cross[pair];
         r.best_hyp = h;
         r.best_sol = s;
         r.threshold = (float)pv.thr[pair];
+        const double* st = pv.mstat + (size_t)pair * 4;
+        r.dist_min = (float)st[0]; r.dist_max = (float)st[1]; r.dist_median = (float)st[2]; r.dist_mean = st[3];
+        r.epi_residual = (found && cnt > 0) ? s_sum[0] / (double)cnt : 0.0;
+        r.reserved = 0;
         pv.rec[pair] = r;
     }
 }

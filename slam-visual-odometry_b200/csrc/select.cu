@@ -153,6 +153,14 @@ select_kernel(StoreView sv, int first_slot) {
             // the cut is the maximum candidate bin over lanes
             for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
             cut = max(best, 0);
+            // retainBest keeps every tie at the cut score.  If they do not fit the working set (saturated or
+            // binary imagery), drop the whole tie bin -- count(score > cut) < 2 N_l always fits -- so the
+            // truncation is deterministic, and flag the slot (B200VO_ST_OVERFLOW in the pair record).
+            int ge = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ge += (tid * 8 + i >= cut) ? local[i] : 0;
+            for (int o = 16; o > 0; o >>= 1) ge += __shfl_xor_sync(0xffffffffu, ge, o);
+            if (ge > g.sel_cap) { cut += 1; if (tid == 0) atomicOr(&sv.flags[slot], 2); }
         }
         if (tid == 0) { s_cut = (n2 > 0) ? cut : 256; s_m = 0; s_out = 0; }
     }

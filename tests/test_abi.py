@@ -27,13 +27,13 @@ def test_every_declared_symbol_is_exported(built):
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(built.EXPORTS) == names
-    assert lib.b200vo_abi_version() == 1
+    assert lib.b200vo_abi_version() == 2
 
 
 def test_struct_layouts(built):
     o = built.default_options(1241, 376)
     assert o.struct_size == ctypes.sizeof(built.Options)
-    assert built.KEYPOINT_DTYPE.itemsize == 32 and built.DMATCH_DTYPE.itemsize == 16 and built.POSE_RECORD_DTYPE.itemsize == 128
+    assert built.KEYPOINT_DTYPE.itemsize == 32 and built.DMATCH_DTYPE.itemsize == 16 and built.POSE_RECORD_DTYPE.itemsize == 160
 
 
 def test_default_options_are_the_reference_constants(built):

@@ -1,5 +1,5 @@
 """Multi-rank logic on CPU (gloo, world_size 2): the contiguous frame-pair partition, the gather
-of fixed-size 128-byte pose records and the host-side chaining.  The records here are synthetic
+of fixed-size 160-byte pose records and the host-side chaining.  The records here are synthetic
 (no GPU): what is tested is that partition + all_gather + chain reproduces the single-process
 trajectory bit for bit, with ranges of unequal length and with failed pairs inside."""
 import os

@@ -238,3 +238,34 @@ def test_filter_compacted_and_full_sort_agree(built, monkeypatch, max_hamming):
         assert len(good) > 1000                                    # the long-list case really is long
         key = good["distance"].astype(np.int64) * 65536 + good["queryIdx"]
         assert np.all(np.diff(key) > 0)                            # (distance, queryIdx) order
+
+
+def test_config4_32k_x_32k_tie_heavy_vs_cv2_live(built):
+    """BASELINE config 4 at full size against the reference's matcher itself: two independent problems of
+    32768 x 32768 descriptors, batched in one launch.  The descriptors vary in only 40 of their 256 bits, so
+    the nearest-neighbour distances pile up at 6..8 and nearly every query has several trains at its minimum
+    distance -- nothing is planted, the lowest-index rule decides both directions.  The cross-checked list
+    must equal cv2.BFMatcher(NORM_HAMMING, crossCheck=True).match exactly: the same (queryIdx, trainIdx,
+    distance) triples in the same order (about 15k of 32k queries survive the cross-check)."""
+    cv2 = pytest.importorskip("cv2")
+    n, P = 32768, 2
+    rng = np.random.default_rng(404)
+    q = np.zeros((P, n, 32), np.uint8); t = np.zeros((P, n, 32), np.uint8)
+    for p in range(P):
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        pos = rng.choice(256, 40, replace=False)
+        for dst in (q, t):
+            bits = np.zeros((n, 256), np.uint8)
+            bits[:, pos] = rng.integers(0, 2, (n, len(pos)), dtype=np.uint8)
+            dst[p] = np.packbits(bits, axis=1, bitorder="little") ^ base
+    with built.Context(640, 240, nfeatures=1000, max_frames=2, ransac_hypotheses=64) as ctx:
+        nq, dq, nt, dt = ctx.match_descriptors(q, t, npairs=P)
+    bf = cv2.BFMatcher_create(cv2.NORM_HAMMING, True)
+    i = np.arange(n)
+    for p in range(P):
+        ref = bf.match(q[p], t[p])
+        keep = nt[p][nq[p]] == i
+        got = np.stack([i[keep], nq[p][keep], dq[p][keep]], 1)
+        want = np.array([(m.queryIdx, m.trainIdx, int(m.distance)) for m in ref], np.int64).reshape(-1, 3)
+        assert len(want) > n // 4 and np.array_equal(got, want), "problem %d: %d vs %d cross-checked matches" % (p, len(got), len(want))
+        assert np.bincount(dq[p]).max() > n // 4          # the data really is tie-heavy: one distance value holds > 25 % of the minima
