@@ -9,13 +9,22 @@ One STEP = one pass of the hot path over the whole synthetic sequence of this ra
 `value`  : whole-job pairs/s with the frames already resident in HBM (device->device ingest).
 `e2e`    : the same through the C ABI with HOST (pinned) frames: H2D copy of every frame and D2H
            read of the pose records + host-side pose chaining inside the timed region.
-Multi-GPU (torchrun, one process per GPU): the global sequence is partitioned into contiguous
-frame-pair ranges (weak scaling: each rank gets its own F-1 pairs); the only exchange is one NCCL
-all_gather of the 160-byte pose records, then rank 0 chains the trajectory on the host.
+Multi-GPU (torchrun, one process per GPU): the headline is weak scaling (each rank owns its own F-1 pairs of
+one long global sequence); the only exchange is one NCCL all_gather of the 160-byte pose records, then rank 0
+chains the trajectory on the host.  After the headline the same run adds
+  `config3` : ONE 1000-frame 1920x1080 sequence, 8000 features, partitioned over the N ranks by contiguous
+              frame-pair ranges (strong scaling; BASELINE.json configs[2]), and
+  `config5` : ONE 256-frame 3840x2160 sequence, 20000 features, 4096 hypotheses per pair (configs[4]),
+each with the whole sequence also run on rank 0 alone, so the line carries the strong-scaling efficiency and a
+byte-comparison of the partitioned records against the one-GPU records.
+Further keys: `streaming` (the reference's real calling pattern: VisualOdometry::process_frame once per frame
+through libb200vo_host.so), `h2d` (per-rank upload bandwidth in the e2e leg and of a plain pinned copy),
+`keypoints_per_frame`, per-stage roofline table.
 --impl reference: the reference's own CPU path (the same OpenCV calls through cv2, oracle/pipeline.py)
 on the host cores, one worker process per core over contiguous pair ranges.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -31,7 +40,9 @@ for p in (ROOT, os.path.join(ROOT, "slam-visual-odometry_b200")):
         sys.path.insert(0, p)
 
 W_IMG, H_IMG = 1241, 376
-MATCH_DRAM_BYTES_PER_LAUNCH = 62631936      # profiles/ncu_r01_match_fullconfig.txt: 60.03 MB read + 2.60 MB written, 500-frame batch, 5.65 ms
+# dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch (500-frame batch) from the ncu --set full capture
+# named in profiles/README.md
+MATCH_DRAM_BYTES_PER_LAUNCH = 62631936
 METRIC = "frame-pairs/sec (detect+match+E-RANSAC+pose)"
 
 
@@ -45,8 +56,11 @@ def parse_args():
     ap.add_argument("--features", type=int, default=3000)
     ap.add_argument("--hypotheses", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=500, help="frames per launch batch (measured: 125 -> 26.6k, 250 -> 28.6k, 500 -> 29.5k, 1000 -> 30.1k pairs/s)")
-    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the bounded CPU sample (0 = auto)")
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs per core in the bounded CPU sample (0 = 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip the config3 / config5 / streaming / adaptive legs")
+    ap.add_argument("--c3-frames", type=int, default=1000)
+    ap.add_argument("--c5-frames", type=int, default=256)
     return ap.parse_args()
 
 
@@ -104,6 +118,41 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# --------------------------------------------------------------------------- accuracy helpers
+def pair_errors(recs, R_gt, C_gt, first_pair=0):
+    """Per-pair relative-pose error against the synthetic ground truth over the pairs with a valid pose:
+    rotation angle and angle between the translation directions (deg).  recs: sequence of mappings with
+    status / R / t (b200vo records or the cv2 pipeline's dicts)."""
+    from b200vo import synth
+    from b200vo import trajectory as T
+    rot, tdir = [], []
+    for i, r in enumerate(recs):
+        if not (int(r["status"]) & 4):
+            continue
+        Rg, tg = synth.relative_pose_gt(R_gt, C_gt, first_pair + i)
+        R = np.asarray(r["R"], np.float64).reshape(3, 3)
+        t = np.asarray(r["t"], np.float64).ravel()
+        rot.append(T.rotation_angle_deg(R, Rg))
+        tdir.append(float(np.degrees(np.arccos(np.clip(t @ tg / max(np.linalg.norm(t), 1e-300), -1.0, 1.0)))))
+    if not rot:
+        return {"pairs": 0}
+    return {"pairs": len(rot), "rot_deg_mean": round(float(np.mean(rot)), 4), "rot_deg_median": round(float(np.median(rot)), 4),
+            "trans_dir_deg_mean": round(float(np.mean(tdir)), 3), "trans_dir_deg_median": round(float(np.median(tdir)), 3)}
+
+
+def accuracy(traj, R_gt, C_gt):
+    """Chained trajectory against the ground truth of the synthetic sequence: similarity-aligned ATE
+    (the reference applies a fixed 0.3 step scale) and mean relative rotation / translation-direction
+    error per pair.  Frame 0 is the identity pose the chain starts from."""
+    from b200vo import trajectory as T
+    poses = np.concatenate([np.concatenate([np.eye(3).ravel(), np.zeros(3)])[None], np.asarray(traj)], 0)
+    n = len(poses)
+    R0, C0 = R_gt[0], C_gt[0]
+    Rg = np.stack([R0.T @ R for R in R_gt[:n]])
+    Cg = np.stack([R0.T @ (C - C0) for C in C_gt[:n]])
+    return T.accuracy_report(poses, Rg, Cg)
+
+
 # --------------------------------------------------------------------------- CPU reference arm
 def _cpu_worker(args):
     frames, nfeatures, nthreads = args
@@ -112,12 +161,14 @@ def _cpu_worker(args):
     from oracle import pipeline as PL
     t0 = time.perf_counter()
     recs, _ = PL.run_pairs_cv2(frames, nfeatures)
-    return len(recs), time.perf_counter() - t0
+    dt = time.perf_counter() - t0
+    slim = [{"status": int(r["status"]), "R": np.asarray(r["R"], np.float64).reshape(9), "t": np.asarray(r["t"], np.float64).reshape(3)} for r in recs]
+    return len(recs), dt, slim
 
 
 def cpu_reference_throughput(frames_host, nfeatures, pairs_total, nproc):
     """The reference path (cv2) over `pairs_total` pairs split into contiguous ranges, one process
-    per core with cv2.setNumThreads(1).  Returns (pairs/s, pairs, seconds)."""
+    per core with cv2.setNumThreads(1).  Returns (pairs/s, pairs, seconds, records in pair order)."""
     import multiprocessing as mp
     nproc = max(1, min(nproc, pairs_total))
     per = pairs_total // nproc
@@ -132,7 +183,8 @@ def cpu_reference_throughput(frames_host, nfeatures, pairs_total, nproc):
         res = pool.map(_cpu_worker, jobs)
         dt = time.perf_counter() - t0
     pairs = sum(r[0] for r in res)
-    return pairs / dt, pairs, dt
+    recs = [x for r in res for x in r[2]]
+    return pairs / dt, pairs, dt, recs
 
 
 def run_reference(args):
@@ -150,8 +202,9 @@ def run_reference(args):
     frames = synth.render_frames(W_IMG, H_IMG, R_wc[:nfr], C_w[:nfr], tex, device="cpu").numpy()
     pairs = min(pairs, nfr - 1)
     vals = []
+    recs = []
     for i in range(args.warmup + args.steps):
-        v, n, dt = cpu_reference_throughput(frames, args.features, pairs, ncpu)
+        v, n, dt, recs = cpu_reference_throughput(frames, args.features, pairs, ncpu)
         if i >= args.warmup:
             vals.append((v, n, dt))
     v = float(np.mean([x[0] for x in vals]))
@@ -164,7 +217,8 @@ def run_reference(args):
             "dtype": "u8/f64", "data": "synthetic",
             "config": {"workload": "%d-frame synthetic KITTI-shaped sequence %dx%d, %d ORB features (bounded sample)" % (args.frames, W_IMG, H_IMG, args.features)},
             "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": min(ncpu, pairs), "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "result_check": {"vs_ground_truth_pairs": pair_errors(recs, R_wc, C_w)}}
     emit(line)
     return 0
 
@@ -179,8 +233,7 @@ class DevView:
 
 def bind_to_gpu_numa_node(index):
     """Pin this rank to the CPU cores NVML reports as local to its GPU BEFORE the pinned frame buffer is
-    allocated (first touch decides the NUMA node): with eight ranks uploading 467 MB per step each, host
-    memory on the wrong socket makes the e2e path PCIe/UPI-bound.  Best effort; silently skipped."""
+    allocated (first touch decides the NUMA node).  Best effort; returns (cpus bound, cpus NVML named)."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -193,13 +246,13 @@ def bind_to_gpu_numa_node(index):
             h = pynvml.nvmlDeviceGetHandleByIndex(index)
         words = (os.cpu_count() + 63) // 64
         mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
-        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
-        cpus &= set(os.sched_getaffinity(0))
+        named = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus = named & set(os.sched_getaffinity(0))
         if cpus:
             os.sched_setaffinity(0, cpus)
-        return len(cpus)
+        return len(cpus), len(named)
     except Exception:
-        return 0
+        return 0, 0
 
 
 def algorithmic_bytes(ctx, nfeatures):
@@ -214,18 +267,196 @@ def algorithmic_bytes(ctx, nfeatures):
     }
 
 
-def accuracy(traj, R_gt, C_gt):
-    """Chained trajectory against the ground truth of the synthetic sequence: similarity-aligned ATE
-    (the reference applies a fixed 0.3 step scale) and mean relative rotation / translation-direction
-    error per pair.  Frame 0 is the identity pose the chain starts from."""
-    from b200vo import trajectory as T
-    poses = np.concatenate([np.concatenate([np.eye(3).ravel(), np.zeros(3)])[None], np.asarray(traj)], 0)
-    n = len(poses)
-    # ground truth relative to its own first frame (the estimate starts at identity)
-    R0, C0 = R_gt[0], C_gt[0]
-    Rg = np.stack([R0.T @ R for R in R_gt[:n]])
-    Cg = np.stack([R0.T @ (C - C0) for C in C_gt[:n]])
-    return {"vs_ground_truth": T.accuracy_report(poses, Rg, Cg)}
+class SeqRunner:
+    """One rank's share of a sequence through the C ABI: frames [0, F) of `d_frames` (device) / `h_frames`
+    (pinned host) in launch batches of B frames; pair ids start at pair0.  Records land in self.recs_dev."""
+
+    def __init__(self, torch, b200vo, W, H, NF, hyp, B, local, d_frames, h_frames, pair0, **opts):
+        self.torch, self.b = torch, b200vo
+        self.W, self.H, self.F, self.B = W, H, int(d_frames.shape[0]), max(2, min(B, int(d_frames.shape[0])))
+        self.npairs = self.F - 1
+        self.pair0 = pair0
+        self.dev = "cuda:%d" % local
+        self.d_frames, self.h_frames = d_frames, h_frames
+        self.ctx = b200vo.Context(W, H, device=local, nfeatures=NF, max_frames=self.B + 1, ransac_hypotheses=hyp, **opts)
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream(), device=torch.device("cuda", local))
+        self.RB = b200vo.RECORD_BYTES
+        self.recs_dev = torch.zeros(max(self.npairs, 1) * self.RB, dtype=torch.uint8, device=self.dev)
+        self.fb = W * H
+
+    def batches(self, short_first=False):
+        """(first slot, frames in the batch, frames done before, first pair slot, pairs, pairs done before)"""
+        B, F = self.B, self.F
+        done_f, done_p, prev = 0, 0, 0
+        while done_f < F:
+            n = min(B, F - done_f)
+            if short_first and done_f == 0:
+                n = min(n, max(B // 5, 2))      # e2e: a short first batch, so only its H2D copy is not hidden behind compute
+            first = 0 if done_f == 0 else (prev + 1) % (B + 1)
+            p0, np_ = (first, n - 1) if done_f == 0 else (prev, n)
+            yield first, n, done_f, p0, np_, done_p
+            prev = (first + n - 1) % (B + 1)
+            done_f += n
+            done_p += np_
+
+    def step(self, host_input):
+        torch, ctx = self.torch, self.ctx
+        for first, n, done_f, p0, np_, done_p in self.batches(short_first=host_input):
+            if host_input:
+                ctx.upload_frames_ptr(self.h_frames.data_ptr() + done_f * self.fb, n, self.W, self.fb, 1, first)
+            else:
+                ctx.upload_frames_device(self.d_frames.data_ptr() + done_f * self.fb, n, self.W, self.fb, 1, first)
+            ctx.detect(first, n)
+            if np_ > 0:
+                ptr = ctx.process_pairs_device(p0, np_, self.pair0 + done_p)
+                with torch.cuda.stream(self.stream):
+                    src = torch.as_tensor(DevView(ptr, np_ * self.RB), device=self.dev)
+                    self.recs_dev[done_p * self.RB:(done_p + np_) * self.RB].copy_(src, non_blocking=True)
+
+    def close(self):
+        self.stream.synchronize()
+        self.stream = None
+        self.recs_dev = None
+        self.d_frames = self.h_frames = None
+        self.ctx.close()
+
+
+def timed_steps(torch, dist, world, runner_stream, fn, steps, warmup, dev, launches_of=None):
+    """warm-up, barrier + synchronize, CUDA events on the launching stream around exactly `steps` calls,
+    barrier + synchronize, MAX over ranks.  Returns (ms per step, wall s per step, kernel launches)."""
+    for _ in range(warmup):
+        fn()
+    runner_stream.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = launches_of.kernel_launches() if launches_of is not None else 0
+    t0 = time.perf_counter()
+    e0.record(runner_stream)
+    for _ in range(steps):
+        fn()
+    e1.record(runner_stream)
+    runner_stream.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps, wall / steps, (launches_of.kernel_launches() - l0) if launches_of is not None else 0
+
+
+def render(torch, synth, W, H, R, C, tex, dev, chunk):
+    d = synth.render_frames(W, H, R, C, tex, device=dev, chunk=chunk)
+    h = torch.empty(tuple(d.shape), dtype=torch.uint8, pin_memory=True)
+    h.copy_(d)
+    torch.cuda.synchronize()
+    return d, h
+
+
+def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, F, rank, world, local, steps, warmup):
+    """ONE F-frame sequence partitioned over the ranks by contiguous frame-pair ranges (b200vo/sequence.py), one
+    all_gather of the records; then the same sequence on rank 0 alone.  Returns the leg's JSON object (rank 0)."""
+    from b200vo import sequence as SQ
+    dev = "cuda:%d" % local
+    RB = b200vo.RECORD_BYTES
+    P = F - 1
+    R_all, C_all = synth.make_trajectory(F)
+    lo, hi = SQ.partition_pairs(P, world, rank)
+    f0, f1 = SQ.frames_for_pairs(lo, hi)
+    chunk = max(1, (32 * 1241 * 376) // (W * H))
+    d_fr, h_fr = render(torch, synth, W, H, R_all[f0:f1], C_all[f0:f1], tex, dev, chunk)
+    run = SeqRunner(torch, b200vo, W, H, NF, hyp, B, local, d_fr, h_fr, lo)
+    per = -(-P // world)
+    send = torch.zeros(per * RB, dtype=torch.uint8, device=dev)
+    gath = torch.zeros(world * per * RB, dtype=torch.uint8, device=dev) if world > 1 else send
+    host = torch.empty(world * per * RB, dtype=torch.uint8, pin_memory=True)
+
+    def step(host_input):
+        run.step(host_input)
+        with torch.cuda.stream(run.stream):
+            send[:(hi - lo) * RB].copy_(run.recs_dev[:(hi - lo) * RB], non_blocking=True)
+            if world > 1:
+                dist.all_gather_into_tensor(gath, send)
+            if host_input:
+                host.copy_(gath, non_blocking=True)
+        if host_input:
+            run.stream.synchronize()
+
+    ms_dev, _, launches = timed_steps(torch, dist, world, run.stream, lambda: step(False), steps, warmup, dev, run.ctx)
+    ms_e2e, _, _ = timed_steps(torch, dist, world, run.stream, lambda: step(True), steps, warmup, dev)
+    out, recs = None, None
+    if rank == 0:
+        allb = host.numpy().view(b200vo.POSE_RECORD_DTYPE).reshape(world, per)
+        recs = np.concatenate([allb[r, :SQ.partition_pairs(P, world, r)[1] - SQ.partition_pairs(P, world, r)[0]] for r in range(world)]).copy()
+        del allb
+        out = {"workload": "%s: ONE %d-frame %dx%d sequence, %d features, %d hypotheses/pair, launch batches of %d frames, partitioned over %d GPU(s) by contiguous frame-pair ranges" % (name, F, W, H, NF, hyp, run.B, world),
+               "pairs": P, "scaling": "strong", "value": round(P / (ms_dev * 1e-3), 1), "e2e": round(P / (ms_e2e * 1e-3), 1), "unit": "pairs/s",
+               "ms_per_step": round(ms_dev, 3), "e2e_ms_per_step": round(ms_e2e, 3), "steps": steps, "warmup": warmup,
+               "h2d_bytes_per_step": (P + world) * W * H, "d2h_bytes_per_step": world * per * RB,
+               "boundary_frames_detected_twice": world - 1, "boundary_overhead_frac": round((world - 1) / float(P + 1), 5),
+               "gpu_launches": int(launches) * world,
+               "pairs_pose_ok": int(((recs["status"] & 4) != 0).sum()), "pairs_overflow": int(((recs["status"] & 256) != 0).sum()),
+               "vs_ground_truth_pairs": pair_errors(recs, R_all, C_all)}
+    run.close()
+    del d_fr, h_fr, send, gath
+    # the same sequence on ONE GPU (rank 0; the other ranks wait): denominator of the strong-scaling efficiency and
+    # the byte-identity check of the partition
+    if world > 1:
+        if rank == 0:
+            d_all, h_all = render(torch, synth, W, H, R_all, C_all, tex, dev, chunk)
+            solo = SeqRunner(torch, b200vo, W, H, NF, hyp, B, local, d_all, h_all, 0)
+            ms1, _, _ = timed_steps(torch, None, 1, solo.stream, lambda: solo.step(False), steps, warmup, dev)
+            host1 = torch.empty(P * RB, dtype=torch.uint8, pin_memory=True)
+
+            def e2e1():
+                solo.step(True)
+                with torch.cuda.stream(solo.stream):
+                    host1.copy_(solo.recs_dev[:P * RB], non_blocking=True)
+                solo.stream.synchronize()
+            ms1e, _, _ = timed_steps(torch, None, 1, solo.stream, e2e1, steps, warmup, dev)
+            recs1 = host1.numpy().view(b200vo.POSE_RECORD_DTYPE).copy()
+            out["single_gpu"] = {"value": round(P / (ms1 * 1e-3), 1), "e2e": round(P / (ms1e * 1e-3), 1), "ms_per_step": round(ms1, 3)}
+            out["efficiency_vs_single_gpu"] = {"value": round(ms1 / (world * ms_dev), 4), "e2e": round(ms1e / (world * ms_e2e), 4)}
+            out["records_identical_to_single_gpu"] = bool(recs1.tobytes() == recs.tobytes())
+            solo.close()
+            del d_all, h_all, host1
+        dist.barrier()
+    del host
+    return out
+
+
+def streaming_leg(b200vo, frames_host, nfeatures, nframes):
+    """The reference's real calling pattern (src/main.cpp:155): VisualOdometry::process_frame once per frame,
+    host image in, keypoints / descriptors / pose out, through the C++ class in libb200vo_host.so."""
+    lib = ctypes.CDLL(b200vo.HOST_LIB_PATH)
+    lib.vo_host_create.restype = ctypes.c_void_p
+    lib.vo_host_last_error.restype = ctypes.c_char_p
+    lib.vo_host_destroy.argtypes = [ctypes.c_void_p]
+    H, W = frames_host.shape[1:3]
+    h = lib.vo_host_create(W, H, nfeatures, 0, ctypes.c_ulonglong(42), 0, 0)
+    if not h:
+        return {"error": lib.vo_host_last_error().decode()}
+    h = ctypes.c_void_p(h)
+    pose = np.zeros(12)
+    moved = ctypes.c_int()
+    t = []
+    for i in range(nframes):
+        f = np.ascontiguousarray(frames_host[i])
+        t0 = time.perf_counter()
+        rc = lib.vo_host_process_frame(h, i, f.ctypes.data_as(ctypes.c_void_p), W, H, 1, pose.ctypes.data_as(ctypes.c_void_p), ctypes.byref(moved))
+        t.append(time.perf_counter() - t0)
+        if rc <= 0:
+            lib.vo_host_destroy(h)
+            return {"error": lib.vo_host_last_error().decode()}
+    lib.vo_host_destroy(h)
+    t = np.array(t[10:])
+    return {"frames": int(len(t)), "frames_per_s": round(1.0 / float(t.mean()), 1), "ms_per_frame_mean": round(float(t.mean()) * 1e3, 4),
+            "ms_per_frame_p50": round(float(np.median(t)) * 1e3, 4), "ms_per_frame_p99": round(float(np.percentile(t, 99)) * 1e3, 4)}
 
 
 def run_b200(args):
@@ -238,162 +469,169 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    bind_to_gpu_numa_node(local)
+    dev = "cuda:%d" % local
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     F, NF, B = args.frames, args.features, min(args.batch, args.frames)
     npairs = F - 1
+    RB = b200vo.RECORD_BYTES
     # global sequence: rank r owns pairs [r*(F-1), (r+1)*(F-1)) -> frames [r*(F-1), r*(F-1)+F)
     tex = synth.make_texture()
     R_all, C_all = synth.make_trajectory(world * npairs + 1)
     f0 = rank * npairs
-    d_frames = synth.render_frames(W_IMG, H_IMG, R_all[f0:f0 + F], C_all[f0:f0 + F], tex, device="cuda:%d" % local, chunk=32)
-    h_frames = torch.empty((F, H_IMG, W_IMG), dtype=torch.uint8, pin_memory=True)
-    h_frames.copy_(d_frames)
-    torch.cuda.synchronize()
-
-    ctx = b200vo.Context(W_IMG, H_IMG, device=local, nfeatures=NF, max_frames=B + 1, ransac_hypotheses=args.hypotheses)
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    RB = b200vo.RECORD_BYTES
-    recs_dev = torch.zeros(npairs * RB, dtype=torch.uint8, device="cuda:%d" % local)
-    recs_all = torch.zeros(world * npairs * RB, dtype=torch.uint8, device="cuda:%d" % local) if world > 1 else recs_dev
-    recs_host = torch.empty(world * npairs * RB, dtype=torch.uint8, pin_memory=True)
+    d_frames, h_frames = render(torch, synth, W_IMG, H_IMG, R_all[f0:f0 + F], C_all[f0:f0 + F], tex, dev, 32)
     frame_bytes = W_IMG * H_IMG
+
+    run = SeqRunner(torch, b200vo, W_IMG, H_IMG, NF, args.hypotheses, B, local, d_frames, h_frames, f0)
+    ctx, stream = run.ctx, run.stream
+    gathered = {"t": torch.zeros(world * npairs * RB, dtype=torch.uint8, device=dev) if world > 1 else None}
+    recs_host = torch.empty(world * npairs * RB, dtype=torch.uint8, pin_memory=True)
     state = {"traj": None}
 
-    def step(host_input):
-        done_frames, done_pairs, prev_slot = 0, 0, 0
-        while done_frames < F:
-            n = min(B, F - done_frames)
-            if host_input and done_frames == 0:
-                n = min(n, max(B // 5, 2))      # e2e: a short first batch, so only its H2D copy is not hidden behind compute
-            first = 0 if done_frames == 0 else (prev_slot + 1) % (B + 1)
+    def make_step(r, host_input):
+        def fn():
+            r.step(host_input)
+            with torch.cuda.stream(r.stream):
+                if world > 1:
+                    dist.all_gather_into_tensor(gathered["t"], r.recs_dev)     # the one exchange step: 160 B per pair
+                if host_input:
+                    recs_host.copy_(gathered["t"] if world > 1 else r.recs_dev, non_blocking=True)
             if host_input:
-                ctx.upload_frames_ptr(h_frames.data_ptr() + done_frames * frame_bytes, n, W_IMG, frame_bytes, 1, first)
-            else:
-                ctx.upload_frames_device(d_frames.data_ptr() + done_frames * frame_bytes, n, W_IMG, frame_bytes, 1, first)
-            ctx.detect(first, n)
-            if done_frames == 0:
-                p0, np_ = first, n - 1
-            else:
-                p0, np_ = prev_slot, n
-            if np_ > 0:
-                ptr = ctx.process_pairs_device(p0, np_, f0 + done_pairs)
-                with torch.cuda.stream(stream):
-                    src = torch.as_tensor(DevView(ptr, np_ * RB), device="cuda:%d" % local)
-                    recs_dev[done_pairs * RB:(done_pairs + np_) * RB].copy_(src, non_blocking=True)
-            prev_slot = (first + n - 1) % (B + 1)
-            done_frames += n
-            done_pairs += np_
-        with torch.cuda.stream(stream):
-            if world > 1:
-                dist.all_gather_into_tensor(recs_all, recs_dev)     # the one exchange step: 160 B per pair
-            if host_input:
-                recs_host.copy_(recs_all, non_blocking=True)
-        if host_input:
-            stream.synchronize()
-            if rank == 0:   # host-side chaining of the whole trajectory (reference visual_odometry.cpp:340-374)
-                state["traj"] = b200vo.chain_trajectory(recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy())
-
-    def timed(host_input, steps, warmup):
-        for _ in range(warmup):
-            step(host_input)
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ctx.kernel_launches()
-        t0 = time.perf_counter()
-        e0.record(stream)
-        for _ in range(steps):
-            step(host_input)
-        e1.record(stream)
-        stream.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda:%d" % local)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps, wall / steps, ctx.kernel_launches() - l0
+                r.stream.synchronize()
+                if rank == 0:   # host-side chaining of the whole trajectory (reference visual_odometry.cpp:340-374)
+                    state["traj"] = b200vo.chain_trajectory(recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy())
+        return fn
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, wall_dev, launches = timed(False, args.steps, args.warmup)
-    ms_e2e, wall_e2e, _ = timed(True, args.steps, max(args.warmup, 3))
+    ms_dev, wall_dev, launches = timed_steps(torch, dist, world, stream, make_step(run, False), args.steps, args.warmup, dev, ctx)
+    ms_e2e, wall_e2e, _ = timed_steps(torch, dist, world, stream, make_step(run, True), args.steps, max(args.warmup, 3), dev)
     clocks = sampler.stop() if rank == 0 else None
+    ok = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy() if rank == 0 else None
+    traj = state["traj"]
 
-    # ---- extra: the same workload with OpenCV's adaptive RANSAC stopping rule (ransac_adaptive=1),
-    # i.e. what the reference's findEssentialMat does; reported beside the fixed-H headline, not as it
-    main_ctx = ctx
-    ctx = b200vo.Context(W_IMG, H_IMG, device=local, nfeatures=NF, max_frames=B + 1, ransac_hypotheses=args.hypotheses, ransac_adaptive=1)
-    stream_main = stream
-    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
-    ms_dev_ad, _, _ = timed(False, args.steps, args.warmup)
-    ms_e2e_ad, _, _ = timed(True, args.steps, max(args.warmup, 3))
-    rounds_ad = None
-    if rank == 0:
-        rr = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy()
-        rounds_ad = float((((rr["status"] >> 16) & 0xFF) * 128).mean())
-        del rr
-    stream.synchronize()
-    ad_ctx, ad_stream = ctx, stream          # closed at teardown, after the tensors that touched its stream
-    ctx, stream = main_ctx, stream_main
-    step(True)                      # restore the fixed-H records / trajectory for the result check
-    stream.synchronize()
+    # ---- per-rank upload bandwidth: (a) what the e2e leg achieved, (b) a plain pinned -> device copy of the same frames with all
+    # ranks copying at the same time (the ceiling the host's PCIe / memory system gives this box)
+    probe_dst = torch.empty_like(d_frames)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0.record()
+    for _ in range(3):
+        probe_dst.copy_(h_frames, non_blocking=True)
+    pe1.record()
+    torch.cuda.synchronize()
+    h2d_vals = torch.tensor([F * frame_bytes / (ms_e2e * 1e-3) / 1e9, 3 * F * frame_bytes / (pe0.elapsed_time(pe1) * 1e-3) / 1e9,
+                             float(numa[0]), float(numa[1])], device=dev, dtype=torch.float64)
+    h2d_all = [torch.zeros_like(h2d_vals) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(h2d_all, h2d_vals)
+    else:
+        h2d_all = [h2d_vals]
+    h2d = {"e2e_GBps_per_rank": [round(float(v[0]), 2) for v in h2d_all], "plain_pinned_copy_GBps_per_rank_concurrent": [round(float(v[1]), 2) for v in h2d_all],
+           "cpus_bound_per_rank": [int(v[2]) for v in h2d_all], "cpus_nvml_affinity_per_rank": [int(v[3]) for v in h2d_all],
+           "note": "e2e: frame bytes of a rank / its e2e step time (the copy is overlapped with compute, so this is a lower bound of the copy rate); plain: 3 back-to-back pinned->device copies of the same frames, all ranks at once"}
+    del probe_dst, h2d_all, h2d_vals
 
-    # ---- per-stage breakdown (separate instrumented pass; timing mode synchronises per call)
-    stage = {}
+    # ---- per-stage breakdown (separate instrumented pass; timing mode synchronises per call) + keypoints per frame
+    stage, kp_counts = {}, []
     if rank == 0:
         ctx.enable_timing(True)
-        tot = {}
-        done_frames, done_pairs, prev_slot = 0, 0, 0
-        while done_frames < F:
-            n = min(B, F - done_frames)
-            first = 0 if done_frames == 0 else (prev_slot + 1) % (B + 1)
-            ctx.upload_frames_device(d_frames.data_ptr() + done_frames * frame_bytes, n, W_IMG, frame_bytes, 1, first)
+        for first, n, done_f, p0, np_, done_p in run.batches():
+            ctx.upload_frames_device(d_frames.data_ptr() + done_f * frame_bytes, n, W_IMG, frame_bytes, 1, first)
             ctx.detect(first, n)
             st = ctx.stage_times()
-            for k in ("pyramid_ms", "fast_ms", "select_ms", "orient_ms", "blur_ms", "brief_ms"):
-                tot[k] = tot.get(k, 0.0) + st[k]
-            p0, np_ = (first, n - 1) if done_frames == 0 else (prev_slot, n)
+            for k in ("pyramid_ms", "fast_ms", "select_ms", "orient_ms", "blur_ms", "brief_ms", "describe_ms"):
+                stage[k] = stage.get(k, 0.0) + st[k]
             if np_ > 0:
-                ctx.process_pairs_device(p0, np_, f0 + done_pairs)
-                done_pairs += np_
+                ctx.process_pairs_device(p0, np_, f0 + done_p)
                 st = ctx.stage_times()
                 for k in ("match_ms", "filter_ms", "ransac_ms", "pose_ms", "fivept_ms", "score_ms"):
-                    tot[k] = tot.get(k, 0.0) + st[k]
-            prev_slot = (first + n - 1) % (B + 1)
-            done_frames += n
+                    stage[k] = stage.get(k, 0.0) + st[k]
+            for s in range(first, first + n, max(1, n // 64)):           # a sample of the batch's slots
+                try:
+                    kp_counts.append(ctx.feature_count(s % (run.B + 1)))
+                except b200vo.B200VOError:
+                    kp_counts.append(-1)
         ctx.enable_timing(False)
-        stage = tot
+    popc_rate = ctx.measure_popc_rate() if rank == 0 else 0.0
+    alg = algorithmic_bytes(ctx, NF) if rank == 0 else None
+
+    # ---- CPU baseline on rank 0 at N=1: bounded sample of the same frames (the first 8 x cores pairs)
+    cpu, cpu_acc = None, None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            ncpu = os.cpu_count() or 1
+            pairs = ncpu * (args.cpu_pairs or 8)
+            fr = h_frames[:min(F, pairs + 1)].numpy().copy()      # a copy: no view may outlive the pinned tensor
+            v, n, dt, crecs = cpu_reference_throughput(fr, NF, min(pairs, len(fr) - 1), ncpu)
+            import cv2
+            cpu = {"value": round(v, 2), "unit": "pairs/s", "cores": min(ncpu, n), "kind": "port",
+                   "sample": "%d pairs of the same frames, %d processes x cv2.setNumThreads(1) (cv2 %s calling the reference's OpenCV functions), %.1f s" % (n, min(ncpu, n), cv2.__version__, dt)}
+            cpu_acc = {"pairs_sampled": n, "cv2_reference_path": pair_errors(crecs, R_all, C_all, f0), "this_path_same_pairs": pair_errors(ok[:n], R_all, C_all, f0)}
+            del fr
+        except Exception as ex:      # the CPU leg must never take the GPU numbers down with it
+            cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
+
+    # ---- release the headline runner before the extra legs allocate
+    run.close()
+    gathered["t"] = None
+    del d_frames
+    extras = {}
+    if not args.no_extras:
+        # the same workload with OpenCV's adaptive RANSAC stopping rule (what the reference's findEssentialMat does);
+        # reported beside the fixed-H headline, not as it
+        d2 = torch.empty((F, H_IMG, W_IMG), dtype=torch.uint8, device=dev)
+        d2.copy_(h_frames)
+        ad = SeqRunner(torch, b200vo, W_IMG, H_IMG, NF, args.hypotheses, B, local, d2, h_frames, f0, ransac_adaptive=1)
+        if world > 1:
+            gathered["t"] = torch.zeros(world * npairs * RB, dtype=torch.uint8, device=dev)
+        ms_dev_ad, _, _ = timed_steps(torch, dist, world, ad.stream, make_step(ad, False), args.steps, args.warmup, dev)
+        ms_e2e_ad, _, _ = timed_steps(torch, dist, world, ad.stream, make_step(ad, True), args.steps, max(args.warmup, 3), dev)
+        if rank == 0:
+            rr = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy()
+            extras["adaptive_ransac"] = {"note": "same workload with ransac_adaptive=1 (OpenCV confidence-0.999 stopping rule, checked every 128 hypotheses)",
+                                         "value": round(world * npairs / (ms_dev_ad * 1e-3), 1), "e2e": round(world * npairs / (ms_e2e_ad * 1e-3), 1),
+                                         "mean_hypotheses_per_pair": float((((rr["status"] >> 16) & 0xFF) * 128).mean())}
+            del rr
+        ad.close()
+        gathered["t"] = None
+        del d2
+        if rank == 0:
+            fr = h_frames[:min(F, 210)].numpy().copy()
+            extras["streaming"] = {"api": "VisualOdometry::process_frame per frame through libb200vo_host.so (host image in, keypoints + descriptors + pose out, one synchronisation per frame)",
+                                   "features_1200": streaming_leg(b200vo, fr, 1200, len(fr)), "features_3000": streaming_leg(b200vo, fr, 3000, len(fr))}
+            del fr
+        if world > 1:
+            dist.barrier()
+        ls, lw = max(2, min(args.steps, 3)), 1
+        extras["config3"] = strong_scaling_leg(torch, dist, b200vo, synth, tex, "BASELINE configs[2]", 1920, 1080, 8000, 1024, 64, args.c3_frames, rank, world, local, ls, lw)
+        extras["config5"] = strong_scaling_leg(torch, dist, b200vo, synth, tex, "BASELINE configs[4]", 3840, 2160, 20000, 4096, 16, args.c5_frames, rank, world, local, ls, lw)
 
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        del recs_dev, recs_all, d_frames, recs_host, h_frames, stream, ad_stream, stream_main
+        del recs_host, h_frames
         import gc
         gc.collect()
         torch.cuda.synchronize()
         torch.cuda.empty_cache()
-        ad_ctx.close()
-        ctx.close()
         return 0
 
     hbm_peak, peak_src = peaks()
-    popc_rate = ctx.measure_popc_rate()
-    alg = algorithmic_bytes(ctx, NF)
     stages_out = {}
-    for name, key in (("pyramid", "pyramid_ms"), ("fast", "fast_ms"), ("blur", "blur_ms"), ("brief", "brief_ms"), ("orient", "orient_ms")):
+    fused = stage.get("describe_ms", 0.0) > 0
+    rows = [("pyramid", "pyramid_ms", "pyramid"), ("fast", "fast_ms", "fast"), ("blur", "blur_ms", "blur")]
+    rows += [("describe", "describe_ms", None)] if fused else [("brief", "brief_ms", "brief"), ("orient", "orient_ms", "orient")]
+    for name, key, algk in rows:
         ms = stage.get(key, 0.0)
-        gbs = alg[name] * F / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        stages_out[name] = {"ms": round(ms, 3), "bound": "hbm", "algorithmic_bytes_per_frame": alg[name], "achieved_GBps": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)}
+        ab = alg[algk] if algk else alg["orient"] + 32 * NF + 39 * 39 * NF        # fused: disc + pattern window + descriptor per keypoint
+        gbs = ab * F / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stages_out[name] = {"ms": round(ms, 3), "bound": "hbm", "algorithmic_bytes_per_frame": ab, "achieved_GBps": round(gbs, 1), "frac": round(gbs / hbm_peak, 4)}
     # matcher: N1*N2 descriptor pairs; algorithmically 8 popc32 each.  The kernel executes 5 (three
     # carry-save adders move the rest onto the LOP3 pipe), so the POPC-pipe roofline is taken on the
     # EXECUTED population counts against the rate measured by the XOR+POPC+ADD microbenchmark.
@@ -406,16 +644,14 @@ def run_b200(args):
                            "frac": round(popc_exec / popc_rate, 4), "descriptor_pairs_per_s": round(kp_pairs / (mm * 1e-3), 0) if mm > 0 else 0}
     for name in ("select", "filter", "ransac", "pose", "fivept", "score"):
         stages_out[name] = {"ms": round(stage.get(name + "_ms", 0.0), 3)}
-    # FP64 work of the scoring kernel: models x points x ~20 DFMA against 64 DFMA/clk/SM
     kernels = {k: v for k, v in stage.items() if k not in ("ransac_ms",)}
     total_stage_ms = sum(kernels.values())
     dom = max(kernels, key=kernels.get) if kernels else "match_ms"
     if dom == "match_ms":
         roof = {"kernel": "match_kernel<4,%d>" % int(os.environ.get("B200VO_MATCH_CSA", "3")), "bound": "int_pipe", "achieved": round(popc_exec / 1e9, 1), "peak": round(popc_rate / 1e9, 1),
                 "unit": "Gpopc32/s", "frac": round(popc_exec / popc_rate, 4),
-                # dram__bytes_read.sum + dram__bytes_write.sum of one launch (500-frame batch) from the ncu --set full
-                # capture profiles/ncu_r01_match_fullconfig.txt; algorithmic: 500 x 3001 x 32 B = 48 MB with every
-                # descriptor read once (each slot is the query side of one pair and the train side of the next)
+                # algorithmic: 500 x 3001 x 32 B = 48 MB with every descriptor read once (each slot is the query side of one pair and the
+                # train side of the next)
                 "traffic": MATCH_DRAM_BYTES_PER_LAUNCH if (F, NF, B) == (1000, 3000, 500) else None, "traffic_unit": "bytes/launch",
                 "peak_source": "XOR+POPC+ADD microbenchmark measured in this run (b200vo_measure_popc_rate); not an HBM- or tensor-bound kernel "
                                "(63 MB of DRAM traffic per 5.6 ms launch)",
@@ -425,29 +661,22 @@ def run_b200(args):
         sdict = stages_out.get(nm, {})
         roof = {"kernel": nm, "bound": sdict.get("bound", "issue"), "achieved": sdict.get("achieved_GBps"), "peak": hbm_peak, "unit": "GB/s",
                 "frac": sdict.get("frac"), "traffic": None, "peak_source": peak_src, "share_of_step": round(stage[dom] / total_stage_ms, 3)}
-    hb = max(("pyramid", "fast", "blur", "brief"), key=lambda n: stages_out[n]["ms"])
+    hb = max((n for n in ("pyramid", "fast", "blur", "brief", "describe") if n in stages_out), key=lambda n: stages_out[n]["ms"])
     roof_hbm = {"kernel": hb, "bound": "hbm", "achieved": stages_out[hb]["achieved_GBps"], "peak": hbm_peak, "unit": "GB/s",
                 "frac": stages_out[hb]["frac"], "traffic": None, "peak_source": peak_src}
 
     total_pairs = world * npairs
     value = total_pairs / (ms_dev * 1e-3)
     e2e = total_pairs / (ms_e2e * 1e-3)
-
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        try:
-            ncpu = os.cpu_count() or 1
-            pairs = ncpu * (args.cpu_pairs or 8)
-            fr = h_frames[:min(F, pairs + 1)].numpy().copy()      # a copy: no view may outlive the pinned tensor
-            v, n, dt = cpu_reference_throughput(fr, NF, min(pairs, len(fr) - 1), ncpu)
-            import cv2
-            cpu = {"value": round(v, 2), "unit": "pairs/s", "cores": min(ncpu, n), "kind": "port",
-                   "sample": "%d pairs of the same frames, %d processes x cv2.setNumThreads(1) (cv2 %s calling the reference's OpenCV functions), %.1f s" % (n, min(ncpu, n), cv2.__version__, dt)}
-        except Exception as ex:      # the CPU leg must never take the GPU numbers down with it
-            cpu = {"value": None, "unit": "pairs/s", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
-
-    traj = state["traj"]
-    ok = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy()
+    kc = [c for c in kp_counts if c >= 0]
+    found = (ok["status"] & 2) != 0
+    result_check = {"pairs_pose_ok": int(((ok["status"] & 4) != 0).sum()), "pairs_overflow": int(((ok["status"] & 256) != 0).sum()), "pairs_total": int(len(ok)),
+                    "trajectory_end": [round(float(x), 3) for x in traj[-1][9:12]] if traj is not None else None,
+                    "mean_epipolar_residual": float(ok["epi_residual"][found].mean()) if found.any() else None,
+                    "vs_ground_truth": accuracy(traj, R_all, C_all) if traj is not None else None,
+                    "vs_ground_truth_pairs": pair_errors(ok, R_all, C_all)}
+    if cpu_acc:
+        result_check["same_pairs_as_cpu_baseline"] = cpu_acc
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_dev, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -460,27 +689,23 @@ def run_b200(args):
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
         "roofline": roof, "roofline_hbm": roof_hbm, "stages": stages_out,
-        "adaptive_ransac": {"note": "same workload with ransac_adaptive=1 (OpenCV confidence-0.999 stopping rule, checked every 128 hypotheses)",
-                            "value": round(total_pairs / (ms_dev_ad * 1e-3), 1), "e2e": round(total_pairs / (ms_e2e_ad * 1e-3), 1),
-                            "mean_hypotheses_per_pair": rounds_ad},
+        "keypoints_per_frame": {"mean": round(float(np.mean(kc)), 1) if kc else None, "min": int(min(kc)) if kc else None, "frames_sampled": len(kp_counts), "nfeatures": NF},
+        "h2d": h2d,
         "cpu_baseline": cpu,
-        "result_check": dict({"pairs_pose_ok": int(((ok["status"] & 4) != 0).sum()), "pairs_total": int(len(ok)),
-                              "trajectory_end": [round(float(x), 3) for x in traj[-1][9:12]] if traj is not None else None},
-                             **(accuracy(traj, R_all, C_all) if traj is not None else {})),
+        "result_check": result_check,
         "wall_ms_per_step": round(wall_dev * 1e3, 3),
     }
+    line.update(extras)
     emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    # torch tensors that were used on the context's stream must be released before the stream dies
-    del recs_dev, recs_all, d_frames, recs_host, h_frames, ok, stream, ad_stream, stream_main
+    # every context is closed (SeqRunner.close); release the last torch tensors and leave through the normal interpreter exit
+    del recs_host, h_frames, ok
     import gc
     gc.collect()
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
-    ad_ctx.close()
-    ctx.close()
     return 0
 
 

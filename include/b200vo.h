@@ -138,6 +138,8 @@ typedef struct b200vo_stage_times {
     float match_ms, filter_ms, ransac_ms, pose_ms, download_ms;
     /* kernels inside ransac_ms (fixed-H mode: one launch each): five-point solver, Sampson scoring */
     float fivept_ms, score_ms;
+    /* fused orientation + keypoint record + rBRIEF kernel (then orient_ms = brief_ms = 0) */
+    float describe_ms;
 } b200vo_stage_times;
 
 int b200vo_abi_version(void);

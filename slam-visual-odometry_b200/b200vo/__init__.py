@@ -45,7 +45,7 @@ assert KEYPOINT_DTYPE.itemsize == 32 and DMATCH_DTYPE.itemsize == 16 and RECORD_
 class StageTimes(C.Structure):
     _fields_ = [(n, C.c_float) for n in ("upload_ms", "gray_ms", "pyramid_ms", "fast_ms", "select_ms", "orient_ms",
                                          "blur_ms", "brief_ms", "match_ms", "filter_ms", "ransac_ms", "pose_ms",
-                                         "download_ms", "fivept_ms", "score_ms")]
+                                         "download_ms", "fivept_ms", "score_ms", "describe_ms")]
 
 
 EXPORTS = [
@@ -209,6 +209,12 @@ class Context:
         n = C.c_int()
         self._chk(self.lib.b200vo_get_features(self.h, slot, _p(kp), _p(desc), self.kp_cap, C.byref(n)))
         return kp[:n.value].copy(), desc[:n.value].copy()
+
+    def feature_count(self, slot):
+        """Number of keypoints of a slot (no copy of the features)."""
+        n = C.c_int()
+        self._chk(self.lib.b200vo_get_features(self.h, slot, None, None, 0, C.byref(n)))
+        return n.value
 
     def set_features(self, slot, kp, desc):
         desc = np.ascontiguousarray(desc, np.uint8)

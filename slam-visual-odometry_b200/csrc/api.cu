@@ -299,6 +299,10 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         if (const char* v = getenv("B200VO_TMA")) ctx->use_tma = (atoi(v) != 0);
         ctx->match_csa = 3;
         ctx->filter_fast_cap = 1 << 30;
+        ctx->fpg_variant = 0;
+        ctx->fused_describe = ctx->use_tma;
+        if (const char* v = getenv("B200VO_DESCRIBE")) ctx->fused_describe = (atoi(v) != 0);
+        if (const char* v = getenv("B200VO_FPG")) ctx->fpg_variant = atoi(v);
         if (const char* v = getenv("B200VO_FILTER_FAST_CAP")) ctx->filter_fast_cap = atoi(v);
         if (const char* v = getenv("B200VO_MATCH_CSA")) { const int c = atoi(v); if (c >= 0 && c <= 3) ctx->match_csa = c; }
         void* fnp = nullptr;
@@ -309,6 +313,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_fast[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, fast_level_is_wide(l) ? kFastBoxWideW : kFastBoxW, kFastBoxH));
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_blur[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kBlurBoxW, kBlurBoxH));
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_resize[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kResizeBoxW, kResizeBoxH));
+            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_orient[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kOrientBoxW, kOrientBoxH));
+            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_brief[l], sv.blur, sv.lv[l], sv.slot_bytes, sv.slots, kBriefBoxW, kBriefBoxH));
         }
     }
     TRY(upload_brief_pattern());
@@ -456,13 +462,23 @@ int b200vo_detect(b200vo_ctx* ctx, int first_slot, int n) {
     if ((rc = launch_pyramid(ctx, first_slot, n))) return rc;  clk.mark();
     if ((rc = launch_fast(ctx, first_slot, n))) return rc;     clk.mark();
     if ((rc = launch_select(ctx, first_slot, n))) return rc;   clk.mark();
-    if ((rc = launch_orient(ctx, first_slot, n))) return rc;   clk.mark();
-    if ((rc = launch_blur(ctx, first_slot, n))) return rc;     clk.mark();
-    if ((rc = launch_brief(ctx, first_slot, n))) return rc;    clk.mark();
+    if (ctx->fused_describe) {
+        // blur first (it does not depend on the keypoints), then orientation + keypoint record + rBRIEF in one kernel
+        if ((rc = launch_blur(ctx, first_slot, n))) return rc;     clk.mark();
+        if ((rc = launch_describe(ctx, first_slot, n))) return rc; clk.mark();
+    } else {
+        if ((rc = launch_orient(ctx, first_slot, n))) return rc;   clk.mark();
+        if ((rc = launch_blur(ctx, first_slot, n))) return rc;     clk.mark();
+        if ((rc = launch_brief(ctx, first_slot, n))) return rc;    clk.mark();
+    }
     if (ctx->timing) {
         B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
         ctx->times.pyramid_ms = clk.ms(0); ctx->times.fast_ms = clk.ms(1); ctx->times.select_ms = clk.ms(2);
-        ctx->times.orient_ms = clk.ms(3); ctx->times.blur_ms = clk.ms(4); ctx->times.brief_ms = clk.ms(5);
+        if (ctx->fused_describe) {
+            ctx->times.blur_ms = clk.ms(3); ctx->times.describe_ms = clk.ms(4); ctx->times.orient_ms = ctx->times.brief_ms = 0.f;
+        } else {
+            ctx->times.orient_ms = clk.ms(3); ctx->times.blur_ms = clk.ms(4); ctx->times.brief_ms = clk.ms(5); ctx->times.describe_ms = 0.f;
+        }
     }
     return B200VO_OK;
 }

@@ -22,6 +22,9 @@ constexpr int kFastBoxWideW = 160;                 // fast.cu: the 134-pixel-wid
 inline bool fast_level_is_wide(int level) { return level <= 4; }
 constexpr int kBlurBoxW = 160, kBlurBoxH = 38;     // blur.cu: 128+2*16 x 32+6
 constexpr int kResizeBoxW = 176, kResizeBoxH = 24; // pyramid.cu: source footprint of a 128x16 output tile at scale ~1.2
+constexpr int kBriefReach = 19;                     // rotated pattern points stay within |coordinate| <= 18 (max pattern radius 18.38)
+constexpr int kOrientBoxW = 48, kOrientBoxH = 31;   // orient_brief.cu: 31-px disc row + up to 15 bytes of alignment shift, per keypoint
+constexpr int kBriefBoxW = 64, kBriefBoxH = 39;     // orient_brief.cu: (2*19+1)-px window + up to 15 bytes of alignment shift, per keypoint
 
 struct LevelGeom {
     int w, h, pitch;       // pitch: bytes per row, multiple of 128 (TMA needs 16)
@@ -153,8 +156,12 @@ struct b200vo_ctx {
     CUtensorMap tmap_fast[b200vo::kLevels];
     CUtensorMap tmap_blur[b200vo::kLevels];
     CUtensorMap tmap_resize[b200vo::kLevels];    // [l] = level l as the SOURCE of level l+1
+    CUtensorMap tmap_orient[b200vo::kLevels];    // per-keypoint disc box on the unblurred level
+    CUtensorMap tmap_brief[b200vo::kLevels];     // per-keypoint pattern box on the BLURRED level
+    bool fused_describe;       // describe_kernel (default) or the three round-1 kernels (B200VO_DESCRIBE=0)
     bool use_tma;
     int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC, 2: full Harley-Seal (4 POPC), 3: 3 CSA + 5 POPC (default)
+    int fpg_variant;           // five-point launch shape (B200VO_FPG, ransac.cu)
     int filter_fast_cap;       // filter.cu: survivors the compacted sort may hold (B200VO_FILTER_FAST_CAP, tests set 0)
     int64_t launches;
     bool timing;
@@ -195,6 +202,7 @@ int launch_pyramid(b200vo_ctx* ctx, int first_slot, int n);
 int launch_fast(b200vo_ctx* ctx, int first_slot, int n);
 int launch_select(b200vo_ctx* ctx, int first_slot, int n);
 int launch_orient(b200vo_ctx* ctx, int first_slot, int n);
+int launch_describe(b200vo_ctx* ctx, int first_slot, int n);
 int launch_blur(b200vo_ctx* ctx, int first_slot, int n);
 int launch_brief(b200vo_ctx* ctx, int first_slot, int n);
 int launch_match_slots(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_override);

@@ -15,6 +15,7 @@
 // in registers for the lifetime of the warp; the 32 bytes go out as one coalesced 32-B store.
 // The kernel also assembles the frame's final keypoint array in canonical (octave, y, x) order.
 #include "common.cuh"
+#include "tma.cuh"
 #include "brief_pattern.h"
 
 namespace b200vo {
@@ -174,6 +175,143 @@ brief_kernel(StoreView sv, int first_slot) {
     sv.desc[((size_t)slot * sv.kp_cap + i) * kDescBytes + lane] = (uint8_t)byte;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Fused descriptor stage (default): orientation + keypoint record + rBRIEF in ONE kernel on TMA-staged
+// shared-memory boxes.  A CTA takes DK_KP consecutive keypoints of one (slot, level) -- the level lists are in
+// raster order, so they are spatially adjacent -- and for each of them TMA-loads
+//   * the 31 rows x 48 bytes of the UNBLURRED level that cover the radius-15 disc  (box start 16-byte aligned), and
+//   * the 39 rows x 64 bytes of the BLURRED level that cover every rotated pattern point (|coordinate| <= 18)
+// into shared memory (2 x 16 `cp.async.bulk.tensor.3d` per CTA, two mbarriers).  Phase A: warp per keypoint,
+// the 749-pixel moments by dp4a on shared-memory words.  Phase B: thread per keypoint, fastAtan2 + the double-
+// precision sincos + the cv::KeyPoint record (the scalar tail costs one instruction stream per 16 keypoints).
+// Phase C: warp per keypoint, lane = descriptor byte, the 512 taps read shared memory.  The moments and the
+// rotation never touch global memory (round 1: three kernels, kp_mom / kp_rot round trips, 512 scattered global
+// byte loads per keypoint -- long-scoreboard 43 % in brief_kernel).  The blurred box lands while phases A and B run.
+constexpr int DK_KP = 16, DK_THREADS = 128;
+constexpr int DK_OBOX = (kOrientBoxW * kOrientBoxH + 127) / 128 * 128;      // 1536: TMA destinations are 128-byte aligned
+constexpr int DK_BBOX = (kBriefBoxW * kBriefBoxH + 127) / 128 * 128;        // 2560
+constexpr int DK_SMEM = DK_KP * (DK_OBOX + DK_BBOX);
+
+__global__ void __launch_bounds__(DK_THREADS)
+describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps maps_pyr, const __grid_constant__ LevelMaps maps_blur) {
+    extern __shared__ __align__(128) uint8_t dk_smem[];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ int s_x[DK_KP], s_y[DK_KP];
+    __shared__ int2 s_mom[DK_KP];
+    __shared__ float2 s_rot[DK_KP];
+    const int level = blockIdx.y;
+    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int* counts = sv.lkp_count + slot * kLevels;
+    const int cnt = counts[level];
+    int base = 0, total = 0;
+#pragma unroll
+    for (int l = 0; l < kLevels; ++l) {
+        const int c = counts[l];
+        if (l < level) base += c;
+        total += c;
+    }
+    if (level == 0 && blockIdx.x == 0 && tid == 0) {
+        if (total > sv.kp_cap) atomicOr(&sv.flags[slot], 8);
+        sv.kp_count[slot] = min(total, sv.kp_cap);
+    }
+    const int i0 = blockIdx.x * DK_KP;
+    const int nk = min(DK_KP, min(cnt - i0, sv.kp_cap - (base + i0)));          // uniform over the CTA
+    if (nk <= 0) return;
+    const LevelGeom g = sv.lv[level];
+    uint8_t* s_obox = dk_smem;
+    uint8_t* s_bbox = dk_smem + DK_KP * DK_OBOX;
+    const size_t lk = (size_t)slot * sv.lkp_total + sv.lkp_off[level] + i0;
+    if (tid == 0) {
+        tma::mbar_init(&s_bar[0], 1); tma::mbar_init(&s_bar[1], 1); tma::fence_mbar_init();
+        tma::mbar_arrive_expect_tx(&s_bar[0], nk * kOrientBoxW * kOrientBoxH);
+        tma::mbar_arrive_expect_tx(&s_bar[1], nk * kBriefBoxW * kBriefBoxH);
+    }
+    __syncthreads();
+    if (tid < nk) {
+        const uint32_t key = sv.lkp_key[lk + tid];
+        const int x = (key >> 8) & 0xFFF, y = key >> 20;
+        s_x[tid] = x; s_y[tid] = y;
+        tma::load_3d(s_obox + tid * DK_OBOX, &maps_pyr.m[level], &s_bar[0], (x - kHalfPatch) & ~15, y - kHalfPatch, slot);
+        tma::load_3d(s_bbox + tid * DK_BBOX, &maps_blur.m[level], &s_bar[1], (x - kBriefReach) & ~15, y - kBriefReach, slot);
+    }
+    __syncthreads();
+    tma::mbar_wait(&s_bar[0], 0);
+
+    // ---- phase A: moments, warp per keypoint
+    for (int j = warp; j < nk; j += DK_THREADS / 32) {
+        const int sh = (s_x[j] - kHalfPatch) & 15;                                // byte shift of the disc's first column in the box
+        const uint32_t* __restrict__ b32 = reinterpret_cast<const uint32_t*>(s_obox + j * DK_OBOX) + (sh >> 2);
+        const uint2* __restrict__ tab = d_ic_table[sh & 3];
+        int m10 = 0, m01 = 0;
+#pragma unroll
+        for (int it = 0; it < (kIcItems + 31) / 32; ++it) {
+            const int item = lane + 32 * it;
+            if (item < kIcItems) {
+                const int row = item / kIcWords, k = item - row * kIcWords;
+                const uint32_t px = b32[row * (kOrientBoxW / 4) + k];
+                const uint2 wm = __ldg(tab + item);
+                m10 = dp4a_u8_s8(px, wm.x, m10);
+                m01 += (row - kHalfPatch) * dp4a_u8_s8(px, wm.y, 0);
+            }
+        }
+        m10 = __reduce_add_sync(0xffffffffu, m10);
+        m01 = __reduce_add_sync(0xffffffffu, m01);
+        if (lane == 0) s_mom[j] = make_int2(m10, m01);
+    }
+    __syncthreads();
+
+    // ---- phase B: angle, rotation, final keypoint record (canonical (octave, y, x) order), thread per keypoint
+    if (tid < nk) {
+        const int x = s_x[tid], y = s_y[tid];
+        const int2 mom = s_mom[tid];
+        b200vo_keypoint kp;
+        kp.x = __fmul_rn((float)x, g.scale);
+        kp.y = __fmul_rn((float)y, g.scale);
+        kp.size = __fmul_rn(31.0f, g.scale);
+        kp.angle = fast_atan2_deg((float)mom.y, (float)mom.x);
+        kp.response = sv.lkp_resp[lk + tid];
+        kp.octave = level;
+        kp.class_id = -1;
+        kp.lx = (int16_t)x;
+        kp.ly = (int16_t)y;
+        sv.kp[(size_t)slot * sv.kp_cap + base + i0 + tid] = kp;
+        const float theta = __fmul_rn(kp.angle, (float)(3.14159265358979323846 / 180.0));
+        double sd, cd;
+        sincos((double)theta, &sd, &cd);
+        s_rot[tid] = make_float2((float)cd, (float)sd);
+    }
+    __syncthreads();
+    tma::mbar_wait(&s_bar[1], 0);
+
+    // ---- phase C: rBRIEF, warp per keypoint, lane = descriptor byte (pattern rows 8*lane .. 8*lane+7)
+    int8_t pat[32];
+    {
+        const int4* p = reinterpret_cast<const int4*>(d_pattern + lane * 32);
+        *reinterpret_cast<int4*>(&pat[0]) = p[0];
+        *reinterpret_cast<int4*>(&pat[16]) = p[1];
+    }
+    for (int j = warp; j < nk; j += DK_THREADS / 32) {
+        const int sh = (s_x[j] - kBriefReach) & 15;
+        const uint8_t* __restrict__ c = s_bbox + j * DK_BBOX + kBriefReach * kBriefBoxW + sh + kBriefReach;     // the keypoint itself
+        const float a = s_rot[j].x, b = s_rot[j].y;
+        uint32_t byte = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1];
+            const float x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+            const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int t0 = c[iy0 * kBriefBoxW + ix0];
+            const int t1 = c[iy1 * kBriefBoxW + ix1];
+            byte |= (uint32_t)(t0 < t1) << k;
+        }
+        sv.desc[((size_t)slot * sv.kp_cap + base + i0 + j) * kDescBytes + lane] = (uint8_t)byte;
+    }
+}
+
 int upload_brief_pattern() {
     cudaError_t e = cudaMemcpyToSymbol(d_pattern, kBriefPattern31, sizeof(kBriefPattern31));
     if (e != cudaSuccess) { set_error("pattern upload failed: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
@@ -196,6 +334,23 @@ int upload_brief_pattern() {
     return B200VO_OK;
 }
 
+int launch_describe(b200vo_ctx* ctx, int first_slot, int n) {
+    static bool configured_per_device[64] = {};
+    bool& configured = configured_per_device[ctx->device & 63];
+    if (!configured) {
+        B200VO_CUDA_CHECK(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DK_SMEM));
+        configured = true;
+    }
+    int maxkp = 1;
+    for (int l = 0; l < kLevels; ++l) maxkp = max(maxkp, ctx->store.lv[l].kp_cap);
+    dim3 grid(div_up(maxkp, DK_KP), kLevels, n);
+    describe_kernel<<<grid, DK_THREADS, DK_SMEM, ctx->stream>>>(ctx->store, first_slot, *reinterpret_cast<const LevelMaps*>(ctx->tmap_orient),
+                                                               *reinterpret_cast<const LevelMaps*>(ctx->tmap_brief));
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
+// the round-1 three-kernel path (B200VO_DESCRIBE=0): kept for A/B measurements and as a cross-check of the fused kernel
 int launch_orient(b200vo_ctx* ctx, int first_slot, int n) {
     int maxkp = 1;
     for (int l = 0; l < kLevels; ++l) maxkp = max(maxkp, ctx->store.lv[l].kp_cap);

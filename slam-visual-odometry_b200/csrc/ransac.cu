@@ -186,84 +186,121 @@ __device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, 
     return cnt;
 }
 
-// K14: one CTA per (pair, block of SC_HB hypotheses); the pair's correspondences are staged once in
-// shared memory (float4 per point) and every warp scores the valid models of the block against them.
+// K14: one CTA per (pair, block of SC_HB hypotheses).  The pair's correspondences are staged once in shared
+// memory (float4 per point); the valid models of the block (~4.85 of the 10 root slots per hypothesis) are
+// compacted and copied to shared memory with coalesced loads, so the scoring loop itself touches no global
+// memory (round 1 walked the root slots one by one -- a dependent model_ok / model load per slot: 69 % of the
+// stall samples were long-scoreboard, issue utilisation 26 %).
 // K15: arg-max with "first model wins" through one 64-bit atomicMax on (count << 32 | ~model index).
-// Models are abandoned as soon as they cannot reach the pair's best count so far (exact: such a
-// model can neither win nor tie), which removes most of the work of the spurious roots.
+// Models are abandoned as soon as they cannot reach the best count known so far (exact: such a model can neither
+// win nor tie).  The floor is the CTA's own best (shared memory) joined with the pair's global best as read one
+// model earlier -- a stale floor only abandons later, never wrongly.
 constexpr int SC_THREADS = 256;
-constexpr int SC_HB = 64;
+constexpr int SC_HB = 32;
 constexpr int SC_MAXPTS = 2048;                            // staging capacity: 32 KB of float4 (pairs with more good matches read global memory)
+constexpr int SC_SLOTS = SC_HB * kMaxSolutions;
 
 __global__ void __launch_bounds__(SC_THREADS)
 score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
     extern __shared__ __align__(16) unsigned char sc_smem[];
+    __shared__ int s_n, s_best;
+    __shared__ unsigned short s_slot[SC_SLOTS];
     const int pair = blockIdx.y;
     if (ra.adaptive && pv.done[pair]) return;
     const int m = pv.n_good[pair];
     if (m < ra.min_matches || m < 5) return;
     const int hb0 = ra.h0 + blockIdx.x * SC_HB;
     const int hb1 = min(hb0 + SC_HB, ra.h0 + ra.nround);
+    const int tid = threadIdx.x;
+    double* s_E = reinterpret_cast<double*>(sc_smem);                      // [SC_SLOTS][9]
+    float4* s_pts = reinterpret_cast<float4*>(sc_smem + SC_SLOTS * 9 * sizeof(double));
     const float4* xf = pv.xf + (size_t)pair * pv.kp_cap;
     const bool staged = m <= stage_cap;                    // uniform over the CTA
+    if (tid == 0) { s_n = 0; s_best = 0; }
+    __syncthreads();
+    const size_t slot0 = ((size_t)pair * pv.nhyp_cap + hb0) * kMaxSolutions;
+    const int nslots = (hb1 - hb0) * kMaxSolutions;
+    for (int i = tid; i < nslots; i += SC_THREADS)
+        if (pv.model_ok[slot0 + i]) s_slot[atomicAdd(&s_n, 1)] = (unsigned short)i;
     if (staged) {
-        float4* s = reinterpret_cast<float4*>(sc_smem);
-        for (int i = threadIdx.x; i < m; i += SC_THREADS) s[i] = xf[i];
-        __syncthreads();
-        xf = s;
+        for (int i = tid; i < m; i += SC_THREADS) s_pts[i] = xf[i];
+        xf = s_pts;
     }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    const int n = s_n;
+    for (int i = tid; i < n * 9; i += SC_THREADS) {
+        const int j = i / 9, k = i - j * 9;
+        s_E[i] = pv.models[(slot0 + s_slot[j]) * 9 + k];
+    }
+    __syncthreads();
+    const int lane = tid & 31, warp = tid >> 5;
     const geom::SampsonThreshold thr = geom::make_sampson_threshold(ra.thr2f);
-    const int nslots = (hb1 - hb0) * 10;
-    for (int i = warp; i < nslots; i += SC_THREADS / 32) {
-        const int h = hb0 + i / 10, s = i - (i / 10) * 10;
-        const size_t gid = (size_t)pair * pv.nhyp_cap + h;
-        if (!pv.model_ok[gid * 10 + s]) continue;
-        const double* mp = pv.models + gid * 90 + s * 9;
-        double E[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) E[k] = mp[k];
-        const int floor_count = pv.counts ? 0 : (int)(*(volatile unsigned long long*)&pv.best[pair] >> 32);
+    const volatile unsigned long long* gbest = &pv.best[pair];
+    int gfloor = pv.counts ? 0 : (int)(*gbest >> 32);
+    for (int j = warp; j < n; j += SC_THREADS / 32) {
+        const int slot = s_slot[j];
+        const int floor_count = pv.counts ? 0 : max(gfloor, *(volatile int*)&s_best);
+        const unsigned long long gnext = *gbest;           // consumed by the NEXT model: its latency hides behind this one
+        const double* E = s_E + j * 9;
         const int cnt = staged ? warp_count_inliers<true>(pv, pair, m, E, xf, thr, lane, floor_count)
                                : warp_count_inliers<false>(pv, pair, m, E, xf, thr, lane, floor_count);
         if (lane == 0) {
-            if (pv.counts) pv.counts[gid * 10 + s] = cnt;
-            const unsigned long long packed =
-                ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)(h * 10 + s));
-            if (cnt >= floor_count) atomicMax(&pv.best[pair], packed);
+            if (pv.counts) pv.counts[slot0 + slot] = cnt;
+            if (cnt >= floor_count) {
+                const uint32_t model = (uint32_t)(hb0 * kMaxSolutions + slot);            // = h * 10 + s
+                atomicMax(&pv.best[pair], ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - model));
+                atomicMax(&s_best, cnt);
+            }
         }
+        gfloor = (int)(gnext >> 32);
     }
 }
 
-static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
-    // measured on B200 (1000 frames, H = 1024): 256 threads x 2 CTAs/SM 8.0 ms; 128 x 4: 10.2; 64 x 8: 12.3;
-    // 512 x 1: 10.3 (larger CTAs keep more warps on the same instruction-cache lines; beyond 256 the
-    // register file fits only one CTA)
-    constexpr int THREADS = 256, GROUPS = 3 * (THREADS / 32);
-    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.fb_count, 0, sizeof(unsigned), ctx->stream));
+template <int THREADS, int MINB>
+static int launch_five_point_as(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
+    constexpr int GROUPS = 3 * (THREADS / 32);
     const size_t smem = GROUPS * sizeof(geom::GroupShared);
-    five_point_group_kernel<THREADS, 2><<<dim3(div_up(ra.nround, GROUPS), npairs), THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
+    five_point_group_kernel<THREADS, MINB><<<dim3(div_up(ra.nround, GROUPS), npairs), THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
-    // the queue length is only known on the device (measured share: 2-6 %): the grid covers the worst
+    // the queue length is only known on the device (measured share: 0.5-6 %): the grid covers the worst
     // case, CTAs beyond the queue exit at once
-    five_point_deferred_kernel<THREADS, 2><<<div_up(npairs * ra.nround, GROUPS), THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
+    five_point_deferred_kernel<THREADS, MINB><<<div_up(npairs * ra.nround, GROUPS), THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
+}
+
+static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
+    // launch shape (threads x CTAs/SM -> register cap), measured on B200 at 1000 frames, H = 1024 -- see DESIGN.md section 4
+    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.fb_count, 0, sizeof(unsigned), ctx->stream));
+    switch (ctx->fpg_variant) {
+        case 1: return launch_five_point_as<192, 2>(ctx, ra, npairs);      // 168 registers: no spills, 12 warps/SM
+        case 2: return launch_five_point_as<256, 3>(ctx, ra, npairs);      // 80 registers: 24 warps/SM, spills
+        case 3: return launch_five_point_as<128, 4>(ctx, ra, npairs);      // 128 registers, smaller CTAs
+        case 4: return launch_five_point_as<160, 3>(ctx, ra, npairs);      // 136 registers, 15 warps/SM
+        default: return launch_five_point_as<256, 2>(ctx, ra, npairs);     // 128 registers, 16 warps/SM
+    }
 }
 
 static int launch_score(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     const dim3 grid(div_up(ra.nround, SC_HB), npairs);
     const int cap = std::min(ctx->pairs.kp_cap, SC_MAXPTS);
-    score_kernel<<<grid, SC_THREADS, (size_t)cap * sizeof(float4), ctx->stream>>>(ctx->pairs, ra, cap);
+    score_kernel<<<grid, SC_THREADS, SC_SLOTS * 9 * sizeof(double) + (size_t)cap * sizeof(float4), ctx->stream>>>(ctx->pairs, ra, cap);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
 
 int init_ransac_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_MAXPTS * sizeof(float4)));
-    const int fpg_smem = 3 * (256 / 32) * (int)sizeof(geom::GroupShared);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(five_point_group_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpg_smem);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(five_point_deferred_kernel<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpg_smem);
+    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_SLOTS * 9 * sizeof(double) + SC_MAXPTS * sizeof(float4)));
+    auto fpg_attr = [&](auto main_k, auto def_k, int threads) {
+        const int bytes = 3 * (threads / 32) * (int)sizeof(geom::GroupShared);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(main_k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(def_k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    fpg_attr(five_point_group_kernel<256, 2>, five_point_deferred_kernel<256, 2>, 256);
+    fpg_attr(five_point_group_kernel<192, 2>, five_point_deferred_kernel<192, 2>, 192);
+    fpg_attr(five_point_group_kernel<256, 3>, five_point_deferred_kernel<256, 3>, 256);
+    fpg_attr(five_point_group_kernel<128, 4>, five_point_deferred_kernel<128, 4>, 128);
+    fpg_attr(five_point_group_kernel<160, 3>, five_point_deferred_kernel<160, 3>, 160);
     if (e != cudaSuccess) { set_error("ransac kernel smem attribute: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
     return B200VO_OK;
 }

@@ -196,6 +196,22 @@ def test_tma_and_word_staging_agree(built, seq_small, monkeypatch):
             assert np.array_equal(a, b)
 
 
+def test_fused_describe_equals_three_kernel_path(built, seq_kitti, monkeypatch):
+    """The fused orientation + keypoint + rBRIEF kernel on per-keypoint TMA boxes (default) and the
+    round-1 path (orient_kernel, keypoint_finalize_kernel, brief_kernel reading global memory;
+    B200VO_DESCRIBE=0) produce byte-identical keypoints and descriptors at the headline configuration."""
+    frames = seq_kitti[0]
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("B200VO_DESCRIBE", mode)
+        with built.Context(1241, 376, nfeatures=3000, max_frames=3, ransac_hypotheses=64) as ctx:
+            ctx.upload_frames(frames, 0)
+            ctx.detect(0, 2)
+            out[mode] = [ctx.get_features(s) for s in range(2)]
+    for (ka, da), (kb, db) in zip(out["1"], out["0"]):
+        assert len(ka) >= 2900 and ka.tobytes() == kb.tobytes() and np.array_equal(da, db)
+
+
 @pytest.mark.parametrize("W,H,NF", [(100, 80, 300), (333, 222, 700), (1999, 1001, 5000), (64, 64, 100), (4095, 300, 2000)])
 def test_odd_sizes_bit_exact(built, W, H, NF):
     """Widths that are not multiples of 4 / 16, the smallest and the widest supported images, a level

@@ -68,6 +68,11 @@ def test_accuracy_vs_ground_truth_and_cv2(built, seq, records):
     frames, R_wc, C_w, K = seq
     batched, _ = records
     cv_recs, _ = PL.run_pairs_cv2(list(frames), NF)
+    vo = PL.Cv2VisualOdometry(W, H, NF)
+    with built.Context(W, H, nfeatures=NF, max_frames=NFRAMES + 1, ransac_hypotheses=NHYP) as ctx:
+        ctx.upload_frames(frames, 0)
+        ctx.detect(0, NFRAMES)
+        descs = [ctx.get_features(s)[1] for s in range(NFRAMES)]
     dt_gt, dt_cv, dt_cv_gt = [], [], []
     for i, r in enumerate(batched):
         assert r["status"] & built.ST_E_FOUND
@@ -75,10 +80,13 @@ def test_accuracy_vs_ground_truth_and_cv2(built, seq, records):
         R = r["R"].reshape(3, 3)
         assert abs(np.linalg.det(R) - 1) < 1e-9 and abs(np.linalg.norm(r["t"]) - 1) < 1e-9
         assert G.rotation_angle_deg(R, Rg) < 1.0, "pair %d rotation error vs GT" % i
-        # same correspondences as the cv2 pipeline (identical good-match count).  cv2 draws its own
-        # hypotheses (parity is by tolerance): both results are minimal-sample models
-        # within a degree of the ground truth, hence within two degrees of each other
-        assert r["n_matches"] == cv_recs[i]["n_matches"]
+        # the reference's matcher on the SAME descriptor matrices gives the identical good-match list length
+        # (cv2's own ORB returns its keypoints in another order, and BFMatcher breaks distance ties by index, so
+        # the end-to-end cv2 pipeline may cross-check a few ties differently -- SURVEY section 7.4).  cv2 draws its
+        # own hypotheses (parity is by tolerance): both results are minimal-sample models within a
+        # degree of the ground truth, hence within two degrees of each other
+        assert r["n_matches"] == len(vo.good_matches(descs[i], descs[i + 1]))
+        assert abs(int(r["n_matches"]) - cv_recs[i]["n_matches"]) <= 0.2 * cv_recs[i]["n_matches"]
         assert G.rotation_angle_deg(cv_recs[i]["R"], Rg) < 1.0, "pair %d: cv2 rotation error vs GT" % i
         assert G.rotation_angle_deg(R, cv_recs[i]["R"]) < 2.0
         # translation direction: the scene has near structure, so the direction is observable; a minimal-
