@@ -314,11 +314,30 @@ class SeqRunner:
                     self.recs_dev[done_p * self.RB:(done_p + np_) * self.RB].copy_(src, non_blocking=True)
 
     def close(self):
+        """Drop the tensors; the context itself (and with it the CUDA stream torch has seen) is destroyed only at
+        the very end of the run (close_contexts): torch's pinned-memory allocator records an event on every stream a
+        pinned tensor was used on when that tensor is freed, so no stream may die before the last such tensor."""
         self.stream.synchronize()
         self.stream = None
         self.recs_dev = None
         self.d_frames = self.h_frames = None
-        self.ctx.close()
+        _OPEN_CONTEXTS.append(self.ctx)
+
+
+_OPEN_CONTEXTS = []
+
+
+def close_contexts(torch):
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    try:
+        torch._C._host_emptyCache()          # return the pinned blocks now, while every stream they were used on still exists
+    except Exception:
+        pass
+    while _OPEN_CONTEXTS:
+        _OPEN_CONTEXTS.pop().close()
 
 
 def timed_steps(torch, dist, world, runner_stream, fn, steps, warmup, dev, launches_of=None):
@@ -616,10 +635,7 @@ def run_b200(args):
             dist.barrier()
             dist.destroy_process_group()
         del recs_host, h_frames
-        import gc
-        gc.collect()
-        torch.cuda.synchronize()
-        torch.cuda.empty_cache()
+        close_contexts(torch)
         return 0
 
     hbm_peak, peak_src = peaks()
@@ -700,12 +716,9 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    # every context is closed (SeqRunner.close); release the last torch tensors and leave through the normal interpreter exit
+    # release the last torch tensors, then destroy the contexts, then leave through the normal interpreter exit
     del recs_host, h_frames, ok
-    import gc
-    gc.collect()
-    torch.cuda.synchronize()
-    torch.cuda.empty_cache()
+    close_contexts(torch)
     return 0
 
 

@@ -32,6 +32,7 @@
  *                                     contiguous range of frame pairs  src/visual_odometry.cpp:340-366
  * b200vo_chain_pose                 invert_relative_... + compose_next_...  src/visual_odometry.cpp:292-314,350-360
  * b200vo_fundamental_from_essential F = K^-T E K^-1                   src/visual_odometry.cpp:225-246
+ * b200vo_group_process_sequence     [ext] the frame loop of main() over several GPUs   src/main.cpp:128-194
  */
 #ifndef B200VO_H
 #define B200VO_H
@@ -232,6 +233,29 @@ int b200vo_fundamental_from_essential(const b200vo_ctx* ctx, const double* essen
 /* process_frame's accumulation over a whole range of records (reference src/visual_odometry.cpp:340-374):
  * poses_out[i] = pose after applying recs[0..i] to (R0, t0); 12 doubles each (R_wc row-major, t_wc). */
 int b200vo_chain_trajectory(const b200vo_pose_record* recs, int n, const double* R0, const double* t0, double* poses_out);
+
+/* ---- [ext] device groups: ONE sequence over the GPUs of one node ------------------------------------------
+ * The reference walks a sequence strictly in order on one thread (src/main.cpp:128-194).  Frame pairs are
+ * independent until the poses are chained, so a group partitions the pair range into contiguous blocks, one
+ * per device, runs every block on its own context (one host thread each), all-gathers the 160-byte records
+ * with NCCL (ncclCommInitAll + ncclAllGather over NVLink; libnccl.so.2 is bound at first use) and hands them to
+ * the caller in pair order for b200vo_chain_trajectory.  Pair results are byte-identical to the one-device
+ * run: nothing in a pair's computation depends on device, slot or batch. */
+typedef struct b200vo_group b200vo_group;
+int b200vo_group_create(const b200vo_options* opt, const int* devices, int ndev, b200vo_group** out);
+void b200vo_group_destroy(b200vo_group* g);
+int b200vo_group_size(const b200vo_group* g);
+b200vo_ctx* b200vo_group_ctx(b200vo_group* g, int i);                 /* the i-th device's context (owned by the group) */
+/* Contiguous pair range [lo, hi) of `rank` among `world` (the first ranks take the remainder). */
+int b200vo_partition_pairs(int total_pairs, int world, int rank, int* lo, int* hi);
+/* nframes host frames (layout as b200vo_upload_frames) -> nframes-1 records in pair order.  opt.max_frames of the
+ * group must be >= batch_frames + 1. */
+int b200vo_group_process_sequence(b200vo_group* g, const uint8_t* frames, int nframes, size_t pitch, size_t frame_stride,
+                                  int channels, int batch_frames, int64_t first_pair_id, b200vo_pose_record* out);
+/* The exchange step alone: device i contributes counts[i] records from its send buffer (filled by
+ * b200vo_group_process_sequence); out receives sum(counts) records in rank order. */
+int b200vo_group_allgather_records(b200vo_group* g, const int* counts, b200vo_pose_record* out);
+int b200vo_nccl_version(void);                                          /* 0 when NCCL could not be loaded */
 
 /* Microbenchmark of the XOR+POPC+ADD instruction mix the matcher is bound by: sustained 32-bit
  * population counts per second on this device (the matcher's roofline denominator). */

@@ -13,6 +13,7 @@
 #include "vo_cv_compat.h"
 
 struct b200vo_ctx;
+struct b200vo_group;
 
 class VisualOdometry {
 public:
@@ -21,6 +22,9 @@ public:
         int ransac_hypotheses = 1024;
         uint64_t ransac_seed = 42;
         int device = 0;
+        std::vector<int> devices;          // [ext] more than one entry: process_sequence partitions the pair range over these GPUs
+                                           // (contiguous blocks, one host thread per GPU, NCCL all-gather of the pose records);
+                                           // process_frame always runs on the first
         int batch_frames = 64;             // frames per launch batch in process_sequence
         bool ratio_test = false;           // false: cross-check (reference :87); true: Lowe ratio test on 2-NN
         float ratio = 0.75f;
@@ -56,7 +60,8 @@ private:
 
     Options options_;
     int width_ = 0, height_ = 0;
-    b200vo_ctx* ctx_ = nullptr;
+    b200vo_ctx* ctx_ = nullptr;         // context of the first device (owned by group_)
+    b200vo_group* group_ = nullptr;
     cv::Mat camera_matrix_;
     bool has_last_F_ = false;
     cv::Matx33d last_F_{};

@@ -57,6 +57,8 @@ EXPORTS = [
     "b200vo_process_pairs_device", "b200vo_five_point", "b200vo_score_models", "b200vo_recover_pose",
     "b200vo_draw_samples", "b200vo_chain_pose", "b200vo_chain_trajectory", "b200vo_measure_popc_rate", "b200vo_fundamental_from_essential", "b200vo_enable_timing",
     "b200vo_get_stage_times", "b200vo_kernel_launches", "b200vo_stream",
+    "b200vo_group_create", "b200vo_group_destroy", "b200vo_group_size", "b200vo_group_ctx", "b200vo_partition_pairs",
+    "b200vo_group_process_sequence", "b200vo_group_allgather_records", "b200vo_nccl_version",
 ]
 
 _lib = None
@@ -77,6 +79,9 @@ def load_library():
     lib.b200vo_stream.argtypes = [C.c_void_p]
     lib.b200vo_destroy.argtypes = [C.c_void_p]
     lib.b200vo_destroy.restype = None
+    lib.b200vo_group_destroy.argtypes = [C.c_void_p]
+    lib.b200vo_group_destroy.restype = None
+    lib.b200vo_group_process_sequence.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int64, C.c_void_p]
     _lib = lib
     return lib
 
@@ -365,3 +370,56 @@ class Context:
 
     def stream(self):
         return self.lib.b200vo_stream(self.h)
+
+
+class Group:
+    """A device group (b200vo_group): one sequence partitioned over several GPUs of this node, records
+    all-gathered with NCCL inside the library."""
+
+    def __init__(self, width, height, devices, **options):
+        self.lib = load_library()
+        self.opt = default_options(width, height, **options)
+        dev = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        rc = self.lib.b200vo_group_create(C.byref(self.opt), dev, len(devices), C.byref(h))
+        if rc:
+            raise B200VOError(rc, self.lib.b200vo_last_error().decode())
+        self.h = h
+        self.width, self.height = int(width), int(height)
+
+    def process_sequence(self, frames, batch_frames, first_pair_id=0):
+        f = np.ascontiguousarray(frames, np.uint8)
+        ch = 3 if f.ndim == 4 else 1
+        pitch = f.shape[2] * ch
+        out = np.zeros(len(f) - 1, POSE_RECORD_DTYPE)
+        rc = self.lib.b200vo_group_process_sequence(self.h, _p(f), len(f), C.c_size_t(pitch), C.c_size_t(pitch * f.shape[1]), ch,
+                                                    int(batch_frames), C.c_int64(first_pair_id), _p(out))
+        if rc:
+            raise B200VOError(rc, self.lib.b200vo_last_error().decode())
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200vo_group_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def partition_pairs(total_pairs, world, rank):
+    lib = load_library()
+    lo, hi = C.c_int(), C.c_int()
+    rc = lib.b200vo_partition_pairs(int(total_pairs), int(world), int(rank), C.byref(lo), C.byref(hi))
+    if rc:
+        raise B200VOError(rc, lib.b200vo_last_error().decode())
+    return lo.value, hi.value

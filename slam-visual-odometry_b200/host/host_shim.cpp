@@ -26,6 +26,20 @@ void* vo_host_create(int width, int height, int nfeatures, int ransac_hypotheses
     } catch (const std::exception& e) { g_msg = e.what(); return nullptr; }
 }
 
+// the same over several devices (Options::devices): process_sequence partitions the pair range over them
+void* vo_host_create_multi(int width, int height, int nfeatures, int ransac_hypotheses, unsigned long long seed, const int* devices,
+                           int ndev, int batch_frames) {
+    try {
+        VisualOdometry::Options o;
+        if (nfeatures > 0) o.nfeatures = nfeatures;
+        if (ransac_hypotheses > 0) o.ransac_hypotheses = ransac_hypotheses;
+        o.ransac_seed = seed;
+        o.devices.assign(devices, devices + ndev);
+        if (batch_frames > 0) o.batch_frames = batch_frames;
+        return new VisualOdometry(width, height, o);
+    } catch (const std::exception& e) { g_msg = e.what(); return nullptr; }
+}
+
 void vo_host_destroy(void* h) { delete static_cast<VisualOdometry*>(h); }
 
 // pose_out: 12 doubles (R_wc row-major, then t_wc); returns number of keypoints or <0 on error

@@ -54,14 +54,16 @@ void VisualOdometry::init(int w, int h, const Options& o) {
     opt.match_mode = o.ratio_test ? B200VO_MATCH_RATIO : B200VO_MATCH_CROSSCHECK;
     opt.ratio = o.ratio;
     opt.max_frames = std::max(2, o.batch_frames + 1);
-    check(b200vo_create(&opt, o.device, &ctx_), "create");
+    std::vector<int> devs = o.devices.empty() ? std::vector<int>{o.device} : o.devices;
+    check(b200vo_group_create(&opt, devs.data(), (int)devs.size(), &group_), "group_create");
+    ctx_ = b200vo_group_ctx(group_, 0);
     // intrinsics synthesised from the image size (reference src/visual_odometry.cpp:90-98)
     camera_matrix_ = cv::Mat::eye(3, 3, CV_64F);
     camera_matrix_.at<double>(0, 0) = opt.fx; camera_matrix_.at<double>(1, 1) = opt.fy;
     camera_matrix_.at<double>(0, 2) = opt.cx; camera_matrix_.at<double>(1, 2) = opt.cy;
 }
 
-VisualOdometry::~VisualOdometry() { b200vo_destroy(ctx_); }
+VisualOdometry::~VisualOdometry() { b200vo_group_destroy(group_); }
 
 void VisualOdometry::push_pose(const Pose& p) {
     std::lock_guard<std::mutex> lock(trajectory_mutex_);
@@ -141,6 +143,46 @@ std::vector<Pose> VisualOdometry::process_sequence(const std::vector<cv::Mat>& i
         frame_counter_ = 1;
         initialized_ = true;
         next = 1;
+    }
+    if (b200vo_group_size(group_) > 1 && images.size() - next >= 2 * (size_t)b200vo_group_size(group_)) {
+        // Several GPUs: the remaining frames (plus the previous frame, which is pair 0's first image) form one
+        // sequence that the group partitions by contiguous pair ranges; the records come back in pair order and
+        // are chained here exactly as below.  The previous frame's pixels are needed again (another device may
+        // own the first block), so this path requires it in `images`: it is taken from images[next - 1] when the
+        // whole sequence goes through one call, which is how main() would use it.
+        if (next == 0) throw std::runtime_error("process_sequence on several GPUs must start a sequence (call it once with all frames)");
+        const size_t first_img = next - 1, nimg = images.size() - first_img;
+        const ImageView v0 = view_of(images[first_img], width_, height_);
+        const size_t fbytes = (size_t)width_ * v0.channels * height_;
+        std::vector<uint8_t> packed(nimg * fbytes);
+        for (size_t i = 0; i < nimg; ++i) {
+            const ImageView v = view_of(images[first_img + i], width_, height_);
+            if (v.channels != v0.channels) throw std::runtime_error("all images of a sequence must have the same channel count");
+            for (int y = 0; y < height_; ++y) std::copy(v.data + (size_t)y * v.pitch, v.data + (size_t)y * v.pitch + (size_t)width_ * v.channels,
+                                                        packed.data() + i * fbytes + (size_t)y * width_ * v.channels);
+        }
+        std::vector<b200vo_pose_record> recs(nimg - 1);
+        check(b200vo_group_process_sequence(group_, packed.data(), (int)nimg, (size_t)width_ * v0.channels, fbytes, v0.channels, B,
+                                            frame_counter_ - 1, recs.data()), "group_process_sequence");
+        Pose cur(previous_frame_.pose.R_wc, previous_frame_.pose.t_wc);
+        for (size_t i = 0; i < recs.size(); ++i) {
+            if (recs[i].status & B200VO_ST_E_FOUND) cur = chained(cur, recs[i]);
+            push_pose(cur);
+            out.emplace_back(cur.R_wc, cur.t_wc);
+        }
+        previous_frame_.pose = Pose(cur.R_wc, cur.t_wc);
+        previous_frame_.id = (int)(frame_counter_ + (int64_t)recs.size() - 1);
+        frame_counter_ += (int64_t)recs.size();
+        // the last frame's features live on the last device; a following process_frame / process_sequence call
+        // re-detects it on the first device
+        {
+            const ImageView v = view_of(images.back(), width_, height_);
+            check(b200vo_upload_frames(ctx_, v.data, 1, v.pitch, v.pitch * height_, v.channels, 0), "upload_frames");
+            check(b200vo_detect(ctx_, 0, 1), "detect");
+            check(b200vo_synchronize(ctx_), "synchronize");
+            previous_slot_ = 0;
+        }
+        return out;
     }
     std::vector<b200vo_pose_record> recs((size_t)B);
     while (next < images.size()) {

@@ -328,3 +328,53 @@ def test_two_gpus_split_range_is_byte_identical(built, seq, records):
             out.append(ctx.process_pairs(0, hi - lo, lo))
     got = np.concatenate(out)
     assert got.tobytes() == batched.tobytes()
+
+
+def test_group_of_one_device_equals_context(built, seq, records):
+    """b200vo_group_process_sequence on a one-device group (no NCCL involved): the same records as the
+    plain context path, for a batch size that makes the ring wrap."""
+    frames = seq[0]
+    batched, _ = records
+    with built.Group(W, H, [0], nfeatures=NF, max_frames=4, ransac_hypotheses=NHYP) as g:
+        recs = g.process_sequence(frames, 3)
+    assert recs.tobytes() == batched.tobytes()
+
+
+def test_group_partition_matches_python_helper(built):
+    from b200vo import sequence as SQ
+    for total, world in ((999, 8), (7, 2), (3, 4), (0, 3), (255, 8)):
+        for r in range(world):
+            assert built.partition_pairs(total, world, r) == SQ.partition_pairs(total, world, r)
+
+
+def test_group_on_two_gpus_is_byte_identical_and_uses_nccl(built, seq, records):
+    """The C multi-GPU path (skipped on a one-GPU box): a two-device group partitions the pair range, each
+    device runs its block on its own host thread, the records are all-gathered by NCCL inside the library.
+    Byte-identical to the one-GPU records; and through the C++ class (Options::devices) the trajectory of
+    process_sequence equals the one-GPU trajectory exactly."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    frames = seq[0]
+    batched, _ = records
+    assert built.load_library().b200vo_nccl_version() > 20000
+    with built.Group(W, H, [0, 1], nfeatures=NF, max_frames=4, ransac_hypotheses=NHYP) as g:
+        recs = g.process_sequence(frames, 3)
+        again = g.process_sequence(frames, 2)
+    assert recs.tobytes() == batched.tobytes() and again.tobytes() == batched.tobytes()
+    lib = _host(built)
+    lib.vo_host_create_multi.restype = ctypes.c_void_p
+    devs = (ctypes.c_int * 2)(0, 1)
+    out = {}
+    for name, h in (("multi", lib.vo_host_create_multi(W, H, NF, NHYP, ctypes.c_ulonglong(42), devs, 2, 3)),
+                    ("single", lib.vo_host_create(W, H, NF, NHYP, ctypes.c_ulonglong(42), 0, 3))):
+        assert h, lib.vo_host_last_error()
+        h = ctypes.c_void_p(h)
+        o = np.zeros((NFRAMES, 12))
+        f = np.ascontiguousarray(frames)
+        n = lib.vo_host_process_sequence(h, f.ctypes.data_as(ctypes.c_void_p), NFRAMES, W, H, 1, o.ctypes.data_as(ctypes.c_void_p))
+        assert n == NFRAMES, lib.vo_host_last_error()
+        out[name] = o
+        lib.vo_host_destroy(h)
+    assert out["multi"].tobytes() == out["single"].tobytes()
+    assert np.allclose(out["single"][1:], built.chain_trajectory(batched), atol=1e-15)
