@@ -300,6 +300,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         ctx->match_csa = 3;
         ctx->filter_fast_cap = 1 << 30;
         ctx->fpg_variant = 0;
+        ctx->pdl = false; ctx->pdl_enabled = true;
+        if (const char* v = getenv("B200VO_PDL")) ctx->pdl_enabled = (atoi(v) != 0);
         ctx->fused_describe = ctx->use_tma;
         if (const char* v = getenv("B200VO_DESCRIBE")) ctx->fused_describe = (atoi(v) != 0);
         if (const char* v = getenv("B200VO_FPG")) ctx->fpg_variant = atoi(v);
@@ -458,6 +460,10 @@ int b200vo_detect(b200vo_ctx* ctx, int first_slot, int n) {
     if (!ctx || n <= 0 || n > ctx->store.slots || !slot_ok(ctx, first_slot)) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
     B200VO_CUDA_CHECK(cudaSetDevice(ctx->device));
     int rc;
+    // small batches (the per-frame streaming step) are a chain of dependent launches of a few CTAs each:
+    // programmatic dependent launch overlaps each launch latency with the predecessor's tail (common.cuh)
+    ctx->pdl = ctx->pdl_enabled && !ctx->timing && n <= kMergedLevelsMaxFrames;
+    struct PdlOff { b200vo_ctx* c; ~PdlOff() { c->pdl = false; } } pdl_off{ctx};
     StageClock clk(ctx);
     if ((rc = launch_pyramid(ctx, first_slot, n))) return rc;  clk.mark();
     if ((rc = launch_fast(ctx, first_slot, n))) return rc;     clk.mark();
@@ -649,6 +655,8 @@ int b200vo_match(b200vo_ctx* ctx, int slot1, int slot2, b200vo_dmatch* out, int 
 static int run_pairs(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_override, int64_t first_pair_id,
                      const int32_t* d_samples, int nhyp) {
     int rc;
+    ctx->pdl = ctx->pdl_enabled && !ctx->timing && npairs <= kMergedLevelsMaxFrames;
+    struct PdlOff { b200vo_ctx* c; ~PdlOff() { c->pdl = false; } } pdl_off{ctx};
     StageClock clk(ctx);
     if ((rc = launch_match_slots(ctx, first_slot, npairs, slot_b_override))) return rc;    clk.mark();
     if ((rc = launch_filter(ctx, first_slot, npairs, slot_b_override))) return rc;         clk.mark();

@@ -31,6 +31,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 template <bool MERGED>
 __global__ void __launch_bounds__(256)
 blur_kernel(StoreView sv, const __grid_constant__ LevelTiles lt, int level_arg, int first_slot, const __grid_constant__ LevelMaps maps, int use_tma) {
+    pdl_grid_sync();
     __shared__ __align__(128) uint32_t s_in[BL_SH][BL_SWW];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(16) float s_row[BL_SH][BL_W];
@@ -40,7 +41,7 @@ blur_kernel(StoreView sv, const __grid_constant__ LevelTiles lt, int level_arg, 
     int level = level_arg, bx = blockIdx.x, by = blockIdx.y, frame = blockIdx.z;
     if (MERGED) { const TileCoord tc = tile_coord(lt, blockIdx.x); level = tc.level; bx = tc.bx; by = tc.by; frame = tc.frame; }
     const LevelGeom g = sv.lv[level];
-    const int slot = (first_slot + frame) % sv.slots;
+    const int slot = ring_slot(first_slot, frame, sv.slots);
     const uint8_t* __restrict__ img = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset;
     uint8_t* out = sv.blur + (size_t)slot * sv.slot_bytes + g.offset;
     const int ox = bx * BL_W, oy = by * BL_H;
@@ -159,14 +160,14 @@ int launch_blur(b200vo_ctx* ctx, int first_slot, int n) {
     for (int l = 0; l < kLevels; ++l) level_tiles_add(lt, l, div_up(ctx->store.lv[l].w, BL_W), div_up(ctx->store.lv[l].h, BL_H), n);
     if (n <= kMergedLevelsMaxFrames) {
         // one launch for all eight levels
-        blur_kernel<true><<<lt.first[kLevels], 256, 0, ctx->stream>>>(ctx->store, lt, 0, first_slot, maps, ctx->use_tma ? 1 : 0);
+        launch_k(ctx, blur_kernel<true>, dim3(lt.first[kLevels]), dim3(256), 0, ctx->store, lt, 0, first_slot, maps, ctx->use_tma ? 1 : 0);
         B200VO_LAUNCH_CHECK(ctx);
         return B200VO_OK;
     }
     for (int l = 0; l < kLevels; ++l) {
         const LevelGeom& g = ctx->store.lv[l];
         dim3 grid(div_up(g.w, BL_W), div_up(g.h, BL_H), n);
-        blur_kernel<false><<<grid, 256, 0, ctx->stream>>>(ctx->store, lt, l, first_slot, maps, ctx->use_tma ? 1 : 0);
+        launch_k(ctx, blur_kernel<false>, dim3(grid), dim3(256), 0, ctx->store, lt, l, first_slot, maps, ctx->use_tma ? 1 : 0);
         B200VO_LAUNCH_CHECK(ctx);
     }
     return B200VO_OK;

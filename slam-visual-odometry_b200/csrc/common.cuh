@@ -64,6 +64,9 @@ __device__ __forceinline__ TileCoord tile_coord(const LevelTiles& lt, int cta) {
     t.bx = tile - t.by * lt.tx[t.level];
     return t;
 }
+// slot (first + k) of the ring, first < slots, k <= slots: one compare instead of an integer division (~20 instructions,
+// 2-3 % of the short per-tile kernels in the round-2 profile)
+__host__ __device__ __forceinline__ int ring_slot(int first, int k, int slots) { const int s = first + k; return s >= slots ? s - slots : s; }
 inline void level_tiles_add(LevelTiles& lt, int l, int tx, int ty, int n) {      // host: append level l (ty == 0: not in this launch)
     lt.tx[l] = tx > 0 ? tx : 1;
     lt.tiles[l] = tx * ty > 0 ? tx * ty : 1;
@@ -161,6 +164,8 @@ struct b200vo_ctx {
     bool fused_describe;       // describe_kernel (default) or the three round-1 kernels (B200VO_DESCRIBE=0)
     bool use_tma;
     int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC, 2: full Harley-Seal (4 POPC), 3: 3 CSA + 5 POPC (default)
+    bool pdl;                  // programmatic dependent launch for the current call (small batches only; B200VO_PDL=0 disables)
+    bool pdl_enabled;
     int fpg_variant;           // five-point launch shape (B200VO_FPG, ransac.cu)
     int filter_fast_cap;       // filter.cu: survivors the compacted sort may hold (B200VO_FILTER_FAST_CAP, tests set 0)
     int64_t launches;
@@ -195,6 +200,31 @@ void set_error(const char* fmt, ...);
     } while (0)
 
 inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+// ---- launches ------------------------------------------------------------------------------------------------
+// Every kernel of the library starts with pdl_grid_sync(): `griddepcontrol.launch_dependents` lets the NEXT kernel
+// of the stream be scheduled while this one still runs, `griddepcontrol.wait` blocks until the PREVIOUS grid has
+// completed and its memory is visible -- so nothing is read early.  Both are no-ops unless the launch carries the
+// programmatic-stream-serialization attribute, which launch_k sets only for small batches (ctx->pdl): the
+// per-frame streaming step is a chain of ~20 dependent launches of a few CTAs each, and the 3-4 us launch latency
+// of each then overlaps the tail of its predecessor; large batched launches fill the GPU and keep plain ordering.
+__device__ __forceinline__ void pdl_grid_sync() {
+#if defined(__CUDA_ARCH__)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(b200vo_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = ctx->pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);       // the error, if any, is picked up by B200VO_LAUNCH_CHECK
+}
 
 // stage launchers (each enqueues on ctx->stream and returns a b200vo_status)
 int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int first_slot, int n);

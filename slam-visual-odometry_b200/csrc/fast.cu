@@ -69,7 +69,7 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
     __shared__ int s_hist[256];                     // score histogram of this tile, flushed once (one global atomic per non-empty bin)
 
     const LevelGeom g = sv.lv[level];
-    const int slot = (first_slot + frame) % sv.slots;
+    const int slot = ring_slot(first_slot, frame, sv.slots);
     const uint8_t* __restrict__ img = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset;
     const int ox = kEdge + bx * FT_W;       // first output pixel of the tile
     const int oy = kEdge + by * FT_H;
@@ -113,16 +113,22 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
     // hold for two adjacent k:  (m0&m4)|(m4&m8)|(m8&m12)|(m12&m0) = (m0|m8)&(m4|m12).  The test ignores
     // the polarity (18 % of the pixels of a textured frame pass instead of 15 % -- phase 2 decides), which
     // lets it run on VABSDIFF4 plus a carry-free byte compare: ~15 instructions per pixel instead of ~45.
+    // A thread keeps the pass flags of all its words (16 cells) in one register and appends its survivors
+    // after ONE warp scan and ONE shared atomic per warp (round 1: four ballots, four popcounts and an atomic
+    // per word -- a fifth of the kernel's instructions).
     {
         const uint32_t* s32 = reinterpret_cast<const uint32_t*>(s_img);
         const uint32_t tt = (uint32_t)t;
         const bool t_hi = tt >= 128u;                               // x > t needs bit 7 of x when t >= 128
         const uint32_t kadd = (t_hi ? 255u - tt : 127u - tt) * 0x01010101u;
         const int obyte = 3 + shift;                                // byte column of score-tile cell 0 in a pixel-tile row
+        constexpr int ITERS = (FT_CH * FT_CW / 4) / 256;            // words per thread: 4 (wide tile) or 2
+        constexpr int ROWS_PER_IT = 256 / (FT_CW / 4);              // tile rows covered by one pass of the CTA
+        const int j = tid % (FT_CW / 4), cy0 = tid / (FT_CW / 4);   // this thread's word column and its row in the first pass
+        uint32_t flags = 0;                                         // bit 4*it + b: cell (cy0 + it*ROWS_PER_IT, 4*j + b) passed
 #pragma unroll
-        for (int it = 0; it < (FT_CH * FT_CW / 4) / 256; ++it) {
-            const int wi = tid + 256 * it;
-            const int cy = wi / (FT_CW / 4), j = wi - cy * (FT_CW / 4);
+        for (int it = 0; it < ITERS; ++it) {
+            const int cy = cy0 + it * ROWS_PER_IT;
             const int bc = obyte + 4 * j;                            // first of the four centres
             const uint32_t* rc = s32 + (cy + 3) * FT_SWW;
             auto ld4 = [](const uint32_t* row, int byte) -> uint32_t {
@@ -138,22 +144,25 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
             };
             const uint32_t m0 = gt_t(__vabsdiffu4(r0, c)), m4 = gt_t(__vabsdiffu4(r4, c));
             const uint32_t m8 = gt_t(__vabsdiffu4(r8, c)), m12 = gt_t(__vabsdiffu4(r12, c));
-            const uint32_t pass4 = (m0 | m8) & (m4 | m12);
-            // warp-aggregated append: one ballot per byte position
-            const uint32_t lt = (1u << lane) - 1u;
-            const uint32_t b0 = __ballot_sync(0xffffffffu, pass4 & 0x80u), b1 = __ballot_sync(0xffffffffu, pass4 & 0x8000u);
-            const uint32_t b2 = __ballot_sync(0xffffffffu, pass4 & 0x800000u), b3 = __ballot_sync(0xffffffffu, pass4 & 0x80000000u);
-            const int n0 = __popc(b0), n1 = __popc(b1), n2 = __popc(b2), n3 = __popc(b3);
-            if (n0 + n1 + n2 + n3) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&s_nsurv, n0 + n1 + n2 + n3);
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int cell = cy * FT_CW + 4 * j;
-                if (pass4 & 0x80u) s_surv[base + __popc(b0 & lt)] = (uint16_t)cell;
-                if (pass4 & 0x8000u) s_surv[base + n0 + __popc(b1 & lt)] = (uint16_t)(cell + 1);
-                if (pass4 & 0x800000u) s_surv[base + n0 + n1 + __popc(b2 & lt)] = (uint16_t)(cell + 2);
-                if (pass4 & 0x80000000u) s_surv[base + n0 + n1 + n2 + __popc(b3 & lt)] = (uint16_t)(cell + 3);
-            }
+            const uint32_t pass4 = (m0 | m8) & (m4 | m12);           // 0x80 per passing byte
+            // gather bits 7, 15, 23, 31 into a nibble: (x >> 7) has them at 0, 8, 16, 24; the multiply moves them to 24..27
+            flags |= ((((pass4 >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * it);
+        }
+        // exclusive scan of the per-thread counts over the warp, one reservation per warp
+        const int cnt = __popc(flags);
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        int base = 0;
+        if (lane == 31 && incl) base = atomicAdd(&s_nsurv, incl);
+        base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
+        while (flags) {                                             // ~3 survivors per thread on a textured frame
+            const int b = __ffs(flags) - 1;
+            flags &= flags - 1;
+            s_surv[base++] = (uint16_t)((cy0 + (b >> 2) * ROWS_PER_IT) * FT_CW + 4 * j + (b & 3));
         }
     }
     __syncthreads();
@@ -252,6 +261,7 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
 template <int CW>
 __global__ void __launch_bounds__(256)
 fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap, int use_tma) {
+    pdl_grid_sync();
     fast_tile<CW>(sv, level, blockIdx.x, blockIdx.y, blockIdx.z, first_slot, &tmap, use_tma);
 }
 
@@ -259,11 +269,13 @@ fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUt
 template <int CW>
 __global__ void __launch_bounds__(256, 6)
 fast_levels_kernel(StoreView sv, const __grid_constant__ LevelTiles lt, int first_slot, const __grid_constant__ LevelMaps maps, int use_tma) {
+    pdl_grid_sync();
     const TileCoord tc = tile_coord(lt, blockIdx.x);
     fast_tile<CW>(sv, tc.level, tc.bx, tc.by, tc.frame, first_slot, &maps.m[tc.level], use_tma);
 }
 
 __global__ void clear_detect_state_kernel(StoreView sv, int first_slot, int n) {
+    pdl_grid_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int per = kLevels * 256;
     if (i < n * per) {
@@ -285,7 +297,7 @@ __global__ void clear_detect_state_kernel(StoreView sv, int first_slot, int n) {
 int launch_fast(b200vo_ctx* ctx, int first_slot, int n) {
     {
         const int total = n * kLevels * 256;
-        clear_detect_state_kernel<<<div_up(total, 256), 256, 0, ctx->stream>>>(ctx->store, first_slot, n);
+        launch_k(ctx, clear_detect_state_kernel, dim3(div_up(total, 256)), dim3(256), 0, ctx->store, first_slot, n);
         B200VO_LAUNCH_CHECK(ctx);
     }
     const LevelMaps& maps = *reinterpret_cast<const LevelMaps*>(ctx->tmap_fast);
@@ -302,11 +314,11 @@ int launch_fast(b200vo_ctx* ctx, int first_slot, int n) {
     if (n <= kMergedLevelsMaxFrames) {
         // two launches: the wide-tile levels (0..4) and the narrow-tile levels (5..7)
         if (wide.first[kLevels] > 0) {
-            fast_levels_kernel<128><<<wide.first[kLevels], 256, 0, ctx->stream>>>(ctx->store, wide, first_slot, maps, tma);
+            launch_k(ctx, fast_levels_kernel<128>, dim3(wide.first[kLevels]), dim3(256), 0, ctx->store, wide, first_slot, maps, tma);
             B200VO_LAUNCH_CHECK(ctx);
         }
         if (narrow.first[kLevels] > 0) {
-            fast_levels_kernel<64><<<narrow.first[kLevels], 256, 0, ctx->stream>>>(ctx->store, narrow, first_slot, maps, tma);
+            launch_k(ctx, fast_levels_kernel<64>, dim3(narrow.first[kLevels]), dim3(256), 0, ctx->store, narrow, first_slot, maps, tma);
             B200VO_LAUNCH_CHECK(ctx);
         }
         return B200VO_OK;
@@ -317,10 +329,10 @@ int launch_fast(b200vo_ctx* ctx, int first_slot, int n) {
         if (iw <= 0 || ih <= 0) continue;
         if (fast_level_is_wide(l)) {
             dim3 grid(div_up(iw, FastTile<128>::FT_W), div_up(ih, FastTile<128>::FT_H), n);
-            fast_kernel<128><<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], tma);
+            launch_k(ctx, fast_kernel<128>, dim3(grid), dim3(256), 0, ctx->store, l, first_slot, ctx->tmap_fast[l], tma);
         } else {
             dim3 grid(div_up(iw, FastTile<64>::FT_W), div_up(ih, FastTile<64>::FT_H), n);
-            fast_kernel<64><<<grid, 256, 0, ctx->stream>>>(ctx->store, l, first_slot, ctx->tmap_fast[l], tma);
+            launch_k(ctx, fast_kernel<64>, dim3(grid), dim3(256), 0, ctx->store, l, first_slot, ctx->tmap_fast[l], tma);
         }
         B200VO_LAUNCH_CHECK(ctx);
     }

@@ -48,6 +48,7 @@ __device__ __forceinline__ void bitonic_sort_u32(uint32_t* keys, int P, int tid)
 
 __global__ void __launch_bounds__(FL_THREADS)
 filter_kernel(StoreView sv, PairView pv, FilterArgs fa, int P /* pow2 >= kp_cap */) {
+    pdl_grid_sync();
     extern __shared__ uint32_t keys[];             // [P] all candidates | [FL_FAST_CAP] compacted survivors
     uint32_t* sub = keys + P;
     __shared__ int s_hist[288];                    // distance histogram (0..256), padded to 32 lanes x 9 bins
@@ -200,7 +201,7 @@ int launch_filter(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_overri
     fa.mode = ctx->opt.match_mode; fa.ratio = ctx->opt.ratio;
     fa.fast_cap = std::min(std::max(ctx->filter_fast_cap, 0), FL_FAST_CAP);
     fa.fx = ctx->K[0]; fa.fy = ctx->K[1]; fa.cx = ctx->K[2]; fa.cy = ctx->K[3];
-    filter_kernel<<<npairs, FL_THREADS, smem, ctx->stream>>>(ctx->store, ctx->pairs, fa, P);
+    launch_k(ctx, filter_kernel, dim3(npairs), dim3(FL_THREADS), smem, ctx->store, ctx->pairs, fa, P);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }

@@ -97,6 +97,7 @@ __device__ __forceinline__ void resolve_pair(const MatchArgs& a, int pair, const
 template <int R, int CSA>
 __global__ void __launch_bounds__(MT_THREADS)
 match_kernel(MatchArgs a) {
+    pdl_grid_sync();
     __shared__ __align__(16) uint32_t s_t[MT_MAXCHUNK * 8];
     __shared__ uint32_t s_col[MT_MAXCHUNK];
 
@@ -176,6 +177,7 @@ match_kernel(MatchArgs a) {
 template <int R>
 __global__ void __launch_bounds__(MT_THREADS)
 match_knn2_kernel(MatchArgs a) {
+    pdl_grid_sync();
     __shared__ __align__(16) uint32_t s_t[MT_MAXCHUNK * 8];
     const int pair = blockIdx.z;
     const uint8_t* q; const uint8_t* t;
@@ -237,9 +239,9 @@ static int run_match_knn2(b200vo_ctx* ctx, MatchArgs a, int n1max, int n1_expect
     while (R > 1 && (long)div_up(n1_expected, MT_THREADS * R) * npairs < 2 * 148) R >>= 1;
     dim3 grid(1, div_up(n1max, MT_THREADS * R), npairs);
     switch (R) {
-        case 4: match_knn2_kernel<4><<<grid, MT_THREADS, 0, ctx->stream>>>(a); break;
-        case 2: match_knn2_kernel<2><<<grid, MT_THREADS, 0, ctx->stream>>>(a); break;
-        default: match_knn2_kernel<1><<<grid, MT_THREADS, 0, ctx->stream>>>(a); break;
+        case 4: launch_k(ctx, match_knn2_kernel<4>, dim3(grid), dim3(MT_THREADS), 0, a); break;
+        case 2: launch_k(ctx, match_knn2_kernel<2>, dim3(grid), dim3(MT_THREADS), 0, a); break;
+        default: launch_k(ctx, match_knn2_kernel<1>, dim3(grid), dim3(MT_THREADS), 0, a); break;
     }
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
@@ -270,10 +272,10 @@ static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_
     dim3 grid(div_up(n2max, chunk), row_tiles, npairs);
     const int csa = ctx->match_csa;
 #define LAUNCH_MATCH(RR) \
-    do { if (csa == 3) match_kernel<RR, 3><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \
-         else if (csa == 2) match_kernel<RR, 2><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \
-         else if (csa == 1) match_kernel<RR, 1><<<grid, MT_THREADS, 0, ctx->stream>>>(a); \
-         else match_kernel<RR, 0><<<grid, MT_THREADS, 0, ctx->stream>>>(a); } while (0)
+    do { if (csa == 3) launch_k(ctx, match_kernel<RR, 3>, dim3(grid), dim3(MT_THREADS), 0, a); \
+         else if (csa == 2) launch_k(ctx, match_kernel<RR, 2>, dim3(grid), dim3(MT_THREADS), 0, a); \
+         else if (csa == 1) launch_k(ctx, match_kernel<RR, 1>, dim3(grid), dim3(MT_THREADS), 0, a); \
+         else launch_k(ctx, match_kernel<RR, 0>, dim3(grid), dim3(MT_THREADS), 0, a); } while (0)
     switch (R) {
         case 8: LAUNCH_MATCH(8); break;
         case 6: LAUNCH_MATCH(6); break;
@@ -332,6 +334,7 @@ int launch_match_knn2_raw(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8
 // per thread, enough CTAs to fill every SM; reports sustained popc32/s.
 __global__ void __launch_bounds__(256)
 popc_rate_kernel(uint32_t* out, int iters) {
+    pdl_grid_sync();
     uint32_t a[8], acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) { a[k] = threadIdx.x * 2654435761u + k * 40503u + blockIdx.x; acc[k] = 0; }
@@ -352,7 +355,7 @@ int measure_popc_rate(b200vo_ctx* ctx, double* popc_per_second) {
     float best = 1e30f;
     for (int rep = 0; rep < 4; ++rep) {
         B200VO_CUDA_CHECK(cudaEventRecord(ctx->ev[14], ctx->stream));
-        popc_rate_kernel<<<blocks, 256, 0, ctx->stream>>>(d, iters);
+        launch_k(ctx, popc_rate_kernel, dim3(blocks), dim3(256), 0, d, iters);
         B200VO_LAUNCH_CHECK(ctx);
         B200VO_CUDA_CHECK(cudaEventRecord(ctx->ev[15], ctx->stream));
         B200VO_CUDA_CHECK(cudaEventSynchronize(ctx->ev[15]));

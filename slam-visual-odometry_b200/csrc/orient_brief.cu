@@ -56,8 +56,9 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 // grid: (ceil(max level kp / warps per block), kLevels, n); block: 256 threads = 8 warps
 __global__ void __launch_bounds__(256)
 orient_kernel(StoreView sv, int first_slot) {
+    pdl_grid_sync();
     const int level = blockIdx.y;
-    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    const int slot = ring_slot(first_slot, blockIdx.z, sv.slots);
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int* counts = sv.lkp_count + slot * kLevels;
@@ -106,7 +107,8 @@ orient_kernel(StoreView sv, int first_slot) {
 // full warp instruction stream per keypoint; here 32 keypoints share one.)
 __global__ void __launch_bounds__(256)
 keypoint_finalize_kernel(StoreView sv, int first_slot) {
-    const int slot = (first_slot + blockIdx.y) % sv.slots;
+    pdl_grid_sync();
+    const int slot = ring_slot(first_slot, blockIdx.y, sv.slots);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int* counts = sv.lkp_count + slot * kLevels;
     int level = 0, base = 0, total = 0;
@@ -143,7 +145,8 @@ keypoint_finalize_kernel(StoreView sv, int first_slot) {
 // grid: (ceil(kp_cap / 8), n); one warp per keypoint
 __global__ void __launch_bounds__(256)
 brief_kernel(StoreView sv, int first_slot) {
-    const int slot = (first_slot + blockIdx.y) % sv.slots;
+    pdl_grid_sync();
+    const int slot = ring_slot(first_slot, blockIdx.y, sv.slots);
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (i >= sv.kp_count[slot]) return;
@@ -187,23 +190,28 @@ brief_kernel(StoreView sv, int first_slot) {
 // Phase C: warp per keypoint, lane = descriptor byte, the 512 taps read shared memory.  The moments and the
 // rotation never touch global memory (round 1: three kernels, kp_mom / kp_rot round trips, 512 scattered global
 // byte loads per keypoint -- long-scoreboard 43 % in brief_kernel).  The blurred box lands while phases A and B run.
-constexpr int DK_KP = 16, DK_THREADS = 128;
+constexpr int DK_KP = 8, DK_THREADS = 128;          // 32 KB of boxes per CTA: 7 CTAs = 28 warps per SM (16 keypoints / 64 KB: 12 warps,
+                                                    // 33 % of the stall samples at the phase barriers, issue utilisation 39 %)
 constexpr int DK_OBOX = (kOrientBoxW * kOrientBoxH + 127) / 128 * 128;      // 1536: TMA destinations are 128-byte aligned
 constexpr int DK_BBOX = (kBriefBoxW * kBriefBoxH + 127) / 128 * 128;        // 2560
 constexpr int DK_SMEM = DK_KP * (DK_OBOX + DK_BBOX);
 
 __global__ void __launch_bounds__(DK_THREADS)
 describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps maps_pyr, const __grid_constant__ LevelMaps maps_blur) {
+    pdl_grid_sync();
     extern __shared__ __align__(128) uint8_t dk_smem[];
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ int s_x[DK_KP], s_y[DK_KP];
     __shared__ int2 s_mom[DK_KP];
     __shared__ float2 s_rot[DK_KP];
     const int level = blockIdx.y;
-    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    int slot = first_slot + blockIdx.z;                    // blockIdx.z < slots
+    if (slot >= sv.slots) slot -= sv.slots;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int* counts = sv.lkp_count + slot * kLevels;
     const int cnt = counts[level];
+    const int i0 = blockIdx.x * DK_KP;
+    if (i0 >= cnt && !(level == 0 && blockIdx.x == 0)) return;      // most CTAs of the (kp_cap-sized) grid are empty: leave before any arithmetic
     int base = 0, total = 0;
 #pragma unroll
     for (int l = 0; l < kLevels; ++l) {
@@ -215,7 +223,6 @@ describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps 
         if (total > sv.kp_cap) atomicOr(&sv.flags[slot], 8);
         sv.kp_count[slot] = min(total, sv.kp_cap);
     }
-    const int i0 = blockIdx.x * DK_KP;
     const int nk = min(DK_KP, min(cnt - i0, sv.kp_cap - (base + i0)));          // uniform over the CTA
     if (nk <= 0) return;
     const LevelGeom g = sv.lv[level];
@@ -285,11 +292,13 @@ describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps 
     tma::mbar_wait(&s_bar[1], 0);
 
     // ---- phase C: rBRIEF, warp per keypoint, lane = descriptor byte (pattern rows 8*lane .. 8*lane+7)
-    int8_t pat[32];
+    float pat[32];                                         // the lane's 16 pattern points as floats, converted once
     {
         const int4* p = reinterpret_cast<const int4*>(d_pattern + lane * 32);
-        *reinterpret_cast<int4*>(&pat[0]) = p[0];
-        *reinterpret_cast<int4*>(&pat[16]) = p[1];
+        const int4 w0 = p[0], w1 = p[1];
+        const int wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int q = 0; q < 32; ++q) pat[q] = (float)(int)(int8_t)((uint32_t)wv[q >> 2] >> (8 * (q & 3)));
     }
     for (int j = warp; j < nk; j += DK_THREADS / 32) {
         const int sh = (s_x[j] - kBriefReach) & 15;
@@ -298,8 +307,8 @@ describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps 
         uint32_t byte = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1];
-            const float x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
+            const float x0 = pat[4 * k], y0 = pat[4 * k + 1];
+            const float x1 = pat[4 * k + 2], y1 = pat[4 * k + 3];
             const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
             const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
@@ -344,7 +353,7 @@ int launch_describe(b200vo_ctx* ctx, int first_slot, int n) {
     int maxkp = 1;
     for (int l = 0; l < kLevels; ++l) maxkp = max(maxkp, ctx->store.lv[l].kp_cap);
     dim3 grid(div_up(maxkp, DK_KP), kLevels, n);
-    describe_kernel<<<grid, DK_THREADS, DK_SMEM, ctx->stream>>>(ctx->store, first_slot, *reinterpret_cast<const LevelMaps*>(ctx->tmap_orient),
+    launch_k(ctx, describe_kernel, dim3(grid), dim3(DK_THREADS), DK_SMEM, ctx->store, first_slot, *reinterpret_cast<const LevelMaps*>(ctx->tmap_orient),
                                                                *reinterpret_cast<const LevelMaps*>(ctx->tmap_brief));
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
@@ -355,16 +364,16 @@ int launch_orient(b200vo_ctx* ctx, int first_slot, int n) {
     int maxkp = 1;
     for (int l = 0; l < kLevels; ++l) maxkp = max(maxkp, ctx->store.lv[l].kp_cap);
     dim3 grid(div_up(maxkp, 8), kLevels, n);
-    orient_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, first_slot);
+    launch_k(ctx, orient_kernel, dim3(grid), dim3(256), 0, ctx->store, first_slot);
     B200VO_LAUNCH_CHECK(ctx);
-    keypoint_finalize_kernel<<<dim3(div_up(ctx->store.kp_cap, 256), n), 256, 0, ctx->stream>>>(ctx->store, first_slot);
+    launch_k(ctx, keypoint_finalize_kernel, dim3(dim3(div_up(ctx->store.kp_cap, 256), n)), dim3(256), 0, ctx->store, first_slot);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
 
 int launch_brief(b200vo_ctx* ctx, int first_slot, int n) {
     dim3 grid(div_up(ctx->store.kp_cap, 8), n);
-    brief_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, first_slot);
+    launch_k(ctx, brief_kernel, dim3(grid), dim3(256), 0, ctx->store, first_slot);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }

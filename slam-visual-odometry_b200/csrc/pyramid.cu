@@ -17,8 +17,9 @@ namespace b200vo {
 // (3735 B + 19235 G + 9798 R + 2^14) >> 15   
 __global__ void bgr2gray_kernel(StoreView sv, const uint8_t* __restrict__ bgr, size_t pitch, size_t frame_stride,
                                 int first_slot) {
+    pdl_grid_sync();
     const LevelGeom g = sv.lv[0];
-    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    const int slot = ring_slot(first_slot, blockIdx.z, sv.slots);
     const int y = blockIdx.y;
     const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (x >= g.w) return;
@@ -40,6 +41,7 @@ __global__ void bgr2gray_kernel(StoreView sv, const uint8_t* __restrict__ bgr, s
 // tab: xofs[dwp], xc1[dwp], yofs[dhp], yc1[dhp]  (dwp/dhp = sizes padded to 4)
 __global__ void __launch_bounds__(256)
 resize_kernel(StoreView sv, const int* __restrict__ tab, int level, int first_slot) {
+    pdl_grid_sync();
     const LevelGeom gs = sv.lv[level - 1];
     const LevelGeom gd = sv.lv[level];
     const int dwp = (gd.w + 3) & ~3, dhp = (gd.h + 3) & ~3;
@@ -51,7 +53,7 @@ resize_kernel(StoreView sv, const int* __restrict__ tab, int level, int first_sl
     const int x = (blockIdx.x * 32 + threadIdx.x) * 4;
     const int y = blockIdx.y * 8 + threadIdx.y;
     if (x >= gd.w || y >= gd.h) return;
-    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    const int slot = ring_slot(first_slot, blockIdx.z, sv.slots);
     const uint8_t* __restrict__ src = sv.pyr + (size_t)slot * sv.slot_bytes + gs.offset;
     uint8_t* dst = sv.pyr + (size_t)slot * sv.slot_bytes + gd.offset + (size_t)y * gd.pitch + x;
 
@@ -87,6 +89,7 @@ constexpr int RZ_W = 128, RZ_H = 16;
 
 __global__ void __launch_bounds__(256)
 resize_tma_kernel(StoreView sv, const int* __restrict__ tab, int level, int first_slot, const __grid_constant__ CUtensorMap tmap) {
+    pdl_grid_sync();
     __shared__ __align__(128) uint8_t s_src[kResizeBoxH * kResizeBoxW];
     __shared__ __align__(16) uint16_t s_h[kResizeBoxH][RZ_W];
     __shared__ __align__(8) uint64_t s_bar;
@@ -97,7 +100,7 @@ resize_tma_kernel(StoreView sv, const int* __restrict__ tab, int level, int firs
     const int* __restrict__ xc1 = xofs + dwp;
     const int* __restrict__ yofs = xc1 + dwp;
     const int* __restrict__ yc1 = yofs + dhp;
-    const int slot = (first_slot + blockIdx.z) % sv.slots;
+    const int slot = ring_slot(first_slot, blockIdx.z, sv.slots);
     const int x0 = blockIdx.x * RZ_W, y0 = blockIdx.y * RZ_H;
     const int tid = threadIdx.x;
     const int sx0 = xofs[x0] & ~15;
@@ -161,7 +164,7 @@ resize_tma_kernel(StoreView sv, const int* __restrict__ tab, int level, int firs
 int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int first_slot, int n) {
     const LevelGeom& g = ctx->store.lv[0];
     dim3 block(64), grid(div_up(div_up(g.w, 4), 64), g.h, n);
-    bgr2gray_kernel<<<grid, block, 0, ctx->stream>>>(ctx->store, d_bgr, pitch, frame_stride, first_slot);
+    launch_k(ctx, bgr2gray_kernel, dim3(grid), dim3(block), 0, ctx->store, d_bgr, pitch, frame_stride, first_slot);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
@@ -171,10 +174,10 @@ int launch_pyramid(b200vo_ctx* ctx, int first_slot, int n) {
         const LevelGeom& g = ctx->store.lv[l];
         if (ctx->use_tma) {
             dim3 grid(div_up(g.w, RZ_W), div_up(g.h, RZ_H), n);
-            resize_tma_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->store, ctx->d_tab, l, first_slot, ctx->tmap_resize[l - 1]);
+            launch_k(ctx, resize_tma_kernel, dim3(grid), dim3(256), 0, ctx->store, ctx->d_tab, l, first_slot, ctx->tmap_resize[l - 1]);
         } else {
             dim3 block(32, 8), grid(div_up(g.w, 128), div_up(g.h, 8), n);
-            resize_kernel<<<grid, block, 0, ctx->stream>>>(ctx->store, ctx->d_tab, l, first_slot);
+            launch_k(ctx, resize_kernel, dim3(grid), dim3(block), 0, ctx->store, ctx->d_tab, l, first_slot);
         }
         B200VO_LAUNCH_CHECK(ctx);
     }

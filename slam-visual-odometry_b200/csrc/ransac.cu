@@ -116,6 +116,7 @@ __device__ __forceinline__ void fpg_solve(const PairView& pv, const RansacArgs& 
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 five_point_group_kernel(PairView pv, RansacArgs ra) {
+    pdl_grid_sync();
     constexpr int GROUPS = 3 * (THREADS / 32);
     extern __shared__ __align__(16) unsigned char fpg_smem[];
     __shared__ int s_nroot;
@@ -132,6 +133,7 @@ five_point_group_kernel(PairView pv, RansacArgs ra) {
 template <int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 five_point_deferred_kernel(PairView pv, RansacArgs ra) {
+    pdl_grid_sync();
     constexpr int GROUPS = 3 * (THREADS / 32);
     extern __shared__ __align__(16) unsigned char fpg_smem[];
     __shared__ int s_nroot;
@@ -154,12 +156,12 @@ five_point_deferred_kernel(PairView pv, RansacArgs ra) {
 // `floor_count`: the scan stops as soon as even all remaining points could not lift the model to
 // floor_count inliers (it then can neither win nor tie; the returned count is a lower bound).
 template <bool STAGED>
-__device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, int m, const double* E, const float4* __restrict__ xf,
-                                                  const geom::SampsonThreshold& thr, int lane, int floor_count) {
+__device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, int m, const double* E, const float* __restrict__ Ef,
+                                                  const float4* __restrict__ xf, const geom::SampsonThreshold& thr, int lane, int floor_count) {
     const size_t base = (size_t)pair * pv.kp_cap;
     float e[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) e[k] = (float)E[k];
+    for (int k = 0; k < 9; ++k) e[k] = Ef[k];
     const float tmid = (float)thr.tmid;
     int cnt = 0;
     for (int i0 = 0; i0 < m; i0 += 32) {
@@ -193,8 +195,10 @@ __device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, 
 // stall samples were long-scoreboard, issue utilisation 26 %).
 // K15: arg-max with "first model wins" through one 64-bit atomicMax on (count << 32 | ~model index).
 // Models are abandoned as soon as they cannot reach the best count known so far (exact: such a model can neither
-// win nor tie).  The floor is the CTA's own best (shared memory) joined with the pair's global best as read one
-// model earlier -- a stale floor only abandons later, never wrongly.
+// win nor tie).  The floor is the CTA's own best (shared memory), seeded with the pair's global best at CTA start --
+// a stale floor only abandons later, never wrongly.  E is kept twice in shared memory: double for the exact
+// re-evaluation inside the threshold band, float (converted once at staging) for the scoring loop -- the per-model
+// double->float conversions were 13 % of the kernel's instructions.
 constexpr int SC_THREADS = 256;
 constexpr int SC_HB = 32;
 constexpr int SC_MAXPTS = 2048;                            // staging capacity: 32 KB of float4 (pairs with more good matches read global memory)
@@ -202,6 +206,7 @@ constexpr int SC_SLOTS = SC_HB * kMaxSolutions;
 
 __global__ void __launch_bounds__(SC_THREADS)
 score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
+    pdl_grid_sync();
     extern __shared__ __align__(16) unsigned char sc_smem[];
     __shared__ int s_n, s_best;
     __shared__ unsigned short s_slot[SC_SLOTS];
@@ -212,11 +217,12 @@ score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
     const int hb0 = ra.h0 + blockIdx.x * SC_HB;
     const int hb1 = min(hb0 + SC_HB, ra.h0 + ra.nround);
     const int tid = threadIdx.x;
-    double* s_E = reinterpret_cast<double*>(sc_smem);                      // [SC_SLOTS][9]
-    float4* s_pts = reinterpret_cast<float4*>(sc_smem + SC_SLOTS * 9 * sizeof(double));
+    double* s_E = reinterpret_cast<double*>(sc_smem);                      // [SC_SLOTS][9] (exact re-evaluation inside the threshold band)
+    float* s_Ef = reinterpret_cast<float*>(sc_smem + SC_SLOTS * 9 * sizeof(double));   // [SC_SLOTS][9] the same rounded to float, converted once
+    float4* s_pts = reinterpret_cast<float4*>(sc_smem + SC_SLOTS * 9 * (sizeof(double) + sizeof(float)));
     const float4* xf = pv.xf + (size_t)pair * pv.kp_cap;
     const bool staged = m <= stage_cap;                    // uniform over the CTA
-    if (tid == 0) { s_n = 0; s_best = 0; }
+    if (tid == 0) { s_n = 0; s_best = pv.counts ? 0 : (int)(pv.best[pair] >> 32); }
     __syncthreads();
     const size_t slot0 = ((size_t)pair * pv.nhyp_cap + hb0) * kMaxSolutions;
     const int nslots = (hb1 - hb0) * kMaxSolutions;
@@ -230,29 +236,29 @@ score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
     const int n = s_n;
     for (int i = tid; i < n * 9; i += SC_THREADS) {
         const int j = i / 9, k = i - j * 9;
-        s_E[i] = pv.models[(slot0 + s_slot[j]) * 9 + k];
+        const double v = pv.models[(slot0 + s_slot[j]) * 9 + k];
+        s_E[i] = v;
+        s_Ef[i] = (float)v;
     }
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
     const geom::SampsonThreshold thr = geom::make_sampson_threshold(ra.thr2f);
-    const volatile unsigned long long* gbest = &pv.best[pair];
-    int gfloor = pv.counts ? 0 : (int)(*gbest >> 32);
     for (int j = warp; j < n; j += SC_THREADS / 32) {
         const int slot = s_slot[j];
-        const int floor_count = pv.counts ? 0 : max(gfloor, *(volatile int*)&s_best);
-        const unsigned long long gnext = *gbest;           // consumed by the NEXT model: its latency hides behind this one
-        const double* E = s_E + j * 9;
-        const int cnt = staged ? warp_count_inliers<true>(pv, pair, m, E, xf, thr, lane, floor_count)
-                               : warp_count_inliers<false>(pv, pair, m, E, xf, thr, lane, floor_count);
+        // the floor: the best count this CTA knows of -- the pair's global best when the CTA started and its own models
+        // since.  No global read inside the loop: the round-2 profile of the first staged version showed the per-model
+        // read of the global best (L2 round trip, consumed one model later) as 62 % of all stall samples.
+        const int floor_count = pv.counts ? 0 : *(volatile int*)&s_best;
+        const int cnt = staged ? warp_count_inliers<true>(pv, pair, m, s_E + j * 9, s_Ef + j * 9, xf, thr, lane, floor_count)
+                               : warp_count_inliers<false>(pv, pair, m, s_E + j * 9, s_Ef + j * 9, xf, thr, lane, floor_count);
         if (lane == 0) {
             if (pv.counts) pv.counts[slot0 + slot] = cnt;
             if (cnt >= floor_count) {
                 const uint32_t model = (uint32_t)(hb0 * kMaxSolutions + slot);            // = h * 10 + s
-                atomicMax(&pv.best[pair], ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - model));
+                atomicMax(&pv.best[pair], ((unsigned long long)(uint32_t)cnt << 32) | (unsigned long long)(0xFFFFFFFFu - model));   // no return value used: a RED, nobody waits
                 atomicMax(&s_best, cnt);
             }
         }
-        gfloor = (int)(gnext >> 32);
     }
 }
 
@@ -260,11 +266,11 @@ template <int THREADS, int MINB>
 static int launch_five_point_as(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     constexpr int GROUPS = 3 * (THREADS / 32);
     const size_t smem = GROUPS * sizeof(geom::GroupShared);
-    five_point_group_kernel<THREADS, MINB><<<dim3(div_up(ra.nround, GROUPS), npairs), THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
+    launch_k(ctx, five_point_group_kernel<THREADS, MINB>, dim3(dim3(div_up(ra.nround, GROUPS), npairs)), dim3(THREADS), smem, ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
     // the queue length is only known on the device (measured share: 0.5-6 %): the grid covers the worst
     // case, CTAs beyond the queue exit at once
-    five_point_deferred_kernel<THREADS, MINB><<<div_up(npairs * ra.nround, GROUPS), THREADS, smem, ctx->stream>>>(ctx->pairs, ra);
+    launch_k(ctx, five_point_deferred_kernel<THREADS, MINB>, dim3(div_up(npairs * ra.nround, GROUPS)), dim3(THREADS), smem, ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
@@ -284,13 +290,13 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
 static int launch_score(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     const dim3 grid(div_up(ra.nround, SC_HB), npairs);
     const int cap = std::min(ctx->pairs.kp_cap, SC_MAXPTS);
-    score_kernel<<<grid, SC_THREADS, SC_SLOTS * 9 * sizeof(double) + (size_t)cap * sizeof(float4), ctx->stream>>>(ctx->pairs, ra, cap);
+    launch_k(ctx, score_kernel, dim3(grid), dim3(SC_THREADS), SC_SLOTS * 9 * (sizeof(double) + sizeof(float)) + (size_t)cap * sizeof(float4), ctx->pairs, ra, cap);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
 
 int init_ransac_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_SLOTS * 9 * sizeof(double) + SC_MAXPTS * sizeof(float4)));
+    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_SLOTS * 9 * (sizeof(double) + sizeof(float)) + SC_MAXPTS * sizeof(float4)));
     auto fpg_attr = [&](auto main_k, auto def_k, int threads) {
         const int bytes = 3 * (threads / 32) * (int)sizeof(geom::GroupShared);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(main_k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -307,6 +313,7 @@ int init_ransac_kernels() {
 
 __global__ void __launch_bounds__(256)
 finalize_kernel(PairView pv, RansacArgs ra) {
+    pdl_grid_sync();
     const int pair = blockIdx.x;
     const int tid = threadIdx.x;
     const int m = pv.n_good[pair];
@@ -377,6 +384,7 @@ struct PoseArgs { int min_valid, min_inliers; uint8_t* mask_out; /* [pairs][kp_c
 //   pose_select_kernel     thread / pair           first maximum wins -> record
 __global__ void __launch_bounds__(64)
 pose_decompose_kernel(PairView pv, int npairs) {
+    pdl_grid_sync();
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair >= npairs) return;
     int* cnt = pv.pose_cnt + pair * 4;
@@ -389,6 +397,7 @@ pose_decompose_kernel(PairView pv, int npairs) {
 // thread = (point, candidate): 4x the threads, a quarter of the serial latency per thread
 __global__ void __launch_bounds__(128)
 pose_vote_kernel(PairView pv) {
+    pdl_grid_sync();
     const int pair = blockIdx.y;
     if (!(pv.rec[pair].status & B200VO_ST_E_FOUND)) return;
     const int m = pv.n_good[pair];
@@ -418,6 +427,7 @@ pose_vote_kernel(PairView pv) {
 
 __global__ void __launch_bounds__(64)
 pose_select_kernel(PairView pv, PoseArgs pa, int npairs) {
+    pdl_grid_sync();
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair >= npairs) return;
     b200vo_pose_record* rec = pv.rec + pair;
@@ -437,6 +447,7 @@ pose_select_kernel(PairView pv, PoseArgs pa, int npairs) {
 
 // parity hook only: cv::recoverPose overwrites the mask with the winning candidate's test
 __global__ void pose_mask_kernel(PairView pv, PoseArgs pa) {
+    pdl_grid_sync();
     const int pair = blockIdx.y;
     const b200vo_pose_record* rec = pv.rec + pair;
     if (!(rec->status & B200VO_ST_E_FOUND)) return;
@@ -450,14 +461,14 @@ __global__ void pose_mask_kernel(PairView pv, PoseArgs pa) {
 
 int launch_recover_pose_masked(b200vo_ctx* ctx, int npairs, uint8_t* d_mask_out) {
     PoseArgs pa{ctx->opt.min_valid_points, ctx->opt.min_inliers, d_mask_out};
-    pose_decompose_kernel<<<div_up(npairs, 64), 64, 0, ctx->stream>>>(ctx->pairs, npairs);
+    launch_k(ctx, pose_decompose_kernel, dim3(div_up(npairs, 64)), dim3(64), 0, ctx->pairs, npairs);
     B200VO_LAUNCH_CHECK(ctx);
-    pose_vote_kernel<<<dim3(div_up(4 * ctx->pairs.kp_cap, 128), npairs), 128, 0, ctx->stream>>>(ctx->pairs);
+    launch_k(ctx, pose_vote_kernel, dim3(dim3(div_up(4 * ctx->pairs.kp_cap, 128), npairs)), dim3(128), 0, ctx->pairs);
     B200VO_LAUNCH_CHECK(ctx);
-    pose_select_kernel<<<div_up(npairs, 64), 64, 0, ctx->stream>>>(ctx->pairs, pa, npairs);
+    launch_k(ctx, pose_select_kernel, dim3(div_up(npairs, 64)), dim3(64), 0, ctx->pairs, pa, npairs);
     B200VO_LAUNCH_CHECK(ctx);
     if (d_mask_out) {
-        pose_mask_kernel<<<dim3(div_up(ctx->pairs.kp_cap, 128), npairs), 128, 0, ctx->stream>>>(ctx->pairs, pa);
+        launch_k(ctx, pose_mask_kernel, dim3(dim3(div_up(ctx->pairs.kp_cap, 128), npairs)), dim3(128), 0, ctx->pairs, pa);
         B200VO_LAUNCH_CHECK(ctx);
     }
     return B200VO_OK;
@@ -488,6 +499,7 @@ __device__ __forceinline__ int ransac_update_num_iters(double p, double ep, int 
 
 // adaptive mode: after each block of hypotheses decide per pair whether OpenCV's loop would have ended
 __global__ void adaptive_update_kernel(PairView pv, int npairs, int evaluated, int max_iters, double confidence) {
+    pdl_grid_sync();
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair >= npairs || pv.done[pair]) return;
     pv.rounds[pair] += 1;
@@ -499,6 +511,7 @@ __global__ void adaptive_update_kernel(PairView pv, int npairs, int evaluated, i
 }
 
 __global__ void stamp_rounds_kernel(PairView pv, int npairs) {
+    pdl_grid_sync();
     const int pair = blockIdx.x * blockDim.x + threadIdx.x;
     if (pair < npairs) pv.rec[pair].status |= (pv.rounds[pair] & 0xFF) << B200VO_ST_ROUNDS_SHIFT;
 }
@@ -527,14 +540,14 @@ int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int3
         { const int rc = launch_score(ctx, ra, npairs); if (rc) return rc; }
         if (tm) cudaEventRecord(ctx->ev[10], ctx->stream);
         if (ra.adaptive) {
-            adaptive_update_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(ctx->pairs, npairs, h0 + ra.nround, nhyp, 0.999);
+            launch_k(ctx, adaptive_update_kernel, dim3(div_up(npairs, 128)), dim3(128), 0, ctx->pairs, npairs, h0 + ra.nround, nhyp, 0.999);
             B200VO_LAUNCH_CHECK(ctx);
         }
     }
-    finalize_kernel<<<npairs, 256, 0, ctx->stream>>>(ctx->pairs, ra);
+    launch_k(ctx, finalize_kernel, dim3(npairs), dim3(256), 0, ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
     if (ra.adaptive) {
-        stamp_rounds_kernel<<<div_up(npairs, 128), 128, 0, ctx->stream>>>(ctx->pairs, npairs);
+        launch_k(ctx, stamp_rounds_kernel, dim3(div_up(npairs, 128)), dim3(128), 0, ctx->pairs, npairs);
         B200VO_LAUNCH_CHECK(ctx);
     }
     return B200VO_OK;
@@ -542,18 +555,21 @@ int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int3
 
 // ------------------------------------------------------------------ parity hooks (device side)
 __global__ void score_models_kernel(PairView pv, const double* models, int nmodels, float thr2f, int* counts) {
+    pdl_grid_sync();
     const int w = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (w >= nmodels) return;
     double E[9];
     for (int k = 0; k < 9; ++k) E[k] = models[(size_t)w * 9 + k];
     const geom::SampsonThreshold thr = geom::make_sampson_threshold(thr2f);
-    const int cnt = warp_count_inliers<false>(pv, 0, pv.n_good[0], E, pv.xf, thr, lane, 0);      // points staged in pair 0
+    float Ef[9];
+    for (int k = 0; k < 9; ++k) Ef[k] = (float)E[k];
+    const int cnt = warp_count_inliers<false>(pv, 0, pv.n_good[0], E, Ef, pv.xf, thr, lane, 0);      // points staged in pair 0
     if (lane == 0) counts[w] = cnt;
 }
 
 int launch_score_models(b200vo_ctx* ctx, const double* d_models, int nmodels, float thr2f, int* d_counts) {
-    score_models_kernel<<<div_up(nmodels, 8), 256, 0, ctx->stream>>>(ctx->pairs, d_models, nmodels, thr2f, d_counts);
+    launch_k(ctx, score_models_kernel, dim3(div_up(nmodels, 8)), dim3(256), 0, ctx->pairs, d_models, nmodels, thr2f, d_counts);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }

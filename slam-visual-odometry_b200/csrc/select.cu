@@ -113,9 +113,10 @@ __device__ __forceinline__ float harris_at(const uint8_t* __restrict__ img, int 
 
 __global__ void __launch_bounds__(SEL_THREADS)
 select_kernel(StoreView sv, int first_slot) {
+    pdl_grid_sync();
     extern __shared__ __align__(8) unsigned char smem_raw[];
     const int level = blockIdx.x;
-    const int slot = (first_slot + blockIdx.y) % sv.slots;
+    const int slot = ring_slot(first_slot, blockIdx.y, sv.slots);
     const LevelGeom g = sv.lv[level];
     int P2 = 64;                                         // power of two >= kp_cap of this level
     while (P2 < g.kp_cap) P2 <<= 1;
@@ -249,7 +250,7 @@ int launch_select(b200vo_ctx* ctx, int first_slot, int n) {
         configured = smem;
     }
     dim3 grid(kLevels, n);
-    select_kernel<<<grid, SEL_THREADS, smem, ctx->stream>>>(ctx->store, first_slot);
+    launch_k(ctx, select_kernel, dim3(grid), dim3(SEL_THREADS), smem, ctx->store, first_slot);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
