@@ -14,7 +14,8 @@
 
 namespace b200vo {
 
-// Tile geometry: 62x30 outputs -> a 64x32 score tile (1-px NMS halo) -> a 70x38 pixel tile (+3 ring).
+// Tile geometry: 60x30 outputs -> a 64x32 score tile (NMS halo; cell 0 sits on a 4-byte aligned pixel column, so the
+// pre-test reads aligned words: the halo is 3 cells on the left, 1 on the right) -> a 70x38 pixel tile (+3 ring).
 // The pixel tile is fetched as aligned 32-bit words (row of 20 words; `shift` = misalignment of the
 // tile origin), so staging costs ~4 instructions per pixel instead of one byte load each.
 // Two tile widths: the wide one (126 outputs) for the large levels -- its survivor / corner lists are
@@ -23,7 +24,7 @@ namespace b200vo {
 template <int CW>
 struct FastTile {
     static constexpr int FT_CW = CW, FT_CH = 32;                 // score tile
-    static constexpr int FT_W = CW - 2, FT_H = FT_CH - 2;        // outputs
+    static constexpr int FT_W = CW - 4, FT_H = FT_CH - 2;        // outputs: cells 3 .. FT_W + 2 of a row, rows 1 .. FT_H
     static constexpr int FT_SW = (CW + 6 + 15 + 15) / 16 * 16;   // pixel tile row bytes: CW + 6 ring + <= 15 alignment shift, x16
     static constexpr int FT_SWW = FT_SW / 4;
     static constexpr int FT_SH = FT_CH + 6;                      // 38 rows
@@ -73,8 +74,9 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
     const uint8_t* __restrict__ img = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset;
     const int ox = kEdge + bx * FT_W;       // first output pixel of the tile
     const int oy = kEdge + by * FT_H;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int px0 = ox - 4, py0 = oy - 4;           // pixel-tile origin (>= 27: always inside the image)
+    const int tid = threadIdx.x, lane = tid & 31;
+    // score-tile cell (cx, cy) <-> pixel (ox - 3 + cx, oy - 1 + cy): ox - 3 = 28 + bx * FT_W is a multiple of 4
+    const int px0 = ox - 6, py0 = oy - 4;           // pixel-tile origin (>= 25: always inside the image)
     // TMA needs a 16-byte aligned inner coordinate, the word-load path a 4-byte aligned one
     const int x0 = use_tma ? (px0 & ~15) : (px0 & ~3), shift = px0 - x0;
     if (tid == 0) { s_nsurv = 0; s_ncorn = 0; s_n = 0; }
@@ -130,14 +132,10 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
         for (int it = 0; it < ITERS; ++it) {
             const int cy = cy0 + it * ROWS_PER_IT;
             const int bc = obyte + 4 * j;                            // first of the four centres
-            const uint32_t* rc = s32 + (cy + 3) * FT_SWW;
-            auto ld4 = [](const uint32_t* row, int byte) -> uint32_t {
-                const int w = byte >> 2;
-                return __funnelshift_r(row[w], row[w + 1], (byte & 3) * 8);
-            };
-            const uint32_t c = ld4(rc, bc);
-            const uint32_t r4 = ld4(rc, bc + 3), r12 = ld4(rc, bc - 3);
-            const uint32_t r0 = ld4(rc + 3 * FT_SWW, bc), r8 = ld4(rc - 3 * FT_SWW, bc);
+            const uint32_t* rc = s32 + (cy + 3) * FT_SWW + (bc >> 2);   // bc is a multiple of 4: the four centres are one aligned word
+            const uint32_t c = rc[0];
+            const uint32_t r4 = __funnelshift_r(c, rc[1], 24), r12 = __funnelshift_r(rc[-1], c, 8);      // the same row, +3 / -3 bytes
+            const uint32_t r0 = rc[3 * FT_SWW], r8 = rc[-3 * FT_SWW];
             auto gt_t = [&](uint32_t x) -> uint32_t {                // 0x80 in every byte with x > t
                 const uint32_t sm = (x & 0x7F7F7F7Fu) + kadd;        // no carry between bytes
                 return (t_hi ? (sm & x) : (sm | x)) & 0x80808080u;
@@ -232,8 +230,8 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
     for (int k = tid; k < ncorn; k += 256) {
         const int cell = s_corn[k] & 0x7FFF;
         const int cy = cell / FT_CW, cx = cell - cy * FT_CW;
-        if (cx < 1 || cx > FT_W || cy < 1 || cy > FT_H) continue;       // halo cells only feed their neighbours
-        const int gx = ox + cx - 1, gy = oy + cy - 1;
+        if (cx < 3 || cx > FT_W + 2 || cy < 1 || cy > FT_H) continue;   // halo cells only feed their neighbours
+        const int gx = ox + cx - 3, gy = oy + cy - 1;
         if (gx >= xmax || gy >= ymax) continue;
         const uint8_t* s = &s_score[cell];
         const int sc = s[0];

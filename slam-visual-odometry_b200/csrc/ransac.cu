@@ -113,7 +113,10 @@ __device__ __forceinline__ void fpg_solve(const PairView& pv, const RansacArgs& 
     }
 }
 
-template <int THREADS, int MINB>
+// INLINE_EXACT (small batches, i.e. the per-frame streaming step): a group whose Sturm chain is unreliable runs the
+// exact path right here instead of being queued -- the same function on the same inputs as the deferred launch, so
+// the result is identical; with one pair in flight a straggler warp costs nothing, a second dependent launch ~90 us.
+template <int THREADS, int MINB, bool INLINE_EXACT>
 __global__ void __launch_bounds__(THREADS, MINB)
 five_point_group_kernel(PairView pv, RansacArgs ra) {
     pdl_grid_sync();
@@ -127,7 +130,7 @@ five_point_group_kernel(PairView pv, RansacArgs ra) {
     const int lane = threadIdx.x & 31, slot = (threadIdx.x >> 5) * 3 + min(lane / geom::kGroupLanes, 2);
     const int h = ra.h0 + blockIdx.x * GROUPS + slot;
     const bool in_range = (lane < 3 * geom::kGroupLanes) && (h < ra.h0 + ra.nround);
-    fpg_solve<THREADS, false>(pv, ra, reinterpret_cast<geom::GroupShared*>(fpg_smem), &s_nroot, s_gid, s_root, in_range, pair, h);
+    fpg_solve<THREADS, INLINE_EXACT>(pv, ra, reinterpret_cast<geom::GroupShared*>(fpg_smem), &s_nroot, s_gid, s_root, in_range, pair, h);
 }
 
 template <int THREADS, int MINB>
@@ -266,7 +269,12 @@ template <int THREADS, int MINB>
 static int launch_five_point_as(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     constexpr int GROUPS = 3 * (THREADS / 32);
     const size_t smem = GROUPS * sizeof(geom::GroupShared);
-    launch_k(ctx, five_point_group_kernel<THREADS, MINB>, dim3(dim3(div_up(ra.nround, GROUPS), npairs)), dim3(THREADS), smem, ctx->pairs, ra);
+    if (THREADS == 256 && MINB == 2 && npairs <= kMergedLevelsMaxFrames) {
+        launch_k(ctx, five_point_group_kernel<256, 2, true>, dim3(dim3(div_up(ra.nround, GROUPS), npairs)), dim3(THREADS), smem, ctx->pairs, ra);
+        B200VO_LAUNCH_CHECK(ctx);
+        return B200VO_OK;
+    }
+    launch_k(ctx, five_point_group_kernel<THREADS, MINB, false>, dim3(dim3(div_up(ra.nround, GROUPS), npairs)), dim3(THREADS), smem, ctx->pairs, ra);
     B200VO_LAUNCH_CHECK(ctx);
     // the queue length is only known on the device (measured share: 0.5-6 %): the grid covers the worst
     // case, CTAs beyond the queue exit at once
@@ -279,10 +287,10 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
     // launch shape (threads x CTAs/SM -> register cap), measured on B200 at 1000 frames, H = 1024 -- see DESIGN.md section 4
     B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.fb_count, 0, sizeof(unsigned), ctx->stream));
     switch (ctx->fpg_variant) {
-        case 1: return launch_five_point_as<192, 2>(ctx, ra, npairs);      // 168 registers: no spills, 12 warps/SM
-        case 2: return launch_five_point_as<256, 3>(ctx, ra, npairs);      // 80 registers: 24 warps/SM, spills
-        case 3: return launch_five_point_as<128, 4>(ctx, ra, npairs);      // 128 registers, smaller CTAs
-        case 4: return launch_five_point_as<160, 3>(ctx, ra, npairs);      // 136 registers, 15 warps/SM
+        // measured per 250 pairs x 1024 hypotheses (profiles/fpg_variants_r02.jsonl): 256x2 1.42 ms; 192x2 (168 registers, a
+        // third of the spills) 1.64; 256x3 (80 registers) 1.75; 128x4 1.68; 160x3 1.70
+        case 1: return launch_five_point_as<192, 2>(ctx, ra, npairs);
+        case 3: return launch_five_point_as<128, 4>(ctx, ra, npairs);
         default: return launch_five_point_as<256, 2>(ctx, ra, npairs);     // 128 registers, 16 warps/SM
     }
 }
@@ -302,11 +310,10 @@ int init_ransac_kernels() {
         if (e == cudaSuccess) e = cudaFuncSetAttribute(main_k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(def_k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     };
-    fpg_attr(five_point_group_kernel<256, 2>, five_point_deferred_kernel<256, 2>, 256);
-    fpg_attr(five_point_group_kernel<192, 2>, five_point_deferred_kernel<192, 2>, 192);
-    fpg_attr(five_point_group_kernel<256, 3>, five_point_deferred_kernel<256, 3>, 256);
-    fpg_attr(five_point_group_kernel<128, 4>, five_point_deferred_kernel<128, 4>, 128);
-    fpg_attr(five_point_group_kernel<160, 3>, five_point_deferred_kernel<160, 3>, 160);
+    fpg_attr(five_point_group_kernel<256, 2, false>, five_point_deferred_kernel<256, 2>, 256);
+    fpg_attr(five_point_group_kernel<256, 2, true>, five_point_deferred_kernel<256, 2>, 256);
+    fpg_attr(five_point_group_kernel<192, 2, false>, five_point_deferred_kernel<192, 2>, 192);
+    fpg_attr(five_point_group_kernel<128, 4, false>, five_point_deferred_kernel<128, 4>, 128);
     if (e != cudaSuccess) { set_error("ransac kernel smem attribute: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
     return B200VO_OK;
 }

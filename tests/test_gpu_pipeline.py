@@ -378,3 +378,27 @@ def test_group_on_two_gpus_is_byte_identical_and_uses_nccl(built, seq, records):
         lib.vo_host_destroy(h)
     assert out["multi"].tobytes() == out["single"].tobytes()
     assert np.allclose(out["single"][1:], built.chain_trajectory(batched), atol=1e-15)
+
+
+def test_large_batch_path_equals_small_batch_path(built):
+    """Batches of more than 16 pairs queue the hypotheses that need the exact root path for a second dense
+    launch; smaller batches (the per-frame streaming step) solve them inline in the main five-point kernel, run
+    FAST / blur as one launch over all pyramid levels and use programmatic dependent launches.  Both ways must
+    give byte-identical records: 24 frames in one batch against the same pairs one at a time."""
+    from b200vo import synth
+    n = 24
+    frames = synth.make_sequence(640, 240, n, device="cuda")[0].cpu().numpy()
+    with built.Context(640, 240, nfeatures=1500, max_frames=n + 1, ransac_hypotheses=512) as ctx:
+        ctx.upload_frames(frames, 0)
+        ctx.detect(0, n)
+        big = ctx.process_pairs(0, n - 1, 100)
+        feats_big = [ctx.get_features(s) for s in (0, n - 1)]
+        one = np.concatenate([ctx.process_pairs(i, 1, 100 + i) for i in range(n - 1)])
+        for i in (0, n - 1):                       # detection in a batch of one (merged-level launches) vs the batch of 24
+            ctx.upload_frames(frames[i:i + 1], i)
+            ctx.detect(i, 1)
+        feats_one = [ctx.get_features(s) for s in (0, n - 1)]
+    assert big.tobytes() == one.tobytes()
+    for (ka, da), (kb, db) in zip(feats_big, feats_one):
+        assert ka.tobytes() == kb.tobytes() and np.array_equal(da, db)
+    assert (big["status"] & 2).all()
