@@ -291,7 +291,9 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
                 if (std::min(yo[yl] + 1, s.h - 1) - yo[y0] + 1 > kResizeBoxH) { set_error("resize footprint exceeds the TMA box (height)"); b200vo_destroy(ctx); return B200VO_ERR_BAD_ARG; }
             }
         }
-        TRY(dev_alloc(ctx, &ctx->d_tab, (size_t)tab_total));
+        // resize_tma_kernel loads the taps of a whole 128-column tile as int4 even where the tile overhangs the level
+        // (values discarded): keep 128 spare entries behind the last table so that read stays inside the allocation
+        TRY(dev_alloc(ctx, &ctx->d_tab, (size_t)tab_total + 256));
         TRYCUDA(cudaMemcpy(ctx->d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice));
     }
     {   // TMA descriptors

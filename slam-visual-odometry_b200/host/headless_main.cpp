@@ -3,6 +3,7 @@
 //     image -> Frame(i, image) -> timestamp from the file stem -> VisualOdometry::process_frame
 // once per frame exactly as src/main.cpp:128-155 does; then write the trajectory as text instead of
 // screenshots.  `--batched` uses the process_sequence extension (same poses, launch batches).
+#include <cctype>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -25,6 +26,17 @@ int main(int argc, char** argv) {
     std::vector<std::string> paths;
     try { paths = load_image_paths(dir); } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
     if (paths.empty()) { std::fprintf(stderr, "No images found in dataset directory: %s\n", dir.c_str()); return 1; }      // main.cpp:92-95
+    // load_image_paths lists what the reference lists (png / jpg / jpeg, src/main.cpp:26-49) plus Netpbm; this build has no
+    // image codecs, so a directory it cannot read completely is refused up front instead of silently pairing other frames
+    for (const std::string& p : paths) {
+        const size_t dot = p.find_last_of('.');
+        std::string ext = dot == std::string::npos ? "" : p.substr(dot + 1);
+        for (char& c : ext) c = (char)std::tolower((unsigned char)c);
+        if (ext != "pgm" && ext != "ppm" && ext != "pnm") {
+            std::fprintf(stderr, "%s: this build decodes binary Netpbm (P5/P6) only -- convert the sequence, or build with OpenCV and use cv::imread\n", p.c_str());
+            return 1;
+        }
+    }
     const cv::Mat first = read_pnm(paths[0]);
     if (first.empty()) { std::fprintf(stderr, "Failed to load first image: %s (this build decodes P5/P6 only)\n", paths[0].c_str()); return 1; }
     try {

@@ -77,3 +77,9 @@ extern "C" int hs_dbg_group(const double* x1, const double* x2, double* c, doubl
     flags[4] = okc;
     return nf;
 }
+// 1 per point when the adjugate iteration of the DLT null vector converged (0: one-sided Jacobi path)
+extern "C" int hs_cheirality_fast_path(const double* R, const double* t, const double* x1, const double* x2, int n, unsigned char* fast) {
+    int c = 0;
+    for (int i = 0; i < n; ++i) { fast[i] = (unsigned char)cheirality_fast_path(R, t, x1[2*i], x1[2*i+1], x2[2*i], x2[2*i+1]); c += fast[i]; }
+    return c;
+}

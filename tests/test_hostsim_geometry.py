@@ -123,3 +123,36 @@ def test_cooperative_solver_shared_block_layout(hs):
     warp touch disjoint banks when they read the same member)."""
     n = hs.hs_group_shared_bytes()
     assert n % 16 == 0 and n % 128 == 112 and n <= 4096
+
+
+def test_dlt_null_vector_by_adjugate_equals_svd(hs):
+    """cheirality_ok takes the DLT null vector from three products with adj(G^T G) and CHECKS convergence (the
+    Jacobi SVD remains for points that fail it).  Against the oracle's numpy-SVD triangulation: identical
+    cheirality masks over scenes from comfortable to no parallax (depth up to 2000 baselines), with pixel noise,
+    for all four (R, t) candidates; and the fast path must actually carry the triangulable points."""
+    rng = np.random.default_rng(17)
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    th = 0.04
+    R = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]])
+    t = np.array([0.2, -0.1, 1.0]); t /= np.linalg.norm(t)
+    fast_total = n_total = 0
+    for zmax, noise in ((15, 0.0), (40, 8e-4), (300, 8e-4), (2000, 8e-4), (2000, 0.0)):
+        n = 600
+        X = np.c_[rng.uniform(-4, 4, n), rng.uniform(-2, 2, n), rng.uniform(2, zmax, n)]
+        X[::7, 2] *= -1                                           # some points behind the first camera
+        Y = X @ R.T + t
+        x1 = np.ascontiguousarray(X[:, :2] / X[:, 2:] + rng.normal(0, noise, (n, 2)))
+        x2 = np.ascontiguousarray(Y[:, :2] / Y[:, 2:] + rng.normal(0, noise, (n, 2)))
+        tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+        R1, R2, tt = G.decompose_essential(tx @ R)              # the four candidates recoverPose votes on
+        for Rc, tc in ((R1, tt), (R2, tt), (R1, -tt), (R2, -tt)):
+            Rc = np.ascontiguousarray(Rc); tc = np.ascontiguousarray(tc)
+            ok = np.zeros(n, np.uint8); fast = np.zeros(n, np.uint8)
+            hs.hs_cheirality(P(Rc), P(tc), P(x1), P(x2), n, ctypes.c_double(50.0), P(ok))
+            nf = hs.hs_cheirality_fast_path(P(Rc), P(tc), P(x1), P(x2), n, P(fast))
+            if zmax <= 40:                                        # triangulable scenes: the fast path must carry them
+                fast_total += nf
+                n_total += n
+            ref = G.cheirality_mask(Rc, tc, x1, x2)
+            assert np.array_equal(ok.astype(bool), ref), (zmax, noise, int((ok.astype(bool) != ref).sum()))
+    assert fast_total >= 0.98 * n_total, (fast_total, n_total)
