@@ -42,7 +42,7 @@ for p in (ROOT, os.path.join(ROOT, "slam-visual-odometry_b200")):
 W_IMG, H_IMG = 1241, 376
 # dram__bytes_read.sum + dram__bytes_write.sum of one match_kernel launch (500-frame batch) from the ncu --set full capture
 # named in profiles/README.md
-MATCH_DRAM_BYTES_PER_LAUNCH = 62631936
+MATCH_DRAM_BYTES_PER_LAUNCH = 61690000      # profiles/ncu_r02_match_fullconfig.txt: 60.1 MB read + 1.4-1.8 MB written per 5.65 ms launch
 METRIC = "frame-pairs/sec (detect+match+E-RANSAC+pose)"
 
 
@@ -670,7 +670,7 @@ def run_b200(args):
                 # train side of the next)
                 "traffic": MATCH_DRAM_BYTES_PER_LAUNCH if (F, NF, B) == (1000, 3000, 500) else None, "traffic_unit": "bytes/launch",
                 "peak_source": "XOR+POPC+ADD microbenchmark measured in this run (b200vo_measure_popc_rate); not an HBM- or tensor-bound kernel "
-                               "(63 MB of DRAM traffic per 5.6 ms launch)",
+                               "(62 MB of DRAM traffic per 5.6 ms launch)",
                 "share_of_step": round(mm / total_stage_ms, 3)}
     else:
         nm = dom[:-3]

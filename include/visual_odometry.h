@@ -54,6 +54,17 @@ public:
 
     const cv::Mat& camera_matrix() const { return camera_matrix_; }   // [ext]
 
+    // [ext] What the reference prints to stdout for the most recent pair -- the [MatchDebug] line
+    // (src/visual_odometry.cpp:119-129,160-169), the inlier / valid-point counts (:265-279) and the mean
+    // |x2^T F x1| over the inliers (:248-263) -- as values instead of log lines.
+    struct PairDiagnostics {
+        int status = 0;                 // B200VO_ST_* bits (matched / E found / pose ok / overflow)
+        int cross_matches = 0, good_matches = 0, inliers = 0, valid_points = 0;
+        double dist_min = 0, dist_max = 0, dist_mean = 0, dist_median = 0, threshold = 0;
+        double epipolar_residual = 0;
+    };
+    PairDiagnostics last_pair() const { return last_pair_; }
+
 private:
     void init(int w, int h, const Options& o);
     void push_pose(const Pose& p);
@@ -64,6 +75,7 @@ private:
     b200vo_group* group_ = nullptr;
     cv::Mat camera_matrix_;
     bool has_last_F_ = false;
+    PairDiagnostics last_pair_{};
     cv::Matx33d last_F_{};
     std::vector<Pose> trajectory_poses_;
     std::vector<cv::Mat> trajectory_positions_;

@@ -491,6 +491,19 @@ GEOM_HD inline bool null_vector4_adjugate(const double G[4][4], double* Q) {
     return true;
 }
 
+// The rare path of cheirality_ok (no parallax: the adjugate iteration did not converge): one-sided Jacobi SVD.
+GEOM_HD inline void null_vector4_jacobi(double G[4][4], double* Q) {
+    double V[4][4];
+    jacobi_cols<4>(G, V);
+    int jm = 0;
+    double smin = 1e300;
+    for (int j = 0; j < 4; ++j) {
+        const double s = G[0][j] * G[0][j] + G[1][j] * G[1][j] + G[2][j] * G[2][j] + G[3][j] * G[3][j];
+        if (s < smin) { smin = s; jm = j; }
+    }
+    Q[0] = V[0][jm]; Q[1] = V[1][jm]; Q[2] = V[2][jm]; Q[3] = V[3][jm];
+}
+
 // DLT triangulation with P0 = [I|0], P1 = [R|t] + the recoverPose cheirality/distance test.
 GEOM_HD inline bool cheirality_ok(const double* R, const double* t, double x1, double y1, double x2, double y2,
                                   double dist) {
@@ -504,17 +517,7 @@ GEOM_HD inline bool cheirality_ok(const double* R, const double* t, double x1, d
     G[2][3] = x2 * t[2] - t[0];
     G[3][3] = y2 * t[2] - t[1];
     double Q[4];
-    if (!null_vector4_adjugate(G, Q)) {
-        double V[4][4];
-        jacobi_cols<4>(G, V);
-        int jm = 0;
-        double smin = 1e300;
-        for (int j = 0; j < 4; ++j) {
-            const double s = G[0][j] * G[0][j] + G[1][j] * G[1][j] + G[2][j] * G[2][j] + G[3][j] * G[3][j];
-            if (s < smin) { smin = s; jm = j; }
-        }
-        Q[0] = V[0][jm]; Q[1] = V[1][jm]; Q[2] = V[2][jm]; Q[3] = V[3][jm];
-    }
+    if (!null_vector4_adjugate(G, Q)) null_vector4_jacobi(G, Q);
     const double Q0 = Q[0], Q1 = Q[1], Q2 = Q[2], Q3 = Q[3];
     bool ok = (Q2 * Q3 > 0.0);
     const double X = Q0 / Q3, Y = Q1 / Q3, Z = Q2 / Q3;

@@ -291,6 +291,8 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
         // third of the spills) 1.64; 256x3 (80 registers) 1.75; 128x4 1.68; 160x3 1.70
         case 1: return launch_five_point_as<192, 2>(ctx, ra, npairs);
         case 3: return launch_five_point_as<128, 4>(ctx, ra, npairs);
+        case 5: return launch_five_point_as<320, 2>(ctx, ra, npairs);      // 102 registers, 20 warps/SM
+        case 6: return launch_five_point_as<288, 2>(ctx, ra, npairs);      // 113 registers, 18 warps/SM
         default: return launch_five_point_as<256, 2>(ctx, ra, npairs);     // 128 registers, 16 warps/SM
     }
 }
@@ -314,6 +316,8 @@ int init_ransac_kernels() {
     fpg_attr(five_point_group_kernel<256, 2, true>, five_point_deferred_kernel<256, 2>, 256);
     fpg_attr(five_point_group_kernel<192, 2, false>, five_point_deferred_kernel<192, 2>, 192);
     fpg_attr(five_point_group_kernel<128, 4, false>, five_point_deferred_kernel<128, 4>, 128);
+    fpg_attr(five_point_group_kernel<320, 2, false>, five_point_deferred_kernel<320, 2>, 320);
+    fpg_attr(five_point_group_kernel<288, 2, false>, five_point_deferred_kernel<288, 2>, 288);
     if (e != cudaSuccess) { set_error("ransac kernel smem attribute: %s", cudaGetErrorString(e)); return B200VO_ERR_CUDA; }
     return B200VO_OK;
 }

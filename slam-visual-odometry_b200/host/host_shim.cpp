@@ -81,6 +81,14 @@ int vo_host_process_sequence(void* h, const unsigned char* frames, int n, int wi
     } catch (const std::exception& e) { g_msg = e.what(); return -1; }
 }
 
+// out[11]: status, cross, good, inliers, valid, dist min / max / mean / median, threshold, epipolar residual
+void vo_host_last_pair(void* h, double* out) {
+    const VisualOdometry::PairDiagnostics d = static_cast<VisualOdometry*>(h)->last_pair();
+    const double v[11] = {(double)d.status, (double)d.cross_matches, (double)d.good_matches, (double)d.inliers, (double)d.valid_points,
+                          d.dist_min, d.dist_max, d.dist_mean, d.dist_median, d.threshold, d.epipolar_residual};
+    for (int i = 0; i < 11; ++i) out[i] = v[i];
+}
+
 int vo_host_trajectory_size(void* h) { return (int)static_cast<VisualOdometry*>(h)->get_trajectory().size(); }
 
 int vo_host_last_F(void* h, double* F) {

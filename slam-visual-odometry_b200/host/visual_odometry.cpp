@@ -30,6 +30,14 @@ Pose chained(const Pose& prev, const b200vo_pose_record& rec) {
     return Pose(Rm, tm);
 }
 
+VisualOdometry::PairDiagnostics diagnostics_of(const b200vo_pose_record& r) {
+    VisualOdometry::PairDiagnostics d;
+    d.status = r.status; d.cross_matches = r.n_cross; d.good_matches = r.n_matches; d.inliers = r.n_inliers; d.valid_points = r.n_valid;
+    d.dist_min = r.dist_min; d.dist_max = r.dist_max; d.dist_mean = r.dist_mean; d.dist_median = r.dist_median; d.threshold = r.threshold;
+    d.epipolar_residual = r.epi_residual;
+    return d;
+}
+
 // rows of an image as a tightly described u8 buffer
 struct ImageView { const uint8_t* data; size_t pitch; int channels; };
 ImageView view_of(const cv::Mat& img, int w, int h) {
@@ -110,6 +118,7 @@ cv::Mat VisualOdometry::process_frame(Frame& frame) {
 
     // Default to the last known pose; the record's status bits encode the reference's fallbacks.
     frame.pose = Pose(previous_frame_.pose.R_wc, previous_frame_.pose.t_wc);
+    last_pair_ = diagnostics_of(rec);
     if (rec.status & B200VO_ST_E_FOUND) {
         double F[9];
         check(b200vo_fundamental_from_essential(ctx_, E, F), "fundamental");
@@ -170,6 +179,7 @@ std::vector<Pose> VisualOdometry::process_sequence(const std::vector<cv::Mat>& i
             push_pose(cur);
             out.emplace_back(cur.R_wc, cur.t_wc);
         }
+        if (!recs.empty()) last_pair_ = diagnostics_of(recs.back());
         previous_frame_.pose = Pose(cur.R_wc, cur.t_wc);
         previous_frame_.id = (int)(frame_counter_ + (int64_t)recs.size() - 1);
         frame_counter_ += (int64_t)recs.size();
@@ -200,6 +210,7 @@ std::vector<Pose> VisualOdometry::process_sequence(const std::vector<cv::Mat>& i
             push_pose(cur);
             out.emplace_back(cur.R_wc, cur.t_wc);
         }
+        if (n > 0) last_pair_ = diagnostics_of(recs[(size_t)n - 1]);
         previous_frame_.pose = Pose(cur.R_wc, cur.t_wc);
         previous_frame_.id = (int)(frame_counter_ + n - 1);
         previous_slot_ = (first + n - 1) % slots;

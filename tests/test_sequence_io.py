@@ -5,6 +5,7 @@ import ctypes
 import os
 
 import numpy as np
+from conftest import needs_cv2
 import pytest
 
 
@@ -138,3 +139,32 @@ def test_run_directory_equals_batched_pipeline(built, seq_small, tmp_path):
         ctx.detect(0, len(frames))
         ref2 = built.chain_trajectory(ctx.process_pairs(0, len(frames) - 1, 0))
     assert np.allclose(rows[1:, 1:4], ref2[:, 9:12], atol=1e-8) and np.allclose(rows[1:, 4:13], ref2[:, :9], atol=1e-9)
+
+
+@needs_cv2
+def test_read_image_equals_cv2_imread(tmp_path):
+    """The reference reads its frames with cv::imread (src/main.cpp:136).  The Python driver decodes with Pillow: for the
+    lossless formats the pixels must be IDENTICAL to cv2.imread's (gray PNG, colour PNG in BGR order, 16-bit and
+    palette PNGs after cv::imread's default 8-bit BGR conversion is NOT claimed -- only the formats the sequence
+    writers produce); for baseline JPEG the two libjpeg builds may differ by one grey level per pixel (IDCT variants),
+    which is stated here, bounded, and is the reason the parity tests feed identical arrays to both sides."""
+    import cv2
+    from PIL import Image
+    from b200vo import dataset as DS
+    rng = np.random.default_rng(9)
+    gray = rng.integers(0, 256, (61, 83), dtype=np.uint8)
+    rgb = rng.integers(0, 256, (61, 83, 3), dtype=np.uint8)
+    Image.fromarray(gray).save(str(tmp_path / "g.png"))
+    Image.fromarray(rgb).save(str(tmp_path / "c.png"))
+    cv2.imwrite(str(tmp_path / "g.pgm"), gray)
+    cv2.imwrite(str(tmp_path / "c.ppm"), rgb[:, :, ::-1])
+    assert np.array_equal(DS.read_image(str(tmp_path / "g.png")), cv2.imread(str(tmp_path / "g.png"), cv2.IMREAD_UNCHANGED))
+    assert np.array_equal(DS.read_image(str(tmp_path / "c.png")), cv2.imread(str(tmp_path / "c.png")))
+    assert np.array_equal(DS.read_image(str(tmp_path / "g.pgm")), gray)
+    assert np.array_equal(DS.read_image(str(tmp_path / "c.ppm")), cv2.imread(str(tmp_path / "c.ppm")))
+    # the reference converts colour frames with cvtColor(BGR2GRAY): a gray PNG read by cv::imread's DEFAULT flag is 3 equal channels
+    assert np.array_equal(cv2.cvtColor(cv2.imread(str(tmp_path / "g.png")), cv2.COLOR_BGR2GRAY), DS.read_image(str(tmp_path / "g.png")))
+    smooth = cv2.GaussianBlur(rgb, (9, 9), 3)
+    Image.fromarray(smooth).save(str(tmp_path / "c.jpg"), quality=92)
+    a, b = DS.read_image(str(tmp_path / "c.jpg")).astype(int), cv2.imread(str(tmp_path / "c.jpg")).astype(int)
+    assert a.shape == b.shape and np.abs(a - b).max() <= 2
