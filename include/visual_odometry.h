@@ -38,8 +38,8 @@ public:
 
     // Detects features into frame.keypoints/descriptors, writes frame.pose (T_wc), appends to the
     // trajectory and MOVES the frame into the internal previous frame (as the reference does).
-    // Returns the display image; this headless build returns a copy of the input image (the
-    // reference draws the keypoints on it for its GUI).
+    // Returns the display image; this headless build draws nothing (the reference overlays the keypoints for its
+    // GUI) and returns the input image itself -- a reference-counted handle, as every cv::Mat copy is.
     cv::Mat process_frame(Frame& frame);
 
     // [ext] Batched path: all frames are uploaded, detected and matched in launch batches; the
@@ -53,6 +53,8 @@ public:
     cv::Matx33d last_F() const;
 
     const cv::Mat& camera_matrix() const { return camera_matrix_; }   // [ext]
+    Pose current_pose() const;                                         // [ext] T_wc of the most recent frame (no copy of the whole trajectory)
+    size_t trajectory_size() const { return trajectory_poses_.size(); }   // [ext]
 
     // [ext] What the reference prints to stdout for the most recent pair -- the [MatchDebug] line
     // (src/visual_odometry.cpp:119-129,160-169), the inlier / valid-point counts (:265-279) and the mean

@@ -81,6 +81,13 @@ public:
     Mat clone() const {
         Mat m;
         if (empty()) return m;
+        m.rows = rows; m.cols = cols; m.type_ = type_;
+        m.step = (size_t)cols * elemSize();
+        if (step == m.step) {                       // contiguous source: one copy, no zero fill first
+            m.buf_ = std::make_shared<std::vector<uint8_t>>(data, data + (size_t)rows * step);
+            m.data = m.buf_->data();
+            return m;
+        }
         m.create(rows, cols, type_);
         for (int r = 0; r < rows; ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * elemSize());
         return m;

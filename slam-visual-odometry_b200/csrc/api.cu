@@ -154,6 +154,7 @@ void b200vo_destroy(b200vo_ctx* ctx) {
     }
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_frame_pinned) cudaFreeHost(ctx->h_frame_pinned);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -190,6 +191,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     ctx->device = device;
     ctx->stream = nullptr; ctx->d_scratch = nullptr; ctx->scratch_bytes = 0; ctx->h_pinned = nullptr; ctx->pinned_bytes = 0;
     ctx->copy_stream = nullptr; ctx->stage_idx = 0;
+    ctx->h_frame_pinned = nullptr; ctx->frame_pinned_bytes = 0;
     for (int i = 0; i < 2; ++i) { ctx->d_stage[i] = nullptr; ctx->stage_bytes[i] = 0; ctx->stage_ready[i] = nullptr; ctx->stage_free[i] = nullptr; }
     ctx->launches = 0; ctx->timing = false;
     std::memset(&ctx->times, 0, sizeof(ctx->times));
@@ -709,6 +711,31 @@ int b200vo_process_frame(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int
     if (!ctx || !host || !slot_ok(ctx, slot) || prev_slot >= ctx->store.slots || !n || (prev_slot >= 0 && !rec)) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
     const StoreView& sv = ctx->store;
     int rc;
+    if (channels != 1 && channels != 3) { set_error("channels must be 1 or 3"); return B200VO_ERR_BAD_ARG; }
+    if (pitch < (size_t)sv.lv[0].w * channels) { set_error("pitch too small"); return B200VO_ERR_BAD_ARG; }
+    {
+        // The reference hands over an ordinary (pageable) cv::Mat.  cudaMemcpyAsync from pageable memory goes through the
+        // driver's own bounce buffers at a fraction of the PCIe rate and blocks the host meanwhile; one memcpy of the
+        // frame's rows into the context's pinned frame buffer followed by a true asynchronous copy is ~40 us cheaper per
+        // 1241x376 frame.  The buffer is private to this entry point, whose previous call ended with a stream
+        // synchronisation, so it is free.  Pinned callers (cudaHostAlloc / cudaHostRegister) skip the extra memcpy.
+        cudaPointerAttributes pa;
+        const bool pinned = cudaPointerGetAttributes(&pa, host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        if (!pinned) {
+            (void)cudaGetLastError();
+            const size_t row = (size_t)sv.lv[0].w * channels, need = row * sv.lv[0].h;
+            if (ctx->frame_pinned_bytes < need) {
+                if (ctx->h_frame_pinned) cudaFreeHost(ctx->h_frame_pinned);
+                ctx->h_frame_pinned = nullptr; ctx->frame_pinned_bytes = 0;
+                B200VO_CUDA_CHECK(cudaMallocHost(&ctx->h_frame_pinned, need));
+                ctx->frame_pinned_bytes = need;
+            }
+            uint8_t* dst = static_cast<uint8_t*>(ctx->h_frame_pinned);
+            if (pitch == row) std::memcpy(dst, host, need);
+            else for (int y = 0; y < sv.lv[0].h; ++y) std::memcpy(dst + (size_t)y * row, host + (size_t)y * pitch, row);
+            host = dst; pitch = row;
+        }
+    }
     if ((rc = b200vo_upload_frames(ctx, host, 1, pitch, pitch * sv.lv[0].h, channels, slot))) return rc;
     if ((rc = b200vo_detect(ctx, slot, 1))) return rc;
     // results travel through one pinned block: [count, flags | keypoints | descriptors | record | E]

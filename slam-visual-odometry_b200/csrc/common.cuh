@@ -149,6 +149,7 @@ struct b200vo_ctx {
     // scratch for parity hooks / raw matcher
     void* d_scratch; size_t scratch_bytes;
     void* h_pinned; size_t pinned_bytes;
+    void* h_frame_pinned; size_t frame_pinned_bytes;      // b200vo_process_frame: pinned copy of a pageable caller image
     // host uploads: dense H2D copy on a dedicated copy stream into one of two staging buffers, then a
     // device-side repack (or BGR->gray) on the compute stream; events order the two streams
     cudaStream_t copy_stream;

@@ -52,13 +52,12 @@ int vo_host_process_frame(void* h, int frame_id, const unsigned char* img, int w
         const cv::Mat disp = vo->process_frame(f);
         // the reference moves the frame into previous_frame_: the caller's keypoints are gone
         if (moved_from) *moved_from = f.keypoints.empty() ? 1 : 0;
-        const std::vector<Pose> tr = vo->get_trajectory_poses();
-        const Pose& p = tr.back();
+        const Pose p = vo->current_pose();
         for (int i = 0; i < 3; ++i) {
             for (int j = 0; j < 3; ++j) pose_out[i * 3 + j] = p.R_wc.at<double>(i, j);
             pose_out[9 + i] = p.t_wc.at<double>(i, 0);
         }
-        return disp.empty() ? -2 : (int)tr.size();
+        return disp.empty() ? -2 : (int)vo->trajectory_size();
     } catch (const std::exception& e) { g_msg = e.what(); return -1; }
 }
 

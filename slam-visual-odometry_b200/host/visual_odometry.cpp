@@ -104,7 +104,7 @@ cv::Mat VisualOdometry::process_frame(Frame& frame) {
     for (int i = 0; i < n; ++i) std::copy(desc_buf_.data() + (size_t)i * 32, desc_buf_.data() + (size_t)(i + 1) * 32, d.data + (size_t)i * d.step);
     frame.descriptors = d;
     frame.processed = true;
-    const cv::Mat display_image = frame.image.clone();
+    const cv::Mat display_image = frame.image;      // shares the pixels; nothing is drawn in the headless build
 
     if (!initialized_) {
         frame.pose = Pose();
@@ -231,6 +231,12 @@ std::vector<Pose> VisualOdometry::get_trajectory_poses() {
     copy.reserve(trajectory_poses_.size());
     for (const Pose& p : trajectory_poses_) copy.emplace_back(p.R_wc, p.t_wc);
     return copy;
+}
+
+Pose VisualOdometry::current_pose() const {
+    if (trajectory_poses_.empty()) return Pose();
+    const Pose& p = trajectory_poses_.back();
+    return Pose(p.R_wc, p.t_wc);
 }
 
 bool VisualOdometry::has_last_F() const { return has_last_F_; }
