@@ -405,8 +405,9 @@ static int upload_common(b200vo_ctx* ctx, const void* src, int n, size_t pitch, 
             B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->copy_stream));
             if (ctx->d_stage[sb]) cudaFree(ctx->d_stage[sb]);
             ctx->d_stage[sb] = nullptr; ctx->stage_bytes[sb] = 0;
-            B200VO_CUDA_CHECK(cudaMalloc(&ctx->d_stage[sb], need + 256));
-            ctx->stage_bytes[sb] = need;
+            const size_t want = std::max(need, ctx->stage_bytes[sb ^ 1]);      // both buffers grow to the largest batch seen: callers that
+            B200VO_CUDA_CHECK(cudaMalloc(&ctx->d_stage[sb], want + 256));      // vary the batch size settle after one pass
+            ctx->stage_bytes[sb] = want;
         }
         B200VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[sb], 0));
         if (pitch == row && frame_stride == fbytes) {
