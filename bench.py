@@ -283,21 +283,18 @@ class SeqRunner:
         self.RB = b200vo.RECORD_BYTES
         self.recs_dev = torch.zeros(max(self.npairs, 1) * self.RB, dtype=torch.uint8, device=self.dev)
         self.fb = W * H
+        self.e2e_sizes = None
 
     def batches(self, short_first=False):
         """(first slot, frames in the batch, frames done before, first pair slot, pairs, pairs done before).
-        short_first (the e2e leg): batch sizes ramp up geometrically (x1.4 from B/12), so that the H2D copy of batch k+1
-        -- enqueued on the copy stream right behind batch k's -- is never longer than the compute of batch k and only
-        the first small copy is exposed.  (Round 1 and the first round-2 runs used B/5 then B: at 8 ranks the copy of the
-        500-frame second batch took 10 ms against 3 ms of compute on the first, 9 of the 12 ms the e2e step lost.)"""
+        short_first (the e2e leg) follows self.e2e_sizes, the schedule choose_e2e_schedule picked for this rank."""
         B, F = self.B, self.F
+        sizes = self.e2e_sizes if (short_first and self.e2e_sizes) else [B] * (-(-F // B))
         done_f, done_p, prev = 0, 0, 0
-        ramp = max(B // 12, 2)
-        while done_f < F:
-            n = min(B, F - done_f)
-            if short_first:
-                n = min(n, ramp)
-                ramp = int(ramp * 1.4) + 1
+        for n in sizes:
+            n = min(n, F - done_f)
+            if n <= 0:
+                break
             first = 0 if done_f == 0 else (prev + 1) % (B + 1)
             p0, np_ = (first, n - 1) if done_f == 0 else (prev, n)
             yield first, n, done_f, p0, np_, done_p
@@ -346,6 +343,33 @@ def close_contexts(torch):
         _OPEN_CONTEXTS.pop().close()
 
 
+def choose_e2e_schedule(F, B, compute_ms_per_frame, copy_ms_per_frame):
+    """Launch-batch sizes for the e2e leg of one rank.  The upload of batch k+1 is enqueued on the copy stream right behind
+    batch k's, so it hides behind the compute of batch k when it is not longer; what stays exposed is the first upload,
+    every (copy(k+1) - compute(k)) that is positive, and a fixed cost per batch (launch tails; measured 0.58 ms = 20
+    frames' worth at the headline configuration, tools/e2e_schedules.py).  The schedule that minimises that model is
+    picked from first-batch sizes B/12..B and growth factors 1..5 -- with this box's 55 GB/s for one rank it is
+    B/5, B, rest; with eight ranks sharing the host at ~23 GB/s each it is a ramp of about x1.6 from B/4."""
+    c, u, o = compute_ms_per_frame, copy_ms_per_frame, 20.0 * compute_ms_per_frame
+    best = None
+    for div in (12, 8, 6, 5, 4, 3, 2, 1):
+        for g in (1.0, 1.3, 1.6, 2.0, 3.0, 5.0):
+            sizes, r, done = [], max(2, B // div), 0
+            while done < F:
+                n = min(B, F - done, int(r))
+                if F - done - n == 1:          # never leave a single trailing frame to a batch of its own
+                    n += 1 if n < B else -1
+                sizes.append(n)
+                done += n
+                r = r * g + (1 if g > 1.0 else 0)
+            t = F * c + len(sizes) * o + sizes[0] * u
+            for k in range(len(sizes) - 1):
+                t += max(0.0, sizes[k + 1] * u - (sizes[k] * c + o))
+            if best is None or t < best[0] - 1e-9:
+                best = (t, sizes)
+    return best[1], best[0]
+
+
 def timed_steps(torch, dist, world, runner_stream, fn, steps, warmup, dev, launches_of=None):
     """warm-up, barrier + synchronize, CUDA events on the launching stream around exactly `steps` calls,
     barrier + synchronize, MAX over ranks.  Returns (ms per step, wall s per step, kernel launches)."""
@@ -373,6 +397,23 @@ def timed_steps(torch, dist, world, runner_stream, fn, steps, warmup, dev, launc
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     return ms / steps, wall / steps, (launches_of.kernel_launches() - l0) if launches_of is not None else 0
+
+
+def h2d_probe(torch, dist, world, d_like, h_frames):
+    """GB/s of 3 back-to-back pinned -> device copies of h_frames on this rank, all ranks copying at once."""
+    dst = torch.empty_like(d_like)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        dst.copy_(h_frames, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    gbps = 3 * h_frames.numel() / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    del dst
+    return gbps
 
 
 def render(torch, synth, W, H, R, C, tex, dev, chunk):
@@ -413,6 +454,8 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
             run.stream.synchronize()
 
     ms_dev, _, launches = timed_steps(torch, dist, world, run.stream, lambda: step(False), steps, warmup, dev, run.ctx)
+    gbps = h2d_probe(torch, dist, world, d_fr, h_fr)
+    run.e2e_sizes, _ = choose_e2e_schedule(run.F, run.B, ms_dev / max(run.F, 1), W * H / (gbps * 1e9) * 1e3)
     ms_e2e, _, _ = timed_steps(torch, dist, world, run.stream, lambda: step(True), steps, warmup, dev)
     out, recs = None, None
     if rank == 0:
@@ -422,7 +465,7 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
         out = {"workload": "%s: ONE %d-frame %dx%d sequence, %d features, %d hypotheses/pair, launch batches of %d frames, partitioned over %d GPU(s) by contiguous frame-pair ranges" % (name, F, W, H, NF, hyp, run.B, world),
                "pairs": P, "scaling": "strong", "value": round(P / (ms_dev * 1e-3), 1), "e2e": round(P / (ms_e2e * 1e-3), 1), "unit": "pairs/s",
                "ms_per_step": round(ms_dev, 3), "e2e_ms_per_step": round(ms_e2e, 3), "steps": steps, "warmup": warmup,
-               "h2d_bytes_per_step": (P + world) * W * H, "d2h_bytes_per_step": world * per * RB,
+               "h2d_bytes_per_step": (P + world) * W * H, "d2h_bytes_per_step": world * per * RB, "e2e_batch_sizes_rank0": run.e2e_sizes,
                "boundary_frames_detected_twice": world - 1, "boundary_overhead_frac": round((world - 1) / float(P + 1), 5),
                "gpu_launches": int(launches) * world,
                "pairs_pose_ok": int(((recs["status"] & 4) != 0).sum()), "pairs_overflow": int(((recs["status"] & 256) != 0).sum()),
@@ -436,6 +479,7 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
             d_all, h_all = render(torch, synth, W, H, R_all, C_all, tex, dev, chunk)
             solo = SeqRunner(torch, b200vo, W, H, NF, hyp, B, local, d_all, h_all, 0)
             ms1, _, _ = timed_steps(torch, None, 1, solo.stream, lambda: solo.step(False), steps, warmup, dev)
+            solo.e2e_sizes, _ = choose_e2e_schedule(solo.F, solo.B, ms1 / solo.F, W * H / (h2d_probe(torch, None, 1, d_all, h_all) * 1e9) * 1e3)
             host1 = torch.empty(P * RB, dtype=torch.uint8, pin_memory=True)
 
             def e2e1():
@@ -532,24 +576,16 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     ms_dev, wall_dev, launches = timed_steps(torch, dist, world, stream, make_step(run, False), args.steps, args.warmup, dev, ctx)
+    # ---- per-rank upload bandwidth of a plain pinned -> device copy of the same frames with all ranks copying at the same
+    # time (the ceiling the host's PCIe / memory system gives this box); it also picks this rank's e2e batch schedule
+    probe_gbps = h2d_probe(torch, dist, world, d_frames, h_frames)
+    run.e2e_sizes, _ = choose_e2e_schedule(F, run.B, ms_dev / F, frame_bytes / (probe_gbps * 1e9) * 1e3)
     ms_e2e, wall_e2e, _ = timed_steps(torch, dist, world, stream, make_step(run, True), args.steps, max(args.warmup, 3), dev)
     clocks = sampler.stop() if rank == 0 else None
     ok = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy() if rank == 0 else None
     traj = state["traj"]
 
-    # ---- per-rank upload bandwidth: (a) what the e2e leg achieved, (b) a plain pinned -> device copy of the same frames with all
-    # ranks copying at the same time (the ceiling the host's PCIe / memory system gives this box)
-    probe_dst = torch.empty_like(d_frames)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pe0.record()
-    for _ in range(3):
-        probe_dst.copy_(h_frames, non_blocking=True)
-    pe1.record()
-    torch.cuda.synchronize()
-    h2d_vals = torch.tensor([F * frame_bytes / (ms_e2e * 1e-3) / 1e9, 3 * F * frame_bytes / (pe0.elapsed_time(pe1) * 1e-3) / 1e9,
+    h2d_vals = torch.tensor([F * frame_bytes / (ms_e2e * 1e-3) / 1e9, probe_gbps,
                              float(numa[0]), float(numa[1])], device=dev, dtype=torch.float64)
     h2d_all = [torch.zeros_like(h2d_vals) for _ in range(world)]
     if world > 1:
@@ -558,8 +594,9 @@ def run_b200(args):
         h2d_all = [h2d_vals]
     h2d = {"e2e_GBps_per_rank": [round(float(v[0]), 2) for v in h2d_all], "plain_pinned_copy_GBps_per_rank_concurrent": [round(float(v[1]), 2) for v in h2d_all],
            "cpus_bound_per_rank": [int(v[2]) for v in h2d_all], "cpus_nvml_affinity_per_rank": [int(v[3]) for v in h2d_all],
-           "note": "e2e: frame bytes of a rank / its e2e step time (the copy is overlapped with compute, so this is a lower bound of the copy rate); plain: 3 back-to-back pinned->device copies of the same frames, all ranks at once"}
-    del probe_dst, h2d_all, h2d_vals
+           "e2e_batch_sizes_rank0": run.e2e_sizes,
+           "note": "e2e: frame bytes of a rank / its e2e step time (the copy is overlapped with compute, so this is a lower bound of the copy rate); plain: 3 back-to-back pinned->device copies of the same frames, all ranks at once, measured before the e2e leg; the e2e launch-batch schedule of every rank is chosen from its own plain rate (choose_e2e_schedule)"}
+    del h2d_all, h2d_vals
 
     # ---- per-stage breakdown (separate instrumented pass; timing mode synchronises per call) + keypoints per frame
     stage, kp_counts = {}, []
