@@ -305,6 +305,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         ctx->filter_fast_cap = 1 << 30;
         ctx->fpg_variant = 0;
         ctx->pdl = false; ctx->pdl_enabled = true;
+        ctx->repack_kernel = true;
+        if (const char* v = getenv("B200VO_REPACK_KERNEL")) ctx->repack_kernel = (atoi(v) != 0);
         if (const char* v = getenv("B200VO_PDL")) ctx->pdl_enabled = (atoi(v) != 0);
         ctx->fused_describe = ctx->use_tma;
         if (const char* v = getenv("B200VO_DESCRIBE")) ctx->fused_describe = (atoi(v) != 0);
@@ -424,6 +426,10 @@ static int upload_common(b200vo_ctx* ctx, const void* src, int n, size_t pitch, 
         if (rc) return rc;
         B200VO_CUDA_CHECK(cudaEventRecord(ctx->stage_free[sb], ctx->stream));
         return B200VO_OK;
+    }
+    if (channels == 1 && ctx->repack_kernel) {
+        // handles any pitch / alignment and the ring wrap; reads aligned 32-bit words, never beyond the word of a needed byte
+        return launch_repack_gray(ctx, static_cast<const uint8_t*>(src), pitch, frame_stride, first_slot, n);
     }
     if (channels == 1) {
         int done = 0;

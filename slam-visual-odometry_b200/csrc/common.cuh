@@ -165,6 +165,7 @@ struct b200vo_ctx {
     bool fused_describe;       // describe_kernel (default) or the three round-1 kernels (B200VO_DESCRIBE=0)
     bool use_tma;
     int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC, 2: full Harley-Seal (4 POPC), 3: 3 CSA + 5 POPC (default)
+    bool repack_kernel;        // device-side ingest of gray frames by kernel (default) or cudaMemcpy3DAsync (B200VO_REPACK_KERNEL=0)
     bool pdl;                  // programmatic dependent launch for the current call (small batches only; B200VO_PDL=0 disables)
     bool pdl_enabled;
     int fpg_variant;           // five-point launch shape (B200VO_FPG, ransac.cu)
@@ -229,6 +230,7 @@ inline void launch_k(b200vo_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 
 
 // stage launchers (each enqueues on ctx->stream and returns a b200vo_status)
 int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int first_slot, int n);
+int launch_repack_gray(b200vo_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t frame_stride, int first_slot, int n);
 int launch_pyramid(b200vo_ctx* ctx, int first_slot, int n);
 int launch_fast(b200vo_ctx* ctx, int first_slot, int n);
 int launch_select(b200vo_ctx* ctx, int first_slot, int n);

@@ -37,6 +37,45 @@ __global__ void bgr2gray_kernel(StoreView sv, const uint8_t* __restrict__ bgr, s
     *reinterpret_cast<uint32_t*>(dst) = packed;   // rows are 128-B pitched, x multiple of 4
 }
 
+// Gray frames already on the device (dense or arbitrarily pitched) -> level 0 of the frame store (128-B pitch).  A kernel
+// instead of cudaMemcpy3DAsync: a pitched device-to-device copy of 1241-byte rows runs on a copy engine row by row, and
+// during the e2e pipeline it queued behind the host->device transfer of the NEXT batch on that engine; 16 output bytes
+// per thread from unaligned source rows through aligned 32-bit loads and funnel shifts.
+__global__ void __launch_bounds__(256)
+repack_gray_kernel(StoreView sv, const uint8_t* __restrict__ src, size_t pitch, size_t frame_stride, int first_slot) {
+    pdl_grid_sync();
+    const LevelGeom g = sv.lv[0];
+    const int slot = ring_slot(first_slot, blockIdx.z, sv.slots);
+    const int y = blockIdx.y;
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (x >= g.w) return;
+    const uint8_t* row = src + blockIdx.z * frame_stride + (size_t)y * pitch + x;
+    uint8_t* dst = sv.pyr + (size_t)slot * sv.slot_bytes + g.offset + (size_t)y * g.pitch + x;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(row);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const int off = (int)(a & 3), sh = off * 8;
+    // only the aligned words that hold a needed byte are read: at the two ends of the source that touches at most the rest
+    // of an aligned 4-byte word, which cannot leave an allocation (device allocations are at least 4-byte granular)
+    const int nbytes = min(16, g.w - x);
+    uint32_t v[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) v[i] = (4 * i < off + nbytes) ? __ldg(w + i) : 0u;
+    uint4 o;
+    o.x = __funnelshift_r(v[0], v[1], sh); o.y = __funnelshift_r(v[1], v[2], sh);
+    o.z = __funnelshift_r(v[2], v[3], sh); o.w = __funnelshift_r(v[3], v[4], sh);
+    if (nbytes == 16) { *reinterpret_cast<uint4*>(dst) = o; return; }
+    const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+    for (int i = 0; i < nbytes; ++i) dst[i] = (uint8_t)(ow[i >> 2] >> (8 * (i & 3)));
+}
+
+int launch_repack_gray(b200vo_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t frame_stride, int first_slot, int n) {
+    const LevelGeom& g = ctx->store.lv[0];
+    dim3 grid(div_up(div_up(g.w, 16), 256), g.h, n);
+    launch_k(ctx, repack_gray_kernel, grid, dim3(256), 0, ctx->store, d_src, pitch, frame_stride, first_slot);
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
 // One thread produces 4 horizontally adjacent output pixels (one 32-bit store).
 // tab: xofs[dwp], xc1[dwp], yofs[dhp], yc1[dhp]  (dwp/dhp = sizes padded to 4)
 __global__ void __launch_bounds__(256)

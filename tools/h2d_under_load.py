@@ -38,29 +38,31 @@ def compute(nsteps):
 
 
 def copy_rate(chunks, reps):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    """Rate of the FIRST pass over the frames (all ranks are still copying then: the contended rate) and of all passes."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
     n = F // chunks
     with torch.cuda.stream(s2):
-        e0.record()
-        for _ in range(reps):
+        ev[0].record()
+        for r in range(reps):
             for c in range(chunks):
                 dst[c * n:(c + 1) * n].copy_(h[c * n:(c + 1) * n], non_blocking=True)
-        e1.record()
+            ev[r + 1].record()
     torch.cuda.synchronize()
-    return reps * chunks * n * W * H / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    per = chunks * n * W * H / 1e9
+    return per / (ev[0].elapsed_time(ev[1]) * 1e-3), reps * per / (ev[0].elapsed_time(ev[reps]) * 1e-3)
 
 
 compute(1)
 torch.cuda.synchronize()
 out = {}
-for chunks in (1, 8):
+for chunks in (1, 24):
     if world > 1:
         dist.barrier()
-    out["idle_%dchunks" % chunks] = copy_rate(chunks, 3)
+    out["idle_first_pass_%dchunks" % chunks], out["idle_all_passes_%dchunks" % chunks] = copy_rate(chunks, 4)
     if world > 1:
         dist.barrier()
-    compute(6)                       # ~100 ms of queued kernels; the copies below overlap them
-    out["under_compute_%dchunks" % chunks] = copy_rate(chunks, 2)
+    compute(8)                       # ~240 ms of queued kernels; the copies below overlap them
+    out["under_compute_first_pass_%dchunks" % chunks], out["under_compute_all_passes_%dchunks" % chunks] = copy_rate(chunks, 4)
     torch.cuda.synchronize()
 vals = torch.tensor([out[k] for k in sorted(out)], device="cuda:%d" % local, dtype=torch.float64)
 allv = [torch.zeros_like(vals) for _ in range(world)]
