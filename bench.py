@@ -343,31 +343,42 @@ def close_contexts(torch):
         _OPEN_CONTEXTS.pop().close()
 
 
-def choose_e2e_schedule(F, B, compute_ms_per_frame, copy_ms_per_frame):
-    """Launch-batch sizes for the e2e leg of one rank.  The upload of batch k+1 is enqueued on the copy stream right behind
-    batch k's, so it hides behind the compute of batch k when it is not longer; what stays exposed is the first upload,
-    every (copy(k+1) - compute(k)) that is positive, and a fixed cost per batch (launch tails; measured 0.58 ms = 20
-    frames' worth at the headline configuration, tools/e2e_schedules.py).  The schedule that minimises that model is
-    picked from first-batch sizes B/12..B and growth factors 1..5 -- with this box's 55 GB/s for one rank it is
-    B/5, B, rest; with eight ranks sharing the host at ~23 GB/s each it is a ramp of about x1.6 from B/4."""
-    c, u, o = compute_ms_per_frame, copy_ms_per_frame, 20.0 * compute_ms_per_frame
+def e2e_schedule_candidates(F, B):
+    """Launch-batch schedules for the e2e leg.  The upload of batch k+1 is enqueued on the copy stream right behind batch
+    k's, so it hides behind the compute of batch k when it is not longer; what stays exposed is the first upload, every
+    positive (copy(k+1) - compute(k)), and a fixed cost per batch (launch tails: 0.6 ms at the headline configuration).
+    Which schedule wins depends on the upload rate the host gives this rank (55 GB/s alone, 20-35 GB/s with eight ranks
+    copying): `B/5, B, ...` for a fast link, ramps of x2 from B/6 or x1.6 from B/4 for a slow one
+    (tools/e2e_schedules.py, profiles/e2e_schedules_r02_{1,8}gpu.jsonl).  bench.py times each candidate on untimed
+    warm-up steps and keeps the fastest (max over ranks, so every rank keeps the same one)."""
+    def ramp(start, growth):
+        sizes, r, done = [], float(max(2, start)), 0
+        while done < F:
+            n = min(B, F - done, int(r))
+            if F - done - n == 1:              # never leave a single trailing frame to a batch of its own
+                n += 1 if n < B else -1
+            sizes.append(n)
+            done += n
+            r = r * growth + 1
+        return sizes
+    cands = [ramp(B // 5, 1e9), ramp(B // 6, 2.0), ramp(B // 4, 1.6), ramp(B, 1.0)]
+    out = []
+    for c in cands:
+        if c not in out:
+            out.append(c)
+    return out
+
+
+def pick_e2e_schedule(torch, dist, world, runner, step_fn, dev):
+    """Time every candidate schedule for two steps after one settling step; keep the fastest."""
     best = None
-    for div in (12, 8, 6, 5, 4, 3, 2, 1):
-        for g in (1.0, 1.3, 1.6, 2.0, 3.0, 5.0):
-            sizes, r, done = [], max(2, B // div), 0
-            while done < F:
-                n = min(B, F - done, int(r))
-                if F - done - n == 1:          # never leave a single trailing frame to a batch of its own
-                    n += 1 if n < B else -1
-                sizes.append(n)
-                done += n
-                r = r * g + (1 if g > 1.0 else 0)
-            t = F * c + len(sizes) * o + sizes[0] * u
-            for k in range(len(sizes) - 1):
-                t += max(0.0, sizes[k + 1] * u - (sizes[k] * c + o))
-            if best is None or t < best[0] - 1e-9:
-                best = (t, sizes)
-    return best[1], best[0]
+    for sizes in e2e_schedule_candidates(runner.F, runner.B):
+        runner.e2e_sizes = sizes
+        ms, _, _ = timed_steps(torch, dist, world, runner.stream, step_fn, 2, 1, dev)
+        if best is None or ms < best[0]:
+            best = (ms, sizes)
+    runner.e2e_sizes = best[1]
+    return best[1]
 
 
 def timed_steps(torch, dist, world, runner_stream, fn, steps, warmup, dev, launches_of=None):
@@ -454,8 +465,7 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
             run.stream.synchronize()
 
     ms_dev, _, launches = timed_steps(torch, dist, world, run.stream, lambda: step(False), steps, warmup, dev, run.ctx)
-    gbps = h2d_probe(torch, dist, world, d_fr, h_fr)
-    run.e2e_sizes, _ = choose_e2e_schedule(run.F, run.B, ms_dev / max(run.F, 1), W * H / (gbps * 1e9) * 1e3)
+    pick_e2e_schedule(torch, dist, world, run, lambda: step(True), dev)
     ms_e2e, _, _ = timed_steps(torch, dist, world, run.stream, lambda: step(True), steps, warmup, dev)
     out, recs = None, None
     if rank == 0:
@@ -479,7 +489,6 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
             d_all, h_all = render(torch, synth, W, H, R_all, C_all, tex, dev, chunk)
             solo = SeqRunner(torch, b200vo, W, H, NF, hyp, B, local, d_all, h_all, 0)
             ms1, _, _ = timed_steps(torch, None, 1, solo.stream, lambda: solo.step(False), steps, warmup, dev)
-            solo.e2e_sizes, _ = choose_e2e_schedule(solo.F, solo.B, ms1 / solo.F, W * H / (h2d_probe(torch, None, 1, d_all, h_all) * 1e9) * 1e3)
             host1 = torch.empty(P * RB, dtype=torch.uint8, pin_memory=True)
 
             def e2e1():
@@ -487,6 +496,7 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
                 with torch.cuda.stream(solo.stream):
                     host1.copy_(solo.recs_dev[:P * RB], non_blocking=True)
                 solo.stream.synchronize()
+            pick_e2e_schedule(torch, None, 1, solo, e2e1, dev)
             ms1e, _, _ = timed_steps(torch, None, 1, solo.stream, e2e1, steps, warmup, dev)
             recs1 = host1.numpy().view(b200vo.POSE_RECORD_DTYPE).copy()
             out["single_gpu"] = {"value": round(P / (ms1 * 1e-3), 1), "e2e": round(P / (ms1e * 1e-3), 1), "ms_per_step": round(ms1, 3)}
@@ -577,9 +587,9 @@ def run_b200(args):
         sampler.start()
     ms_dev, wall_dev, launches = timed_steps(torch, dist, world, stream, make_step(run, False), args.steps, args.warmup, dev, ctx)
     # ---- per-rank upload bandwidth of a plain pinned -> device copy of the same frames with all ranks copying at the same
-    # time (the ceiling the host's PCIe / memory system gives this box); it also picks this rank's e2e batch schedule
+    # time (the ceiling the host's PCIe / memory system gives this box)
     probe_gbps = h2d_probe(torch, dist, world, d_frames, h_frames)
-    run.e2e_sizes, _ = choose_e2e_schedule(F, run.B, ms_dev / F, frame_bytes / (probe_gbps * 1e9) * 1e3)
+    pick_e2e_schedule(torch, dist, world, run, make_step(run, True), dev)
     ms_e2e, wall_e2e, _ = timed_steps(torch, dist, world, stream, make_step(run, True), args.steps, max(args.warmup, 3), dev)
     clocks = sampler.stop() if rank == 0 else None
     ok = recs_host.numpy().view(b200vo.POSE_RECORD_DTYPE).copy() if rank == 0 else None
@@ -595,7 +605,7 @@ def run_b200(args):
     h2d = {"e2e_GBps_per_rank": [round(float(v[0]), 2) for v in h2d_all], "plain_pinned_copy_GBps_per_rank_concurrent": [round(float(v[1]), 2) for v in h2d_all],
            "cpus_bound_per_rank": [int(v[2]) for v in h2d_all], "cpus_nvml_affinity_per_rank": [int(v[3]) for v in h2d_all],
            "e2e_batch_sizes_rank0": run.e2e_sizes,
-           "note": "e2e: frame bytes of a rank / its e2e step time (the copy is overlapped with compute, so this is a lower bound of the copy rate); plain: 3 back-to-back pinned->device copies of the same frames, all ranks at once, measured before the e2e leg; the e2e launch-batch schedule of every rank is chosen from its own plain rate (choose_e2e_schedule)"}
+           "note": "e2e: frame bytes of a rank / its e2e step time (the copy is overlapped with compute, so this is a lower bound of the copy rate); plain: 3 back-to-back pinned->device copies of the same frames, all ranks at once, measured before the e2e leg; the e2e launch-batch schedule is the fastest of a few candidates timed on warm-up steps (pick_e2e_schedule)"}
     del h2d_all, h2d_vals
 
     # ---- per-stage breakdown (separate instrumented pass; timing mode synchronises per call) + keypoints per frame
