@@ -292,6 +292,11 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
                 const int yl = std::min(y0 + 16, g.h) - 1;
                 if (std::min(yo[yl] + 1, s.h - 1) - yo[y0] + 1 > kResizeBoxH) { set_error("resize footprint exceeds the TMA box (height)"); b200vo_destroy(ctx); return B200VO_ERR_BAD_ARG; }
             }
+            ctx->resize_strip_ok[l] = true;      // resize_strip_kernel: 128 x (8 * kResizeStripRows) output tiles
+            for (int y0 = 0; y0 < g.h; y0 += 8 * kResizeStripRows) {
+                const int yl = std::min(y0 + 8 * kResizeStripRows, g.h) - 1;
+                if (std::min(yo[yl] + 1, s.h - 1) - yo[y0] + 1 > kResizeStripBoxH) ctx->resize_strip_ok[l] = false;
+            }
         }
         // resize_tma_kernel loads the taps of a whole 128-column tile as int4 even where the tile overhangs the level
         // (values discarded): keep 128 spare entries behind the last table so that read stays inside the allocation
@@ -302,6 +307,11 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         ctx->use_tma = true;
         if (const char* v = getenv("B200VO_TMA")) ctx->use_tma = (atoi(v) != 0);
         ctx->match_csa = 3;
+        ctx->match_variant = 1;
+        ctx->blur_rows = 24;
+        ctx->resize_strip = true;
+        if (const char* v = getenv("B200VO_RESIZE_STRIP")) ctx->resize_strip = (atoi(v) != 0);
+        if (const char* v = getenv("B200VO_BLUR_R")) { const int c = atoi(v); if (c == 0 || c == 16 || c == 24) ctx->blur_rows = c; }
         ctx->filter_fast_cap = 1 << 30;
         ctx->fpg_variant = 0;
         ctx->pdl = false; ctx->pdl_enabled = true;
@@ -313,6 +323,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         if (const char* v = getenv("B200VO_FPG")) ctx->fpg_variant = atoi(v);
         if (const char* v = getenv("B200VO_FILTER_FAST_CAP")) ctx->filter_fast_cap = atoi(v);
         if (const char* v = getenv("B200VO_MATCH_CSA")) { const int c = atoi(v); if (c >= 0 && c <= 3) ctx->match_csa = c; }
+        if (const char* v = getenv("B200VO_MATCH_V")) { const int c = atoi(v); if (c >= 0 && c <= 2) ctx->match_variant = c; }
         void* fnp = nullptr;
         cudaDriverEntryPointQueryResult qres;
         TRYCUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qres));
@@ -320,7 +331,10 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         for (int l = 0; l < kLevels; ++l) {
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_fast[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, fast_level_is_wide(l) ? kFastBoxWideW : kFastBoxW, kFastBoxH));
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_blur[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kBlurBoxW, kBlurBoxH));
+            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_blur16[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kBlurBoxW, 8 * 16 + 6));
+            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_blur24[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kBlurBoxW, 8 * 24 + 6));
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_resize[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kResizeBoxW, kResizeBoxH));
+            TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_resize_strip[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kResizeBoxW, kResizeStripBoxH));
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_orient[l], sv.pyr, sv.lv[l], sv.slot_bytes, sv.slots, kOrientBoxW, kOrientBoxH));
             TRY(encode_level_map((EncodeTiledFn)fnp, &ctx->tmap_brief[l], sv.blur, sv.lv[l], sv.slot_bytes, sv.slots, kBriefBoxW, kBriefBoxH));
         }

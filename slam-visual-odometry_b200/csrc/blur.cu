@@ -153,6 +153,125 @@ blur_kernel(StoreView sv, const __grid_constant__ LevelTiles lt, int level_arg, 
     }
 }
 
+// Large batches: the same arithmetic, organised so that the row-pass results never leave registers.
+//
+// Per-line profile of blur_kernel at the bench configuration (profiles/ncu_r02_lines_blur_kernel.txt): 38 thread-instructions
+// per pixel at 80 % issue utilisation -- issue-bound; of the 153 instructions a thread spends per 4 pixels only 56 are the
+// float operations the result needs, the rest is the float tile's shared-memory round trip (one 16-byte store and seven
+// 16-byte loads per 4 pixels), index arithmetic of two strided loops and the barrier between the passes.  Here a warp owns
+// a strip of R output rows x 128 columns and walks down it: a lane row-filters 4 adjacent pixels of the next staged row
+// (3 aligned words in, 28 float operations), keeps the last seven results in a register ring (the loop is unrolled by 7
+// so every ring index is a compile-time constant) and emits one output word per step: ~85 instructions per step.
+// The tile is 8 strips tall (128 x 8R outputs, one TMA box of 160 x (8R + 6) bytes); the row pass is repeated for the
+// 6 halo rows of every strip, (R + 6) / R of the row work.  Same operation order, bit-exact (tests/test_gpu_features.py).
+__device__ __forceinline__ float4 blur_row4(const uint32_t* __restrict__ s, float k0, float k1, float k2, float k3) {
+    // outputs x = 4q..4q+3 need staged bytes 4q+13 .. 4q+22: s points at word q+3
+    const uint32_t w0 = s[0], w1 = s[1], w2 = s[2];
+    float p[10];
+    p[0] = (float)((w0 >> 8) & 0xFF); p[1] = (float)((w0 >> 16) & 0xFF); p[2] = (float)(w0 >> 24);
+    p[3] = (float)(w1 & 0xFF); p[4] = (float)((w1 >> 8) & 0xFF); p[5] = (float)((w1 >> 16) & 0xFF); p[6] = (float)(w1 >> 24);
+    p[7] = (float)(w2 & 0xFF); p[8] = (float)((w2 >> 8) & 0xFF); p[9] = (float)((w2 >> 16) & 0xFF);
+    float4 r;
+    float* rr = &r.x;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float v = __fmul_rn(k0, p[c]);
+        v = __fmaf_rn(p[c + 1], k1, v);
+        v = __fmaf_rn(p[c + 2], k2, v);
+        v = __fmaf_rn(p[c + 3], k3, v);
+        v = __fmaf_rn(p[c + 4], k2, v);
+        v = __fmaf_rn(p[c + 5], k1, v);
+        v = __fmaf_rn(p[c + 6], k0, v);
+        rr[c] = v;
+    }
+    return r;
+}
+__device__ __forceinline__ uint32_t blur_col4(const float4& a0, const float4& a1, const float4& a2, const float4& a3,
+                                              const float4& a4, const float4& a5, const float4& a6, float k0, float k1, float k2, float k3) {
+    uint32_t packed = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float v0 = (&a0.x)[c], v1 = (&a1.x)[c], v2 = (&a2.x)[c], v3 = (&a3.x)[c], v4 = (&a4.x)[c], v5 = (&a5.x)[c], v6 = (&a6.x)[c];
+        float v = __fmul_rn(k3, v3);
+        v = __fmaf_rn(__fadd_rn(v4, v2), k2, v);
+        v = __fmaf_rn(__fadd_rn(v5, v1), k1, v);
+        v = __fmaf_rn(__fadd_rn(v6, v0), k0, v);
+        uint32_t qv;                                             // round-half-even + saturate to 0..255 in one conversion
+        asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(qv) : "f"(v));
+        packed |= qv << (8 * c);
+    }
+    return packed;
+}
+
+template <int R>
+__global__ void __launch_bounds__(256)
+blur_strip_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap) {
+    pdl_grid_sync();
+    constexpr int TH = 8 * R, SH = TH + 6;
+    __shared__ __align__(128) uint32_t s_in[SH][BL_SWW];
+    __shared__ __align__(8) uint64_t s_bar;
+    const float k0 = __uint_as_float(0x3d8fafb1u), k1 = __uint_as_float(0x3e06387eu),
+                k2 = __uint_as_float(0x3e434a39u), k3 = __uint_as_float(0x3e5d4ae0u);
+    const LevelGeom g = sv.lv[level];
+    const int slot = ring_slot(first_slot, blockIdx.z, sv.slots);
+    uint8_t* out = sv.blur + (size_t)slot * sv.slot_bytes + g.offset;
+    const int ox = blockIdx.x * BL_W, oy = blockIdx.y * TH;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) { tma::mbar_init(&s_bar, 1); tma::fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_arrive_expect_tx(&s_bar, SH * BL_SWW * 4);
+        tma::load_3d(&s_in[0][0], &tmap, &s_bar, ox - BL_HALO, oy - 3, slot);
+    }
+    tma::mbar_wait(&s_bar, 0);
+    if ((ox == 0) || (ox + BL_W + 3 > g.w) || (oy < 3) || (oy + TH + 3 > g.h)) {
+        // BORDER_REFLECT_101 halo patched from the tile itself (every reflected source pixel lies inside it):
+        // columns first (all staged rows), then whole rows
+        uint8_t* sb = reinterpret_cast<uint8_t*>(&s_in[0][0]);
+        const int rowb = BL_SWW * 4;
+        __syncthreads();
+        for (int i = tid; i < SH * 6; i += 256) {
+            const int ty = i / 6, k = i - ty * 6;
+            const int x = (k < 3) ? (-1 - k) : (g.w + (k - 3));
+            const int xs = (k < 3) ? (1 + k) : (g.w - 2 - (k - 3));
+            const int c = x - (ox - BL_HALO), cs = xs - (ox - BL_HALO);
+            if (c >= 0 && c < rowb && cs >= 0 && cs < rowb) sb[ty * rowb + c] = sb[ty * rowb + cs];
+        }
+        __syncthreads();
+        for (int i = tid; i < 6 * BL_SWW; i += 256) {
+            const int k = i / BL_SWW, wx = i - k * BL_SWW;
+            const int y = (k < 3) ? (-1 - k) : (g.h + (k - 3));
+            const int ys = (k < 3) ? (1 + k) : (g.h - 2 - (k - 3));
+            const int r = y - (oy - 3), rs = ys - (oy - 3);
+            if (r >= 0 && r < SH && rs >= 0 && rs < SH) s_in[r][wx] = s_in[rs][wx];
+        }
+        __syncthreads();
+    }
+
+    const int q = tid & 31, ty0 = (tid >> 5) * R;               // lane = word column, warp = strip
+    const int gx = ox + 4 * q;
+    const int nrows = min(R, g.h - (oy + ty0));                 // output rows of this strip inside the level
+    if (nrows <= 0 || gx >= g.w) return;
+    const uint32_t* src = &s_in[ty0][q + 3];                    // staged row ty0 + t feeds step t; output row ty0 + t - 6
+    uint8_t* dst = out + (size_t)(oy + ty0) * g.pitch + gx;     // pitch >= round_up(w, 4): whole words can be stored
+    float4 ring[7];
+#pragma unroll
+    for (int u = 0; u < 6; ++u) ring[u] = blur_row4(src + u * BL_SWW, k0, k1, k2, k3);
+    for (int t0 = 6; t0 < nrows + 6; t0 += 7) {
+#pragma unroll
+        for (int u = 0; u < 7; ++u) {
+            const int t = t0 + u;                                // t % 7 == (6 + u) % 7
+            if (t < nrows + 6) {
+                ring[(6 + u) % 7] = blur_row4(src + t * BL_SWW, k0, k1, k2, k3);
+                const uint32_t packed = blur_col4(ring[u % 7], ring[(u + 1) % 7], ring[(u + 2) % 7], ring[(u + 3) % 7],
+                                                  ring[(u + 4) % 7], ring[(u + 5) % 7], ring[(u + 6) % 7], k0, k1, k2, k3);
+                *reinterpret_cast<uint32_t*>(dst + (size_t)(t - 6) * g.pitch) = packed;
+            }
+        }
+    }
+}
+
 int launch_blur(b200vo_ctx* ctx, int first_slot, int n) {
     const LevelMaps& maps = *reinterpret_cast<const LevelMaps*>(ctx->tmap_blur);
     LevelTiles lt;
@@ -166,8 +285,16 @@ int launch_blur(b200vo_ctx* ctx, int first_slot, int n) {
     }
     for (int l = 0; l < kLevels; ++l) {
         const LevelGeom& g = ctx->store.lv[l];
-        dim3 grid(div_up(g.w, BL_W), div_up(g.h, BL_H), n);
-        launch_k(ctx, blur_kernel<false>, dim3(grid), dim3(256), 0, ctx->store, lt, l, first_slot, maps, ctx->use_tma ? 1 : 0);
+        if (ctx->use_tma && ctx->blur_rows == 16) {
+            dim3 grid(div_up(g.w, BL_W), div_up(g.h, 8 * 16), n);
+            launch_k(ctx, blur_strip_kernel<16>, dim3(grid), dim3(256), 0, ctx->store, l, first_slot, ctx->tmap_blur16[l]);
+        } else if (ctx->use_tma && ctx->blur_rows == 24) {
+            dim3 grid(div_up(g.w, BL_W), div_up(g.h, 8 * 24), n);
+            launch_k(ctx, blur_strip_kernel<24>, dim3(grid), dim3(256), 0, ctx->store, l, first_slot, ctx->tmap_blur24[l]);
+        } else {
+            dim3 grid(div_up(g.w, BL_W), div_up(g.h, BL_H), n);
+            launch_k(ctx, blur_kernel<false>, dim3(grid), dim3(256), 0, ctx->store, lt, l, first_slot, maps, ctx->use_tma ? 1 : 0);
+        }
         B200VO_LAUNCH_CHECK(ctx);
     }
     return B200VO_OK;

@@ -22,6 +22,8 @@ constexpr int kFastBoxWideW = 160;                 // fast.cu: the 134-pixel-wid
 inline bool fast_level_is_wide(int level) { return level <= 4; }
 constexpr int kBlurBoxW = 160, kBlurBoxH = 38;     // blur.cu: 128+2*16 x 32+6
 constexpr int kResizeBoxW = 176, kResizeBoxH = 24; // pyramid.cu: source footprint of a 128x16 output tile at scale ~1.2
+constexpr int kResizeStripRows = 16;                // pyramid.cu, large batches: 8 warp strips x 16 output rows per CTA
+constexpr int kResizeStripBoxH = 160;               // source rows of 128 output rows at scale ~1.2 (checked per level at create time)
 constexpr int kBriefReach = 19;                     // rotated pattern points stay within |coordinate| <= 18 (max pattern radius 18.38)
 constexpr int kOrientBoxW = 48, kOrientBoxH = 31;   // orient_brief.cu: 31-px disc row + up to 15 bytes of alignment shift, per keypoint
 constexpr int kBriefBoxW = 64, kBriefBoxH = 39;     // orient_brief.cu: (2*19+1)-px window + up to 15 bytes of alignment shift, per keypoint
@@ -159,11 +161,18 @@ struct b200vo_ctx {
     // TMA descriptors: one per pyramid level and consumer (the box shape is part of the descriptor)
     CUtensorMap tmap_fast[b200vo::kLevels];
     CUtensorMap tmap_blur[b200vo::kLevels];
+    CUtensorMap tmap_blur16[b200vo::kLevels];    // blur_strip_kernel<16>: box 160 x 134
+    CUtensorMap tmap_blur24[b200vo::kLevels];    // blur_strip_kernel<24>: box 160 x 198
     CUtensorMap tmap_resize[b200vo::kLevels];    // [l] = level l as the SOURCE of level l+1
+    CUtensorMap tmap_resize_strip[b200vo::kLevels];   // the same with the tall box of resize_strip_kernel
+    bool resize_strip_ok[b200vo::kLevels];       // [l]: level l's tiles fit the tall box (else resize_tma_kernel)
+    bool resize_strip;         // B200VO_RESIZE_STRIP=0 keeps resize_tma_kernel for large batches too
     CUtensorMap tmap_orient[b200vo::kLevels];    // per-keypoint disc box on the unblurred level
     CUtensorMap tmap_brief[b200vo::kLevels];     // per-keypoint pattern box on the BLURRED level
     bool fused_describe;       // describe_kernel (default) or the three round-1 kernels (B200VO_DESCRIBE=0)
     bool use_tma;
+    int blur_rows;             // rows per warp strip of the large-batch blur (16 or 24; 0: the two-pass tile kernel; B200VO_BLUR_R)
+    int match_variant;         // inner-loop variant of match_kernel (see match.cu)
     int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC, 2: full Harley-Seal (4 POPC), 3: 3 CSA + 5 POPC (default)
     bool repack_kernel;        // device-side ingest of gray frames by kernel (default) or cudaMemcpy3DAsync (B200VO_REPACK_KERNEL=0)
     bool pdl;                  // programmatic dependent launch for the current call (small batches only; B200VO_PDL=0 disables)

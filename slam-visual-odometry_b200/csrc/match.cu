@@ -94,7 +94,15 @@ __device__ __forceinline__ void resolve_pair(const MatchArgs& a, int pair, const
     }
 }
 
-template <int R, int CSA>
+// V selects the inner-loop variant (B200VO_MATCH_V, A/B knob):
+//   0  round-1 loop: after the warp reduction lane 0 merges every column minimum with a shared atomicMin
+//   1  lane (j & 31) keeps the reduced minimum of column j in a register and the warp merges 32 columns with ONE shared
+//      atomicMin per lane: the compiler expands a shared atomic at a warp-uniform address into a second CREDUX plus a
+//      leader election (~10 instructions per column); packed words are formed with + instead of | so the shift-and-add
+//      is one IMAD on the FMA pipe
+//   2  as 1, and the last of the R rows takes the full Harley-Seal tree (4 POPC + 22 LOP3): 19 instead of 20 POPC per
+//      column of four rows, which balances the POPC pipe (8 clk per warp instruction) against the ALU pipe (2 clk)
+template <int R, int CSA, int V>
 __global__ void __launch_bounds__(MT_THREADS)
 match_kernel(MatchArgs a) {
     pdl_grid_sync();
@@ -141,20 +149,44 @@ match_kernel(MatchArgs a) {
     __syncthreads();
 
     const int lane = tid & 31;
+    if (V == 0) {
 #pragma unroll 2
-    for (int j = 0; j < ncols; ++j) {
-        const uint4 t0 = *reinterpret_cast<const uint4*>(&s_t[j * 8]);
-        const uint4 t1 = *reinterpret_cast<const uint4*>(&s_t[j * 8 + 4]);
-        uint32_t colmin = 0xFFFFFFFFu;
-        const uint32_t colidx = (uint32_t)(col0 + j);
+        for (int j = 0; j < ncols; ++j) {
+            const uint4 t0 = *reinterpret_cast<const uint4*>(&s_t[j * 8]);
+            const uint4 t1 = *reinterpret_cast<const uint4*>(&s_t[j * 8 + 4]);
+            uint32_t colmin = 0xFFFFFFFFu;
+            const uint32_t colidx = (uint32_t)(col0 + j);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const uint32_t d = hamming256<CSA>(qd[r], t0, t1);
-            best[r] = min(best[r], (d << 16) | colidx);
-            colmin = min(colmin, (d << 16) + rowpack[r]);
+            for (int r = 0; r < R; ++r) {
+                const uint32_t d = hamming256<CSA>(qd[r], t0, t1);
+                best[r] = min(best[r], (d << 16) | colidx);
+                colmin = min(colmin, (d << 16) + rowpack[r]);
+            }
+            colmin = __reduce_min_sync(0xffffffffu, colmin);
+            if (lane == 0) atomicMin(&s_col[j], colmin);
         }
-        colmin = __reduce_min_sync(0xffffffffu, colmin);
-        if (lane == 0) atomicMin(&s_col[j], colmin);
+    } else {
+        uint32_t mycol = 0xFFFFFFFFu;          // reduced minimum of column (j & ~31) + lane
+        for (int j0 = 0; j0 < ncols; j0 += 32) {
+            const int nj = min(32, ncols - j0);
+#pragma unroll 2
+            for (int jj = 0; jj < nj; ++jj) {
+                const int j = j0 + jj;
+                const uint4 t0 = *reinterpret_cast<const uint4*>(&s_t[j * 8]);
+                const uint4 t1 = *reinterpret_cast<const uint4*>(&s_t[j * 8 + 4]);
+                uint32_t colmin = 0xFFFFFFFFu;
+                const uint32_t colidx = (uint32_t)(col0 + j);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const uint32_t d = (V == 2 && R >= 4 && r == R - 1) ? hamming256<2>(qd[r], t0, t1) : hamming256<CSA>(qd[r], t0, t1);
+                    best[r] = min(best[r], (d << 16) + colidx);
+                    colmin = min(colmin, (d << 16) + rowpack[r]);
+                }
+                colmin = __reduce_min_sync(0xffffffffu, colmin);
+                if (jj == lane) mycol = colmin;
+            }
+            if (lane < nj) atomicMin(&s_col[j0 + lane], mycol);
+        }
     }
 
 #pragma unroll
@@ -271,11 +303,14 @@ static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_
     a.chunk = chunk;
     dim3 grid(div_up(n2max, chunk), row_tiles, npairs);
     const int csa = ctx->match_csa;
+    const int variant = ctx->match_variant;
+#define LAUNCH_MATCH_V(RR, VV) \
+    do { if (csa == 3) launch_k(ctx, match_kernel<RR, 3, VV>, dim3(grid), dim3(MT_THREADS), 0, a); \
+         else if (csa == 2) launch_k(ctx, match_kernel<RR, 2, VV>, dim3(grid), dim3(MT_THREADS), 0, a); \
+         else if (csa == 1) launch_k(ctx, match_kernel<RR, 1, VV>, dim3(grid), dim3(MT_THREADS), 0, a); \
+         else launch_k(ctx, match_kernel<RR, 0, VV>, dim3(grid), dim3(MT_THREADS), 0, a); } while (0)
 #define LAUNCH_MATCH(RR) \
-    do { if (csa == 3) launch_k(ctx, match_kernel<RR, 3>, dim3(grid), dim3(MT_THREADS), 0, a); \
-         else if (csa == 2) launch_k(ctx, match_kernel<RR, 2>, dim3(grid), dim3(MT_THREADS), 0, a); \
-         else if (csa == 1) launch_k(ctx, match_kernel<RR, 1>, dim3(grid), dim3(MT_THREADS), 0, a); \
-         else launch_k(ctx, match_kernel<RR, 0>, dim3(grid), dim3(MT_THREADS), 0, a); } while (0)
+    do { if (variant == 2) LAUNCH_MATCH_V(RR, 2); else if (variant == 1) LAUNCH_MATCH_V(RR, 1); else LAUNCH_MATCH_V(RR, 0); } while (0)
     switch (R) {
         case 8: LAUNCH_MATCH(8); break;
         case 6: LAUNCH_MATCH(6); break;
@@ -284,6 +319,7 @@ static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_
         case 2: LAUNCH_MATCH(2); break;
         default: LAUNCH_MATCH(1); break;
     }
+#undef LAUNCH_MATCH_V
 #undef LAUNCH_MATCH
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;

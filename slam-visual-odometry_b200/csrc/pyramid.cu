@@ -200,6 +200,98 @@ resize_tma_kernel(StoreView sv, const int* __restrict__ tab, int level, int firs
     }
 }
 
+// Large batches: a warp walks down a strip of R output rows x 128 columns and keeps the horizontal 8.8 results of the two
+// current source rows in registers.  resize_tma_kernel spends ~50 thread-instructions per output pixel (ncu, round 2):
+// the u16 tile's shared-memory round trip, the per-row table reads from global memory and the setup of a thread that
+// produces only 8 pixels.  Here a source row is filtered horizontally exactly once per lane (8 byte loads, 8 IMAD) as
+// the walk reaches it, the vertical 16.16 pass is 8 IMAD, and the four result bytes are picked with three PRMT
+// (v >> 16 is byte 2 of v): ~45 instructions per 4 output pixels.  The tile is 8 strips tall (128 x 8R outputs); its
+// source footprint arrives as ONE TMA box of 176 x kResizeStripBoxH bytes; the row taps of the tile are staged in shared
+// memory while the box is in flight.  Same integer arithmetic as above, bit-exact.
+template <int R>
+__global__ void __launch_bounds__(256)
+resize_strip_kernel(StoreView sv, const int* __restrict__ tab, int level, int first_slot, const __grid_constant__ CUtensorMap tmap) {
+    pdl_grid_sync();
+    constexpr int TH = 8 * R;
+    __shared__ __align__(128) uint8_t s_src[kResizeStripBoxH * kResizeBoxW];
+    __shared__ int s_yo[TH], s_yc[TH];
+    __shared__ __align__(8) uint64_t s_bar;
+    const LevelGeom gs = sv.lv[level - 1];
+    const LevelGeom gd = sv.lv[level];
+    const int dwp = (gd.w + 3) & ~3, dhp = (gd.h + 3) & ~3;
+    const int* __restrict__ xofs = tab + gd.tab_off;
+    const int* __restrict__ xc1 = xofs + dwp;
+    const int* __restrict__ yofs = xc1 + dwp;
+    const int* __restrict__ yc1 = yofs + dhp;
+    const int slot = ring_slot(first_slot, blockIdx.z, sv.slots);
+    const int x0 = blockIdx.x * RZ_W, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.x;
+    const int sx0 = xofs[x0] & ~15;
+    const int sy0 = yofs[y0];
+
+    if (tid == 0) { tma::mbar_init(&s_bar, 1); tma::fence_mbar_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        tma::mbar_arrive_expect_tx(&s_bar, kResizeStripBoxH * kResizeBoxW);
+        tma::load_3d(s_src, &tmap, &s_bar, sx0, sy0, slot);
+    }
+    for (int i = tid; i < TH; i += 256) {
+        const int y = y0 + i;
+        if (y < gd.h) { s_yo[i] = yofs[y] - sy0; s_yc[i] = yc1[y]; }
+    }
+    // this lane's four output columns: tap offsets relative to the box and weights, in registers
+    const int cx = (tid & 31) * 4;
+    int o0[4], o1[4];
+    uint32_t c0[4], c1[4];
+    {
+        const int4 xo = *reinterpret_cast<const int4*>(xofs + x0 + cx);
+        const int4 xc = *reinterpret_cast<const int4*>(xc1 + x0 + cx);
+        const int xos[4] = {xo.x, xo.y, xo.z, xo.w}, xcs[4] = {xc.x, xc.y, xc.z, xc.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool valid = (x0 + cx + i) < gd.w;
+            o0[i] = valid ? xos[i] - sx0 : 0;
+            o1[i] = valid ? min(xos[i] + 1, gs.w - 1) - sx0 : 0;
+            c1[i] = (uint32_t)xcs[i];
+            c0[i] = 256u - c1[i];
+        }
+    }
+    __syncthreads();
+    tma::mbar_wait(&s_bar, 0);
+
+    const int ty0 = (tid >> 5) * R;                              // warp = strip
+    const int nrows = min(R, gd.h - (y0 + ty0));
+    if (nrows <= 0 || x0 + cx >= gd.w) return;
+    const int rmax = gs.h - 1 - sy0;                             // last source row, box-relative
+    auto hpass = [&](int r, uint32_t* h) {                       // 8.8 fixed point: h = I[s]*(256-c1) + I[s+1]*c1
+        const uint8_t* row = s_src + r * kResizeBoxW;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = row[o0[i]] * c0[i] + row[o1[i]] * c1[i];
+    };
+    int cur = s_yo[ty0];
+    uint32_t a[4], b[4];
+    hpass(cur, a);
+    hpass(min(cur + 1, rmax), b);
+    uint8_t* dst = sv.pyr + (size_t)slot * sv.slot_bytes + gd.offset + (size_t)(y0 + ty0) * gd.pitch + x0 + cx;
+    for (int i = 0; i < nrows; ++i) {
+        const int ys = s_yo[ty0 + i];
+        const uint32_t cy1 = (uint32_t)s_yc[ty0 + i], cy0 = 256u - cy1;
+#pragma unroll 1
+        while (cur < ys) {                                       // warp-uniform: one or two steps at scale 1.2
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] = b[k];
+            ++cur;
+            hpass(min(cur + 1, rmax), b);
+        }
+        // vertical pass, 16.16 fixed point, +0.5, >> 16: the result is byte 2 of each sum
+        const uint32_t v0 = a[0] * cy0 + b[0] * cy1 + 32768u, v1 = a[1] * cy0 + b[1] * cy1 + 32768u;
+        const uint32_t v2 = a[2] * cy0 + b[2] * cy1 + 32768u, v3 = a[3] * cy0 + b[3] * cy1 + 32768u;
+        const uint32_t lo = __byte_perm(v0, v1, 0x0062), hi = __byte_perm(v2, v3, 0x0062);      // (v0 >> 16) & 0xFF | ((v1 >> 16) & 0xFF) << 8
+        *reinterpret_cast<uint32_t*>(dst) = __byte_perm(lo, hi, 0x5410);
+        dst += gd.pitch;
+    }
+}
+
 int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int first_slot, int n) {
     const LevelGeom& g = ctx->store.lv[0];
     dim3 block(64), grid(div_up(div_up(g.w, 4), 64), g.h, n);
@@ -211,7 +303,10 @@ int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t 
 int launch_pyramid(b200vo_ctx* ctx, int first_slot, int n) {
     for (int l = 1; l < kLevels; ++l) {
         const LevelGeom& g = ctx->store.lv[l];
-        if (ctx->use_tma) {
+        if (ctx->use_tma && ctx->resize_strip && ctx->resize_strip_ok[l] && n > kMergedLevelsMaxFrames) {
+            dim3 grid(div_up(g.w, RZ_W), div_up(g.h, 8 * kResizeStripRows), n);
+            launch_k(ctx, resize_strip_kernel<kResizeStripRows>, dim3(grid), dim3(256), 0, ctx->store, ctx->d_tab, l, first_slot, ctx->tmap_resize_strip[l - 1]);
+        } else if (ctx->use_tma) {
             dim3 grid(div_up(g.w, RZ_W), div_up(g.h, RZ_H), n);
             launch_k(ctx, resize_tma_kernel, dim3(grid), dim3(256), 0, ctx->store, ctx->d_tab, l, first_slot, ctx->tmap_resize[l - 1]);
         } else {
