@@ -28,6 +28,7 @@
  * b200vo_relative_pose              estimate_relative_pose: findEssentialMat + recoverPose
  *                                     src/visual_odometry.cpp:182-281
  * b200vo_process_frame              one whole streaming step of process_frame    src/visual_odometry.cpp:323-378
+ * b200vo_process_frame_begin/_end   the same step in two halves (host work overlaps) src/visual_odometry.cpp:103-117,323-378
  * b200vo_process_pairs              the batched detect-free remainder of process_frame for a
  *                                     contiguous range of frame pairs  src/visual_odometry.cpp:340-366
  * b200vo_chain_pose                 invert_relative_... + compose_next_...  src/visual_odometry.cpp:292-314,350-360
@@ -44,7 +45,7 @@
 extern "C" {
 #endif
 
-#define B200VO_ABI_VERSION 2
+#define B200VO_ABI_VERSION 3
 #define B200VO_NLEVELS 8            /* reference src/visual_odometry.cpp:67 */
 
 typedef enum {
@@ -210,6 +211,13 @@ int b200vo_relative_pose(b200vo_ctx* ctx, int slot1, int slot2, int64_t pair_id,
  * synchronise four times).  kp / desc / essential may be NULL; rec is required when prev_slot >= 0. */
 int b200vo_process_frame(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int channels, int slot, int prev_slot, int64_t pair_id,
                          b200vo_keypoint* kp, uint8_t* desc, int cap, int* n, b200vo_pose_record* rec, double* essential);
+/* The same step in two halves, so the caller's per-frame host work on the features (the reference fills cv::KeyPoint and
+ * the descriptor Mat, src/visual_odometry.cpp:103-117) overlaps the pair's kernels: _begin enqueues the whole step and
+ * returns as soon as the frame's features are on the host; _end waits for the pair and hands out the record and E
+ * (rec is required when the step had prev_slot >= 0).  One step at a time per context. [ext] */
+int b200vo_process_frame_begin(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int channels, int slot, int prev_slot, int64_t pair_id,
+                               b200vo_keypoint* kp, uint8_t* desc, int cap, int* n);
+int b200vo_process_frame_end(b200vo_ctx* ctx, b200vo_pose_record* rec, double* essential);
 
 /* Batched: pairs (first_slot+i, first_slot+i+1), i < npairs, with pair ids first_pair_id+i.
  * Features of all touched slots must exist (b200vo_detect).  Records are copied to `out`. */

@@ -38,7 +38,7 @@ POSE_RECORD_DTYPE = np.dtype([("R", "<f8", (9,)), ("t", "<f8", (3,)), ("n_matche
                               ("dist_mean", "<f8"), ("epi_residual", "<f8"), ("dist_min", "<f4"), ("dist_max", "<f4"),
                               ("dist_median", "<f4"), ("reserved", "<i4")])
 RECORD_BYTES = POSE_RECORD_DTYPE.itemsize
-ABI_VERSION = 2
+ABI_VERSION = 3
 assert KEYPOINT_DTYPE.itemsize == 32 and DMATCH_DTYPE.itemsize == 16 and RECORD_BYTES == 160
 
 
@@ -53,7 +53,7 @@ EXPORTS = [
     "b200vo_synchronize", "b200vo_level_info", "b200vo_max_keypoints", "b200vo_upload_frames",
     "b200vo_upload_frames_device", "b200vo_detect", "b200vo_get_features", "b200vo_get_pyramid_level",
     "b200vo_get_fast_candidates", "b200vo_set_features", "b200vo_match_descriptors",
-    "b200vo_match_descriptors_device", "b200vo_knn_match_descriptors", "b200vo_match", "b200vo_relative_pose", "b200vo_process_frame", "b200vo_process_pairs",
+    "b200vo_match_descriptors_device", "b200vo_knn_match_descriptors", "b200vo_match", "b200vo_relative_pose", "b200vo_process_frame", "b200vo_process_frame_begin", "b200vo_process_frame_end", "b200vo_process_pairs",
     "b200vo_process_pairs_device", "b200vo_five_point", "b200vo_score_models", "b200vo_recover_pose",
     "b200vo_draw_samples", "b200vo_chain_pose", "b200vo_chain_trajectory", "b200vo_measure_popc_rate", "b200vo_fundamental_from_essential", "b200vo_enable_timing",
     "b200vo_get_stage_times", "b200vo_kernel_launches", "b200vo_stream",

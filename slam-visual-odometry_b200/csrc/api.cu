@@ -156,6 +156,8 @@ void b200vo_destroy(b200vo_ctx* ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_frame_pinned) cudaFreeHost(ctx->h_frame_pinned);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->feat_ready) cudaEventDestroy(ctx->feat_ready);
+    if (ctx->feat_copied) cudaEventDestroy(ctx->feat_copied);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -193,6 +195,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
     ctx->copy_stream = nullptr; ctx->stage_idx = 0;
     ctx->h_frame_pinned = nullptr; ctx->frame_pinned_bytes = 0;
     for (int i = 0; i < 2; ++i) { ctx->d_stage[i] = nullptr; ctx->stage_bytes[i] = 0; ctx->stage_ready[i] = nullptr; ctx->stage_free[i] = nullptr; }
+    ctx->feat_ready = ctx->feat_copied = nullptr; ctx->frame_open = ctx->frame_has_pair = false;
     ctx->launches = 0; ctx->timing = false;
     std::memset(&ctx->times, 0, sizeof(ctx->times));
     for (auto& ev : ctx->ev) ev = nullptr;
@@ -210,6 +213,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         TRYCUDA(cudaEventCreateWithFlags(&ctx->stage_free[i], cudaEventDisableTiming));
     }
     for (auto& ev : ctx->ev) TRYCUDA(cudaEventCreate(&ev));
+    TRYCUDA(cudaEventCreateWithFlags(&ctx->feat_ready, cudaEventDisableTiming));
+    TRYCUDA(cudaEventCreateWithFlags(&ctx->feat_copied, cudaEventDisableTiming));
 
     // ---- pyramid geometry and per-level budgets
     StoreView& sv = ctx->store;
@@ -724,27 +729,39 @@ int b200vo_relative_pose(b200vo_ctx* ctx, int slot1, int slot2, int64_t pair_id,
     return B200VO_OK;
 }
 
-// One streaming step of VisualOdometry::process_frame (reference src/visual_odometry.cpp:323-378) with a
-// single host synchronisation: upload + detect of the new frame, the pair (prev_slot, slot) if
-// prev_slot >= 0, and every result the reference's per-frame code reads -- features, pose record, E.
-int b200vo_process_frame(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int channels, int slot, int prev_slot, int64_t pair_id,
-                         b200vo_keypoint* kp, uint8_t* desc, int cap, int* n, b200vo_pose_record* rec, double* essential) {
-    if (!ctx || !host || !slot_ok(ctx, slot) || prev_slot >= ctx->store.slots || !n || (prev_slot >= 0 && !rec)) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
+// One streaming step of VisualOdometry::process_frame (reference src/visual_odometry.cpp:323-378): upload + detect of the
+// new frame, the pair (prev_slot, slot) if prev_slot >= 0, and every result the reference's per-frame code reads --
+// features, pose record, E.  Split in two so that the caller's host work on the features (the reference fills
+// cv::KeyPoint / descriptor Mat per frame, :103-117) overlaps the pair's kernels:
+//   begin: enqueue everything; the features leave on the COPY stream behind an event recorded after the descriptor
+//          kernel, so no copy sits between two kernels of the compute stream (a copy node would also end the chain of
+//          programmatic dependent launches); returns when the features are on the host
+//   end:   wait for the compute stream, hand out the record and E
+static int frame_begin_impl(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int channels, int slot, int prev_slot, int64_t pair_id,
+                            b200vo_keypoint* kp, uint8_t* desc, int cap, int* n) {
+    if (!ctx || !host || !slot_ok(ctx, slot) || prev_slot >= ctx->store.slots || !n) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
+    if (ctx->frame_open) { set_error("b200vo_process_frame_begin called twice without b200vo_process_frame_end"); return B200VO_ERR_BAD_ARG; }
     const StoreView& sv = ctx->store;
+    const LevelGeom& g0 = sv.lv[0];
     int rc;
     if (channels != 1 && channels != 3) { set_error("channels must be 1 or 3"); return B200VO_ERR_BAD_ARG; }
-    if (pitch < (size_t)sv.lv[0].w * channels) { set_error("pitch too small"); return B200VO_ERR_BAD_ARG; }
-    {
-        // The reference hands over an ordinary (pageable) cv::Mat.  cudaMemcpyAsync from pageable memory goes through the
-        // driver's own bounce buffers at a fraction of the PCIe rate and blocks the host meanwhile; one memcpy of the
-        // frame's rows into the context's pinned frame buffer followed by a true asynchronous copy is ~40 us cheaper per
-        // 1241x376 frame.  The buffer is private to this entry point, whose previous call ended with a stream
-        // synchronisation, so it is free.  Pinned callers (cudaHostAlloc / cudaHostRegister) skip the extra memcpy.
-        cudaPointerAttributes pa;
-        const bool pinned = cudaPointerGetAttributes(&pa, host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    if (pitch < (size_t)g0.w * channels) { set_error("pitch too small"); return B200VO_ERR_BAD_ARG; }
+    B200VO_CUDA_CHECK(cudaSetDevice(ctx->device));
+    // The reference hands over an ordinary (pageable) cv::Mat.  cudaMemcpyAsync from pageable memory goes through the
+    // driver's own bounce buffers at a fraction of the PCIe rate and blocks the host meanwhile; the rows are copied into
+    // the context's pinned frame buffer instead (private to this entry point, whose previous step ended with a stream
+    // synchronisation, so it is free).  A gray frame is laid out there with level 0's 128-byte row pitch, so ONE dense
+    // asynchronous copy on the compute stream lands it in the frame store: no staging buffer, no repack kernel, no
+    // hop between two streams.  BGR frames and callers whose memory is already pinned keep the staged path.
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, host) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    if (!pinned) (void)cudaGetLastError();
+    if (!pinned || (channels == 1 && pitch == (size_t)g0.pitch)) {
+        const size_t row = (size_t)g0.w * channels;
+        const size_t dpitch = (channels == 1) ? (size_t)g0.pitch : row;
+        const size_t need = dpitch * (g0.h - 1) + row;               // the last row ends with its last pixel
+        const uint8_t* src = host;
         if (!pinned) {
-            (void)cudaGetLastError();
-            const size_t row = (size_t)sv.lv[0].w * channels, need = row * sv.lv[0].h;
             if (ctx->frame_pinned_bytes < need) {
                 if (ctx->h_frame_pinned) cudaFreeHost(ctx->h_frame_pinned);
                 ctx->h_frame_pinned = nullptr; ctx->frame_pinned_bytes = 0;
@@ -752,12 +769,14 @@ int b200vo_process_frame(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int
                 ctx->frame_pinned_bytes = need;
             }
             uint8_t* dst = static_cast<uint8_t*>(ctx->h_frame_pinned);
-            if (pitch == row) std::memcpy(dst, host, need);
-            else for (int y = 0; y < sv.lv[0].h; ++y) std::memcpy(dst + (size_t)y * row, host + (size_t)y * pitch, row);
-            host = dst; pitch = row;
+            if (pitch == dpitch) std::memcpy(dst, host, need);
+            else for (int y = 0; y < g0.h; ++y) std::memcpy(dst + (size_t)y * dpitch, host + (size_t)y * pitch, row);
+            src = dst;
         }
-    }
-    if ((rc = b200vo_upload_frames(ctx, host, 1, pitch, pitch * sv.lv[0].h, channels, slot))) return rc;
+        if (channels == 1) {
+            B200VO_CUDA_CHECK(cudaMemcpyAsync(sv.pyr + (size_t)slot * sv.slot_bytes + g0.offset, src, need, cudaMemcpyHostToDevice, ctx->stream));
+        } else if ((rc = b200vo_upload_frames(ctx, src, 1, dpitch, dpitch * g0.h, channels, slot))) return rc;
+    } else if ((rc = b200vo_upload_frames(ctx, host, 1, pitch, pitch * g0.h, channels, slot))) return rc;
     if ((rc = b200vo_detect(ctx, slot, 1))) return rc;
     // results travel through one pinned block: [count, flags | keypoints | descriptors | record | E]
     const size_t kb = (size_t)sv.kp_cap * sizeof(b200vo_keypoint), db = (size_t)sv.kp_cap * kDescBytes;
@@ -765,27 +784,67 @@ int b200vo_process_frame(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int
     if ((rc = ensure_pinned(ctx, off_E + 9 * sizeof(double)))) return rc;
     uint8_t* hp = static_cast<uint8_t*>(ctx->h_pinned);
     int* cnt_flags = reinterpret_cast<int*>(hp);
-    B200VO_CUDA_CHECK(cudaMemcpyAsync(&cnt_flags[0], sv.kp_count + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    B200VO_CUDA_CHECK(cudaMemcpyAsync(&cnt_flags[1], sv.flags + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    if (kp) B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_kp, sv.kp + (size_t)slot * sv.kp_cap, kb, cudaMemcpyDeviceToHost, ctx->stream));
-    if (desc) B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_desc, sv.desc + (size_t)slot * sv.kp_cap * kDescBytes, db, cudaMemcpyDeviceToHost, ctx->stream));
+    B200VO_CUDA_CHECK(cudaEventRecord(ctx->feat_ready, ctx->stream));
+    B200VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->feat_ready, 0));
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(&cnt_flags[0], sv.kp_count + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    B200VO_CUDA_CHECK(cudaMemcpyAsync(&cnt_flags[1], sv.flags + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (kp) B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_kp, sv.kp + (size_t)slot * sv.kp_cap, kb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (desc) B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_desc, sv.desc + (size_t)slot * sv.kp_cap * kDescBytes, db, cudaMemcpyDeviceToHost, ctx->copy_stream));
+    B200VO_CUDA_CHECK(cudaEventRecord(ctx->feat_copied, ctx->copy_stream));
+    ctx->frame_open = true;
+    ctx->frame_has_pair = prev_slot >= 0;
     if (prev_slot >= 0) {
         if ((rc = run_pairs(ctx, prev_slot, 1, slot, pair_id, nullptr, ctx->opt.ransac_hypotheses))) return rc;
         B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_rec, ctx->pairs.rec, sizeof(b200vo_pose_record), cudaMemcpyDeviceToHost, ctx->stream));
         B200VO_CUDA_CHECK(cudaMemcpyAsync(hp + off_E, ctx->pairs.E, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     }
-    B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    B200VO_CUDA_CHECK(cudaEventSynchronize(ctx->feat_copied));
     *n = cnt_flags[0];
     // an overflowed internal list (score ties) is a soft failure here, as everything on the per-frame path of the
     // reference is: the truncation is deterministic and the pair record carries B200VO_ST_OVERFLOW
     if ((kp || desc) && cap < cnt_flags[0]) { set_error("capacity %d < %d keypoints", cap, cnt_flags[0]); return B200VO_ERR_CAPACITY; }
     if (kp) std::memcpy(kp, hp + off_kp, (size_t)cnt_flags[0] * sizeof(b200vo_keypoint));
     if (desc) std::memcpy(desc, hp + off_desc, (size_t)cnt_flags[0] * kDescBytes);
-    if (prev_slot >= 0) {
+    return B200VO_OK;
+}
+
+int b200vo_process_frame_begin(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int channels, int slot, int prev_slot, int64_t pair_id,
+                               b200vo_keypoint* kp, uint8_t* desc, int cap, int* n) {
+    const int rc = frame_begin_impl(ctx, host, pitch, channels, slot, prev_slot, pair_id, kp, desc, cap, n);
+    if (rc && ctx && ctx->frame_open) {            // a failed step is closed here: nothing stays in flight behind an error
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->copy_stream);
+        ctx->frame_open = false;
+    }
+    return rc;
+}
+
+int b200vo_process_frame_end(b200vo_ctx* ctx, b200vo_pose_record* rec, double* essential) {
+    if (!ctx || !ctx->frame_open) { set_error("b200vo_process_frame_end without b200vo_process_frame_begin"); return B200VO_ERR_BAD_ARG; }
+    ctx->frame_open = false;
+    B200VO_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->frame_has_pair) {
+        if (!rec) { set_error("the step ran a pair: rec is required"); return B200VO_ERR_BAD_ARG; }
+        const StoreView& sv = ctx->store;
+        const size_t kb = (size_t)sv.kp_cap * sizeof(b200vo_keypoint), db = (size_t)sv.kp_cap * kDescBytes;
+        const size_t off_rec = round_up(64 + kb + db, 64), off_E = off_rec + sizeof(b200vo_pose_record);
+        const uint8_t* hp = static_cast<const uint8_t*>(ctx->h_pinned);
         std::memcpy(rec, hp + off_rec, sizeof(b200vo_pose_record));
         if (essential) std::memcpy(essential, hp + off_E, 9 * sizeof(double));
     }
     return B200VO_OK;
+}
+
+// begin + end: the whole step with one call
+int b200vo_process_frame(b200vo_ctx* ctx, const uint8_t* host, size_t pitch, int channels, int slot, int prev_slot, int64_t pair_id,
+                         b200vo_keypoint* kp, uint8_t* desc, int cap, int* n, b200vo_pose_record* rec, double* essential) {
+    if (prev_slot >= 0 && !rec) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
+    const int rc = b200vo_process_frame_begin(ctx, host, pitch, channels, slot, prev_slot, pair_id, kp, desc, cap, n);
+    if (ctx && ctx->frame_open) {
+        const int rc2 = b200vo_process_frame_end(ctx, rec, essential);
+        return rc ? rc : rc2;
+    }
+    return rc;
 }
 
 int b200vo_process_pairs_device(b200vo_ctx* ctx, int first_slot, int npairs, int64_t first_pair_id, void** records_dev) {

@@ -158,6 +158,9 @@ struct b200vo_ctx {
     uint8_t* d_stage[2]; size_t stage_bytes[2];
     cudaEvent_t stage_ready[2], stage_free[2];
     int stage_idx;
+    // streaming step (b200vo_process_frame_begin / _end): the features leave on the copy stream behind feat_ready
+    cudaEvent_t feat_ready, feat_copied;
+    bool frame_open, frame_has_pair;
     // TMA descriptors: one per pyramid level and consumer (the box shape is part of the descriptor)
     CUtensorMap tmap_fast[b200vo::kLevels];
     CUtensorMap tmap_blur[b200vo::kLevels];

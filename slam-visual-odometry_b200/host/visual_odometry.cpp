@@ -90,10 +90,11 @@ cv::Mat VisualOdometry::process_frame(Frame& frame) {
     int n = 0;
     b200vo_pose_record rec;
     double E[9];
-    check(b200vo_process_frame(ctx_, v.data, v.pitch, v.channels, cur, initialized_ ? previous_slot_ : -1, frame_counter_ - 1,
-                               kp_buf_.data(), desc_buf_.data(), cap, &n, &rec, E), "process_frame");
+    // first half: returns when the features are on the host; the pair's kernels are still running
+    check(b200vo_process_frame_begin(ctx_, v.data, v.pitch, v.channels, cur, initialized_ ? previous_slot_ : -1, frame_counter_ - 1,
+                                     kp_buf_.data(), desc_buf_.data(), cap, &n), "process_frame_begin");
     const b200vo_keypoint* kps = kp_buf_.data();
-    // detect_features(): fill frame.keypoints / frame.descriptors (reference :103-117)
+    // detect_features(): fill frame.keypoints / frame.descriptors (reference :103-117) -- overlaps matching and RANSAC
     frame.keypoints.resize((size_t)n);
     for (int i = 0; i < n; ++i) {
         cv::KeyPoint& k = frame.keypoints[(size_t)i];
@@ -103,6 +104,8 @@ cv::Mat VisualOdometry::process_frame(Frame& frame) {
     cv::Mat d(n, 32, CV_8UC1);
     for (int i = 0; i < n; ++i) std::copy(desc_buf_.data() + (size_t)i * 32, desc_buf_.data() + (size_t)(i + 1) * 32, d.data + (size_t)i * d.step);
     frame.descriptors = d;
+    // second half: the pose record and E of the pair (previous frame, this frame)
+    check(b200vo_process_frame_end(ctx_, &rec, E), "process_frame_end");
     frame.processed = true;
     const cv::Mat display_image = frame.image;      // shares the pixels; nothing is drawn in the headless build
 

@@ -27,7 +27,7 @@ def test_every_declared_symbol_is_exported(built):
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(built.EXPORTS) == names
-    assert lib.b200vo_abi_version() == 2
+    assert lib.b200vo_abi_version() == 3
 
 
 def test_struct_layouts(built):
