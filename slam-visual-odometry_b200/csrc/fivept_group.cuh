@@ -761,10 +761,15 @@ GEOM_HD inline int five_point_group(Exec& ex, GroupShared& gs, const double* pts
                 bool has = false;
                 double root = 0.0;
                 if (r <= cnt) {                            // interval r of cnt + 1
-                    const double flo = horner(d, dk, lo), fhi = horner(d, dk, hi);
+                    double dc[11];                         // the level's polynomial in registers (zero above its degree)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                    for (int i = 0; i <= 10; ++i) dc[i] = (i <= dk) ? d[i] : 0.0;
+                    const double flo = horner_reg10(dc, lo), fhi = horner_reg10(dc, hi);
                     if (flo == 0.0) { if (r == 0) { has = true; root = lo; } }
                     else if (fhi == 0.0) { has = true; root = hi; }
-                    else if ((flo < 0.0) != (fhi < 0.0)) { has = true; root = bracket_root_fast(d, dk, lo, hi, flo); }
+                    else if ((flo < 0.0) != (fhi < 0.0)) { has = true; root = bracket_root_fast_reg10(dc, lo, hi, flo); }
                 }
                 gs.xflag[wr][r] = has ? 1 : 0;
                 if (has) {

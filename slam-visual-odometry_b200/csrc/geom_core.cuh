@@ -97,6 +97,52 @@ GEOM_HD inline double bracket_root_fast(const double* c, int deg, double a, doub
     return x;
 }
 
+// The same with the coefficients of a degree <= 10 polynomial in REGISTERS (c[i] = 0 above the degree) and every
+// loop unrolled.  The exact root path evaluates polynomials of run-time degree from shared memory: one dependent
+// load + FMA per Horner step (~35 cycles) inside up to 64 Newton steps, ten levels deep -- the slowest warp of the
+// streaming step.  Leading zero coefficients leave every intermediate value unchanged (0 * x + c = c exactly), so the
+// results are bit-identical to horner2 / bracket_root_fast on the true degree.
+GEOM_HD inline void horner2_reg10(const double* c, double x, double& f, double& df) {
+    f = c[10];
+    df = 0.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 9; i >= 0; --i) {
+        df = df * x + f;
+        f = f * x + c[i];
+    }
+}
+GEOM_HD inline double horner_reg10(const double* c, double x) {
+    double f = c[10];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 9; i >= 0; --i) f = f * x + c[i];
+    return f;
+}
+GEOM_HD inline double bracket_root_fast_reg10(const double* c, double a, double b, double fa) {
+    double x = 0.5 * (a + b);
+    for (int it = 0; it < 64; ++it) {
+        double f, df;
+        horner2_reg10(c, x, f, df);
+        if (f == 0.0) return x;
+        if ((f < 0.0) == (fa < 0.0)) a = x; else b = x;
+        double xn = x - f / df;
+        const bool newton_ok = (xn > a && xn < b);
+        if (!newton_ok) xn = 0.5 * (a + b);
+        const double step = fabs(xn - x);
+        x = xn;
+        if (newton_ok && step < 1e-6 * (fabs(x) + 1e-3)) {
+            horner2_reg10(c, x, f, df);
+            const double x2 = x - f / df;
+            return (x2 > a && x2 < b) ? x2 : x;
+        }
+        if (b - a <= 4e-16 * fabs(x) + 1e-300) return x;
+    }
+    return x;
+}
+
 // ----------------------------------------------------------------------------- five-point
 // lin x lin -> quad index, quad x lin -> cubic column (Nister's column order:
 // x3 y3 x2y xy2 x2z x2 y2z y2 xyz xy | xz2 xz x yz2 yz y z3 z2 z 1)
