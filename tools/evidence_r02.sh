@@ -1,0 +1,8 @@
+set -x
+python bench.py > gpurun_out/bench_r02_final.json 2> gpurun_out/bench_r02_final.err; echo bench_rc=$?
+python bench.py --impl reference > gpurun_out/bench_r02_final_reference.json 2>/dev/null; echo ref_rc=$?
+python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:resize|fast_|select_kernel|blur_|describe|match_kernel|filter_kernel|five_point|score_kernel|pose_|finalize|repack|clear_detect|adaptive|bgr2gray|popc_rate|orient|brief' -c 2000 --csv --log-file gpurun_out/launches_r02_final.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-extras > gpurun_out/launches_ncu.log 2>&1; echo ncu_rc=$?
+python tools/summarize_launches.py gpurun_out/launches_r02_final.csv > gpurun_out/launches_r02_final_summary.md 2>&1
+python tools/stream_step_launches.py > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02_streaming.csv python tools/stream_step_launches.py > gpurun_out/launches_stream_ncu.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches_r02_streaming.csv > gpurun_out/launches_r02_streaming_summary.md 2>&1
+tools/ncu_capture.sh gpurun_out/ncu_r02_final 'resize_strip|fast_kernel|select_kernel|blur_strip|describe_kernel|match_kernel|filter_kernel|five_point|score_kernel|pose_|finalize' 60 resize_strip,blur_strip -- python tools/stage_times.py --frames 61 --reps 1

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Per-source-line table of one kernel launch from an .ncu-rep captured with --import-source on:
-   python tools/ncu_src.py report.ncu-rep kernel_regex [launch_skip] [top]
+   python tools/ncu_src.py report.ncu-rep kernel_regex [launch_skip] [top] [samples]
+("samples" as the fifth argument sorts by stall samples instead of executed instructions: latency-bound kernels)
 columns: line, warp-instructions executed (share), avg active threads, stall samples (share), source text."""
 import csv, io, subprocess, sys
 
@@ -32,6 +33,6 @@ tot_i = sum(r[1] for v in files.values() for r in v)
 tot_s = sum(r[3] for v in files.values() for r in v)
 print("total warp-instructions %.4g, samples %d" % (tot_i, tot_s))
 rows = [(f,) + r for f, v in files.items() for r in v]
-rows.sort(key=lambda r: -r[2])
+rows.sort(key=lambda r: -(r[4] if len(sys.argv) > 5 and sys.argv[5] == 'samples' else r[2]))
 for f, ln, ie, te, sm, src in rows[:top]:
     print("%-18s %5d  winst %5.1f%%  lanes %4.1f  samples %5.1f%%  %s" % (f, ln, 100 * ie / max(tot_i, 1), te / max(ie, 1), 100 * sm / max(tot_s, 1), src[:110]))
