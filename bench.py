@@ -25,6 +25,7 @@ on the host cores, one worker process per core over contiguous pair ranges.
 """
 import argparse
 import ctypes
+import itertools
 import json
 import os
 import subprocess
@@ -267,11 +268,29 @@ def algorithmic_bytes(ctx, nfeatures):
     }
 
 
+def batch_plan(F, B, sizes):
+    """Launch batches of an F-frame sequence in a ring of B + 1 slots: (first slot, frames in the batch, frames done
+    before, first pair slot, pairs, pairs done before).  `sizes` gives the first batch sizes; after it full batches."""
+    done_f, done_p, prev = 0, 0, 0
+    for n in itertools.chain(sizes, itertools.repeat(B)):
+        n = min(n, F - done_f)
+        if n <= 0:
+            break
+        if F - done_f - n == 1:                                  # never leave a single trailing frame to a batch of its own
+            n += 1 if n < B else -1
+        first = 0 if done_f == 0 else (prev + 1) % (B + 1)
+        p0, np_ = (first, n - 1) if done_f == 0 else (prev, n)
+        yield first, n, done_f, p0, np_, done_p
+        prev = (first + n - 1) % (B + 1)
+        done_f += n
+        done_p += np_
+
+
 class SeqRunner:
     """One rank's share of a sequence through the C ABI: frames [0, F) of `d_frames` (device) / `h_frames`
     (pinned host) in launch batches of B frames; pair ids start at pair0.  Records land in self.recs_dev."""
 
-    def __init__(self, torch, b200vo, W, H, NF, hyp, B, local, d_frames, h_frames, pair0, **opts):
+    def __init__(self, torch, b200vo, W, H, NF, hyp, B, local, d_frames, h_frames, pair0, recs_dev=None, **opts):
         self.torch, self.b = torch, b200vo
         self.W, self.H, self.F, self.B = W, H, int(d_frames.shape[0]), max(2, min(B, int(d_frames.shape[0])))
         self.npairs = self.F - 1
@@ -281,28 +300,26 @@ class SeqRunner:
         self.ctx = b200vo.Context(W, H, device=local, nfeatures=NF, max_frames=self.B + 1, ransac_hypotheses=hyp, **opts)
         self.stream = torch.cuda.ExternalStream(self.ctx.stream(), device=torch.device("cuda", local))
         self.RB = b200vo.RECORD_BYTES
-        self.recs_dev = torch.zeros(max(self.npairs, 1) * self.RB, dtype=torch.uint8, device=self.dev)
+        self.recs_dev = recs_dev if recs_dev is not None else torch.zeros(max(self.npairs, 1) * self.RB, dtype=torch.uint8, device=self.dev)
         self.fb = W * H
         self.e2e_sizes = None
 
+    def kernel_launches(self):
+        return self.ctx.kernel_launches()
+
+    def e2e_candidates(self):
+        return e2e_schedule_candidates(self.F, self.B)
+
     def batches(self, short_first=False):
-        """(first slot, frames in the batch, frames done before, first pair slot, pairs, pairs done before).
-        short_first (the e2e leg) follows self.e2e_sizes, the schedule choose_e2e_schedule picked for this rank."""
-        B, F = self.B, self.F
-        sizes = self.e2e_sizes if (short_first and self.e2e_sizes) else [B] * (-(-F // B))
-        done_f, done_p, prev = 0, 0, 0
-        for n in sizes:
-            n = min(n, F - done_f)
-            if n <= 0:
-                break
-            first = 0 if done_f == 0 else (prev + 1) % (B + 1)
-            p0, np_ = (first, n - 1) if done_f == 0 else (prev, n)
-            yield first, n, done_f, p0, np_, done_p
-            prev = (first + n - 1) % (B + 1)
-            done_f += n
-            done_p += np_
+        """short_first (the e2e leg) follows self.e2e_sizes, the schedule pick_e2e_schedule chose."""
+        return batch_plan(self.F, self.B, self.e2e_sizes if (short_first and self.e2e_sizes) else [])
 
     def step(self, host_input):
+        for _ in self.step_iter(host_input):
+            pass
+
+    def step_iter(self, host_input):
+        """Enqueue the step batch by batch (a generator: MultiRunner interleaves several of them)."""
         torch, ctx = self.torch, self.ctx
         for first, n, done_f, p0, np_, done_p in self.batches(short_first=host_input):
             if host_input:
@@ -315,6 +332,7 @@ class SeqRunner:
                 with torch.cuda.stream(self.stream):
                     src = torch.as_tensor(DevView(ptr, np_ * self.RB), device=self.dev)
                     self.recs_dev[done_p * self.RB:(done_p + np_) * self.RB].copy_(src, non_blocking=True)
+            yield
 
     def close(self):
         """Drop the tensors; the context itself (and with it the CUDA stream torch has seen) is destroyed only at
@@ -325,6 +343,89 @@ class SeqRunner:
         self.recs_dev = None
         self.d_frames = self.h_frames = None
         _OPEN_CONTEXTS.append(self.ctx)
+
+
+class MultiRunner:
+    """The same share of a sequence over K contexts (K CUDA streams) of ONE GPU: context k owns the contiguous pair range
+    [cuts[k], cuts[k+1]) -- the partitioning the multi-GPU path uses, applied inside a GPU -- and the launch batches of the
+    contexts are enqueued round-robin.  Every batch ends in latency-bound kernels (filter, deferred five-point, recoverPose:
+    a few CTAs each) and every kernel in a partially filled last wave; with a second stream those overlap the other
+    context's throughput-bound kernels (tools/two_contexts.py: 28.02 -> 27.33 ms per 999 pairs with K = 2; 27.28 with 3).
+    One boundary frame per cut is detected twice.  Fork / join: the other streams wait on an event of the main stream at
+    the start of a step and the main stream waits on theirs at its end, so CUDA events on the main stream time the whole
+    step and everything enqueued on it afterwards (gather, D2H) sees all records."""
+
+    def __init__(self, torch, b200vo, W, H, NF, hyp, B, local, d_frames, h_frames, pair0, K=2, **opts):
+        F = int(d_frames.shape[0])
+        K = max(1, min(K, (F - 1) // 8 if F > 8 else 1))
+        self.torch, self.K = torch, K
+        self.F, self.npairs = F, F - 1
+        self.dev = "cuda:%d" % local
+        self.RB = b200vo.RECORD_BYTES
+        self.recs_dev = torch.zeros(max(self.npairs, 1) * self.RB, dtype=torch.uint8, device=self.dev)
+        self.cuts = [round(k * self.npairs / K) for k in range(K + 1)]
+        self.sub = []
+        for k in range(K):
+            lo, hi = self.cuts[k], self.cuts[k + 1]
+            # a launch batch may take the K - 1 boundary frames on top of B, so an even split of K * B frames stays one batch per context
+            self.sub.append(SeqRunner(torch, b200vo, W, H, NF, hyp, B + K - 1, local, d_frames[lo:hi + 1], h_frames[lo:hi + 1], pair0 + lo,
+                                      recs_dev=self.recs_dev[lo * self.RB:hi * self.RB], **opts))
+        self.B = self.sub[0].B
+        self.ctx, self.stream = self.sub[0].ctx, self.sub[0].stream
+        self.ev_fork = torch.cuda.Event()
+        self.ev_join = [torch.cuda.Event() for _ in range(K)]
+        self.chained = False        # e2e option: context k starts after context k-1 (its first upload still runs ahead on its copy stream)
+
+    @property
+    def e2e_sizes(self):
+        return self.sub[0].e2e_sizes
+
+    @e2e_sizes.setter
+    def e2e_sizes(self, sizes):
+        for r in self.sub:
+            r.e2e_sizes = sizes
+
+    def e2e_candidates(self):
+        return e2e_schedule_candidates(max(r.F for r in self.sub), self.B)
+
+    def kernel_launches(self):
+        return sum(r.ctx.kernel_launches() for r in self.sub)
+
+    def step(self, host_input):
+        if host_input and self.chained:
+            # one context after the other on the device; what remains of the split is that the first upload of every later
+            # context is hidden behind its predecessor's compute
+            for k, r in enumerate(self.sub):
+                if k:
+                    r.stream.wait_event(self.ev_join[k - 1])
+                r.step(True)
+                self.ev_join[k].record(r.stream)
+            self.stream.wait_event(self.ev_join[self.K - 1])
+            return
+        self.ev_fork.record(self.stream)
+        for r in self.sub[1:]:
+            r.stream.wait_event(self.ev_fork)
+        its = [r.step_iter(host_input) for r in self.sub]
+        while its:
+            its = [it for it in its if next(it, StopIteration) is not StopIteration]
+        for k, r in enumerate(self.sub[1:], 1):
+            self.ev_join[k].record(r.stream)
+            self.stream.wait_event(self.ev_join[k])
+
+    def close(self):
+        for r in self.sub:
+            r.close()
+        self.sub = []
+        self.ctx = self.stream = None
+        self.recs_dev = None
+
+
+def make_runner(torch, b200vo, W, H, NF, hyp, B, local, d_frames, h_frames, pair0, **opts):
+    """B200VO_BENCH_STREAMS contexts per GPU (default 2); 1 = the plain single-stream runner."""
+    K = int(os.environ.get("B200VO_BENCH_STREAMS", "2"))
+    if K <= 1 or int(d_frames.shape[0]) < 17:
+        return SeqRunner(torch, b200vo, W, H, NF, hyp, B, local, d_frames, h_frames, pair0, **opts)
+    return MultiRunner(torch, b200vo, W, H, NF, hyp, B, local, d_frames, h_frames, pair0, K=K, **opts)
 
 
 _OPEN_CONTEXTS = []
@@ -372,12 +473,18 @@ def e2e_schedule_candidates(F, B):
 def pick_e2e_schedule(torch, dist, world, runner, step_fn, dev):
     """Time every candidate schedule for two steps after one settling step; keep the fastest."""
     best = None
-    for sizes in e2e_schedule_candidates(runner.F, runner.B):
-        runner.e2e_sizes = sizes
-        ms, _, _ = timed_steps(torch, dist, world, runner.stream, step_fn, 2, 1, dev)
-        if best is None or ms < best[0]:
-            best = (ms, sizes)
+    modes = (False, True) if hasattr(runner, "chained") else (False,)
+    for chained in modes:
+        if len(modes) > 1:
+            runner.chained = chained
+        for sizes in runner.e2e_candidates():
+            runner.e2e_sizes = sizes
+            ms, _, _ = timed_steps(torch, dist, world, runner.stream, step_fn, 2, 1, dev)
+            if best is None or ms < best[0]:
+                best = (ms, sizes, chained)
     runner.e2e_sizes = best[1]
+    if len(modes) > 1:
+        runner.chained = best[2]
     return best[1]
 
 
@@ -447,7 +554,7 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
     f0, f1 = SQ.frames_for_pairs(lo, hi)
     chunk = max(1, (32 * 1241 * 376) // (W * H))
     d_fr, h_fr = render(torch, synth, W, H, R_all[f0:f1], C_all[f0:f1], tex, dev, chunk)
-    run = SeqRunner(torch, b200vo, W, H, NF, hyp, B, local, d_fr, h_fr, lo)
+    run = make_runner(torch, b200vo, W, H, NF, hyp, B, local, d_fr, h_fr, lo)
     per = -(-P // world)
     send = torch.zeros(per * RB, dtype=torch.uint8, device=dev)
     gath = torch.zeros(world * per * RB, dtype=torch.uint8, device=dev) if world > 1 else send
@@ -464,7 +571,7 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
         if host_input:
             run.stream.synchronize()
 
-    ms_dev, _, launches = timed_steps(torch, dist, world, run.stream, lambda: step(False), steps, warmup, dev, run.ctx)
+    ms_dev, _, launches = timed_steps(torch, dist, world, run.stream, lambda: step(False), steps, warmup, dev, run)
     pick_e2e_schedule(torch, dist, world, run, lambda: step(True), dev)
     ms_e2e, _, _ = timed_steps(torch, dist, world, run.stream, lambda: step(True), steps, warmup, dev)
     out, recs = None, None
@@ -475,7 +582,7 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
         out = {"workload": "%s: ONE %d-frame %dx%d sequence, %d features, %d hypotheses/pair, launch batches of %d frames, partitioned over %d GPU(s) by contiguous frame-pair ranges" % (name, F, W, H, NF, hyp, run.B, world),
                "pairs": P, "scaling": "strong", "value": round(P / (ms_dev * 1e-3), 1), "e2e": round(P / (ms_e2e * 1e-3), 1), "unit": "pairs/s",
                "ms_per_step": round(ms_dev, 3), "e2e_ms_per_step": round(ms_e2e, 3), "steps": steps, "warmup": warmup,
-               "h2d_bytes_per_step": (P + world) * W * H, "d2h_bytes_per_step": world * per * RB, "e2e_batch_sizes_rank0": run.e2e_sizes,
+               "h2d_bytes_per_step": (P + world) * W * H, "d2h_bytes_per_step": world * per * RB, "e2e_batch_sizes_rank0": run.e2e_sizes, "streams_per_gpu": getattr(run, "K", 1), "e2e_contexts_chained": bool(getattr(run, "chained", False)),
                "boundary_frames_detected_twice": world - 1, "boundary_overhead_frac": round((world - 1) / float(P + 1), 5),
                "gpu_launches": int(launches) * world,
                "pairs_pose_ok": int(((recs["status"] & 4) != 0).sum()), "pairs_overflow": int(((recs["status"] & 256) != 0).sum()),
@@ -487,7 +594,7 @@ def strong_scaling_leg(torch, dist, b200vo, synth, tex, name, W, H, NF, hyp, B, 
     if world > 1:
         if rank == 0:
             d_all, h_all = render(torch, synth, W, H, R_all, C_all, tex, dev, chunk)
-            solo = SeqRunner(torch, b200vo, W, H, NF, hyp, B, local, d_all, h_all, 0)
+            solo = make_runner(torch, b200vo, W, H, NF, hyp, B, local, d_all, h_all, 0)
             ms1, _, _ = timed_steps(torch, None, 1, solo.stream, lambda: solo.step(False), steps, warmup, dev)
             host1 = torch.empty(P * RB, dtype=torch.uint8, pin_memory=True)
 
@@ -562,8 +669,9 @@ def run_b200(args):
     d_frames, h_frames = render(torch, synth, W_IMG, H_IMG, R_all[f0:f0 + F], C_all[f0:f0 + F], tex, dev, 32)
     frame_bytes = W_IMG * H_IMG
 
-    run = SeqRunner(torch, b200vo, W_IMG, H_IMG, NF, args.hypotheses, B, local, d_frames, h_frames, f0)
+    run = make_runner(torch, b200vo, W_IMG, H_IMG, NF, args.hypotheses, B, local, d_frames, h_frames, f0)
     ctx, stream = run.ctx, run.stream
+    streams_per_gpu = getattr(run, "K", 1)
     gathered = {"t": torch.zeros(world * npairs * RB, dtype=torch.uint8, device=dev) if world > 1 else None}
     recs_host = torch.empty(world * npairs * RB, dtype=torch.uint8, pin_memory=True)
     state = {"traj": None}
@@ -585,7 +693,7 @@ def run_b200(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, wall_dev, launches = timed_steps(torch, dist, world, stream, make_step(run, False), args.steps, args.warmup, dev, ctx)
+    ms_dev, wall_dev, launches = timed_steps(torch, dist, world, stream, make_step(run, False), args.steps, args.warmup, dev, run)
     # ---- per-rank upload bandwidth of a plain pinned -> device copy of the same frames with all ranks copying at the same
     # time (the ceiling the host's PCIe / memory system gives this box)
     probe_gbps = h2d_probe(torch, dist, world, d_frames, h_frames)
@@ -604,7 +712,7 @@ def run_b200(args):
         h2d_all = [h2d_vals]
     h2d = {"e2e_GBps_per_rank": [round(float(v[0]), 2) for v in h2d_all], "plain_pinned_copy_GBps_per_rank_concurrent": [round(float(v[1]), 2) for v in h2d_all],
            "cpus_bound_per_rank": [int(v[2]) for v in h2d_all], "cpus_nvml_affinity_per_rank": [int(v[3]) for v in h2d_all],
-           "e2e_batch_sizes_rank0": run.e2e_sizes,
+           "e2e_batch_sizes_rank0": run.e2e_sizes, "e2e_contexts_chained": bool(getattr(run, "chained", False)),
            "note": "e2e: frame bytes of a rank / its e2e step time (the copy is overlapped with compute, so this is a lower bound of the copy rate); plain: 3 back-to-back pinned->device copies of the same frames, all ranks at once, measured before the e2e leg; the e2e launch-batch schedule is the fastest of a few candidates timed on warm-up steps (pick_e2e_schedule)"}
     del h2d_all, h2d_vals
 
@@ -612,7 +720,7 @@ def run_b200(args):
     stage, kp_counts = {}, []
     if rank == 0:
         ctx.enable_timing(True)
-        for first, n, done_f, p0, np_, done_p in run.batches():
+        for first, n, done_f, p0, np_, done_p in batch_plan(F, run.B, []):
             ctx.upload_frames_device(d_frames.data_ptr() + done_f * frame_bytes, n, W_IMG, frame_bytes, 1, first)
             ctx.detect(first, n)
             st = ctx.stage_times()
@@ -658,7 +766,7 @@ def run_b200(args):
         # reported beside the fixed-H headline, not as it
         d2 = torch.empty((F, H_IMG, W_IMG), dtype=torch.uint8, device=dev)
         d2.copy_(h_frames)
-        ad = SeqRunner(torch, b200vo, W_IMG, H_IMG, NF, args.hypotheses, B, local, d2, h_frames, f0, ransac_adaptive=1)
+        ad = make_runner(torch, b200vo, W_IMG, H_IMG, NF, args.hypotheses, B, local, d2, h_frames, f0, ransac_adaptive=1)
         if world > 1:
             gathered["t"] = torch.zeros(world * npairs * RB, dtype=torch.uint8, device=dev)
         ms_dev_ad, _, _ = timed_steps(torch, dist, world, ad.stream, make_step(ad, False), args.steps, args.warmup, dev)
@@ -752,7 +860,8 @@ def run_b200(args):
         "dtype": "u8/i32 (features, matching), f64 (geometry)", "data": "synthetic",
         "config": {"workload": "%d-frame synthetic KITTI-shaped sequence %dx%d per GPU, %d ORB features, %d five-point hypotheses/pair, launch batches of %d frames" % (F, W_IMG, H_IMG, NF, args.hypotheses, B),
                    "pairs_per_step": total_pairs, "cache": "inputs larger than L2 (%.0f MB of frames per step)" % (F * frame_bytes / 1e6),
-                   "partition": "contiguous frame-pair ranges, one per GPU; one NCCL all_gather of 160-B pose records" if world > 1 else "single GPU"},
+                   "partition": ("contiguous frame-pair ranges, one per GPU; one NCCL all_gather of 160-B pose records" if world > 1 else "single GPU") +
+                                "; inside a GPU the range is split over %d contexts (CUDA streams) whose launch batches are enqueued round-robin" % streams_per_gpu},
         "e2e": {"value": round(e2e, 1), "unit": "pairs/s", "ms_per_step": round(ms_e2e, 3), "h2d_bytes_per_step": world * F * frame_bytes,
                 "d2h_bytes_per_step": world * npairs * RB, "wall_ms_per_step": round(wall_e2e * 1e3, 3)},
         "gpu_launches": int(launches) * world,
