@@ -286,6 +286,9 @@ def batch_plan(F, B, sizes):
         done_p += np_
 
 
+COPY_BY_KERNEL = os.environ.get("B200VO_BENCH_COPY_KERNEL", "0") != "0"      # experiment knob: no effect measured (profiles/README.md)
+
+
 class SeqRunner:
     """One rank's share of a sequence through the C ABI: frames [0, F) of `d_frames` (device) / `h_frames`
     (pinned host) in launch batches of B frames; pair ids start at pair0.  Records land in self.recs_dev."""
@@ -331,7 +334,11 @@ class SeqRunner:
                 ptr = ctx.process_pairs_device(p0, np_, self.pair0 + done_p)
                 with torch.cuda.stream(self.stream):
                     src = torch.as_tensor(DevView(ptr, np_ * self.RB), device=self.dev)
-                    self.recs_dev[done_p * self.RB:(done_p + np_) * self.RB].copy_(src, non_blocking=True)
+                    dst = self.recs_dev[done_p * self.RB:(done_p + np_) * self.RB]
+                    if COPY_BY_KERNEL:
+                        torch.bitwise_or(src, 0, out=dst)      # an elementwise kernel: a device-to-device cudaMemcpyAsync may be served by
+                    else:                                      # a copy engine and then queues behind the upload that is in flight
+                        dst.copy_(src, non_blocking=True)
             yield
 
     def close(self):
@@ -378,15 +385,29 @@ class MultiRunner:
 
     @property
     def e2e_sizes(self):
-        return self.sub[0].e2e_sizes
+        return getattr(self, "_sizes", None)
 
     @e2e_sizes.setter
     def e2e_sizes(self, sizes):
-        for r in self.sub:
-            r.e2e_sizes = sizes
+        per_ctx = bool(sizes) and isinstance(sizes[0], (list, tuple))       # one schedule for all, or one per context
+        for k, r in enumerate(self.sub):
+            r.e2e_sizes = list(sizes[k]) if per_ctx else sizes
+        self._sizes = sizes
 
     def e2e_candidates(self):
-        return e2e_schedule_candidates(max(r.F for r in self.sub), self.B)
+        """The single-context candidates for every context alike, plus staggered ones: the batches reach the copy engine
+        in round-robin order (context 0's first, context 1's first, context 0's second, ...), each hidden behind the
+        compute of its predecessors only if it is at most ~3x as long (8.5 us of upload vs 29 us of compute per frame
+        at the headline configuration), and only the very first upload is exposed -- so context 0 opens with a small
+        batch and context 1 with one about three times as large."""
+        Fs, B = max(r.F for r in self.sub), self.B
+        cands = list(e2e_schedule_candidates(Fs, B))
+        if self.K == 2:
+            for a0, a1 in ((B // 16, B // 5), (B // 12, B // 4), (B // 24, B // 8)):
+                a0, a1 = max(2, a0), max(3, a1)
+                cands.append([[a0, min(B, 9 * a0)], [a1]])
+                cands.append([[a0], [a1]])
+        return cands
 
     def kernel_launches(self):
         return sum(r.ctx.kernel_launches() for r in self.sub)

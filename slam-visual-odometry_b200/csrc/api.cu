@@ -321,6 +321,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         ctx->fpg_variant = 0;
         ctx->pdl = false; ctx->pdl_enabled = true;
         ctx->repack_kernel = true;
+        ctx->fill_kernel = false;
+        if (const char* v = getenv("B200VO_FILL_KERNEL")) ctx->fill_kernel = (atoi(v) != 0);
         if (const char* v = getenv("B200VO_REPACK_KERNEL")) ctx->repack_kernel = (atoi(v) != 0);
         if (const char* v = getenv("B200VO_PDL")) ctx->pdl_enabled = (atoi(v) != 0);
         ctx->fused_describe = ctx->use_tma;

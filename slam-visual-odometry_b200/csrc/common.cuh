@@ -177,6 +177,7 @@ struct b200vo_ctx {
     int blur_rows;             // rows per warp strip of the large-batch blur (16 or 24; 0: the two-pass tile kernel; B200VO_BLUR_R)
     int match_variant;         // inner-loop variant of match_kernel (see match.cu)
     int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC, 2: full Harley-Seal (4 POPC), 3: 3 CSA + 5 POPC (default)
+    bool fill_kernel;          // device_fill32 by kernel (B200VO_FILL_KERNEL=1) instead of cudaMemsetAsync (default; byte-replicated values only)
     bool repack_kernel;        // device-side ingest of gray frames by kernel (default) or cudaMemcpy3DAsync (B200VO_REPACK_KERNEL=0)
     bool pdl;                  // programmatic dependent launch for the current call (small batches only; B200VO_PDL=0 disables)
     bool pdl_enabled;
@@ -241,6 +242,11 @@ inline void launch_k(b200vo_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 
 }
 
 // stage launchers (each enqueues on ctx->stream and returns a b200vo_status)
+// device fill of 32-bit words on the compute stream: cudaMemsetAsync, or a kernel with B200VO_FILL_KERNEL=1.  (Experiment of
+// round 2: were memsets and device-to-device copies served by a copy engine, they would queue behind the upload of the next
+// batch in the e2e pipeline.  They are not: e2e 29.7 ms either way, the streaming step 0.325 ms with memsets vs 0.330 with
+// kernels -- profiles/README.md.)
+int device_fill32(b200vo_ctx* ctx, void* p, uint32_t value, size_t words);
 int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t frame_stride, int first_slot, int n);
 int launch_repack_gray(b200vo_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t frame_stride, int first_slot, int n);
 int launch_pyramid(b200vo_ctx* ctx, int first_slot, int n);

@@ -334,8 +334,8 @@ int launch_match_slots(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_o
         a.nnq = ctx->pairs.nnq; a.nnq2 = ctx->pairs.nnq2; a.out_stride = sv.kp_cap;
         return run_match_knn2(ctx, a, sv.kp_cap, ctx->opt.nfeatures, npairs);
     }
-    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.nnq, 0xFF, (size_t)npairs * sv.kp_cap * sizeof(uint32_t), ctx->stream));
-    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.nnt, 0xFF, (size_t)npairs * sv.kp_cap * sizeof(uint32_t), ctx->stream));
+    { int rc; if ((rc = device_fill32(ctx, ctx->pairs.nnq, 0xFFFFFFFFu, (size_t)npairs * sv.kp_cap))) return rc;
+      if ((rc = device_fill32(ctx, ctx->pairs.nnt, 0xFFFFFFFFu, (size_t)npairs * sv.kp_cap))) return rc; }
     MatchArgs a{};
     a.q = sv.desc; a.t = sv.desc; a.counts = sv.kp_count;
     a.slots = sv.slots; a.first_slot = first_slot; a.slot_b_override = slot_b_override; a.kp_cap = sv.kp_cap;
@@ -347,8 +347,8 @@ int launch_match_slots(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_o
 int launch_match_raw(b200vo_ctx* ctx, const uint8_t* q, int n1, const uint8_t* t, int n2, int npairs,
                      uint32_t* nnq, uint32_t* nnt) {
     const int stride = max(n1, n2);
-    B200VO_CUDA_CHECK(cudaMemsetAsync(nnq, 0xFF, (size_t)npairs * stride * sizeof(uint32_t), ctx->stream));
-    B200VO_CUDA_CHECK(cudaMemsetAsync(nnt, 0xFF, (size_t)npairs * stride * sizeof(uint32_t), ctx->stream));
+    { int rc; if ((rc = device_fill32(ctx, nnq, 0xFFFFFFFFu, (size_t)npairs * stride))) return rc;
+      if ((rc = device_fill32(ctx, nnt, 0xFFFFFFFFu, (size_t)npairs * stride))) return rc; }
     MatchArgs a{};
     a.q = q; a.t = t; a.q_stride = (size_t)n1 * kDescBytes; a.t_stride = (size_t)n2 * kDescBytes;
     a.counts = nullptr; a.n1 = n1; a.n2 = n2;

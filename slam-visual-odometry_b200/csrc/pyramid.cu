@@ -68,6 +68,26 @@ repack_gray_kernel(StoreView sv, const uint8_t* __restrict__ src, size_t pitch, 
     for (int i = 0; i < nbytes; ++i) dst[i] = (uint8_t)(ow[i >> 2] >> (8 * (i & 3)));
 }
 
+__global__ void __launch_bounds__(256)
+fill32_kernel(uint32_t* __restrict__ p, uint32_t value, size_t words) {
+    pdl_grid_sync();
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 4 <= words && (reinterpret_cast<uintptr_t>(p + i) & 15) == 0) { *reinterpret_cast<uint4*>(p + i) = make_uint4(value, value, value, value); return; }
+    for (size_t k = i; k < words && k < i + 4; ++k) p[k] = value;
+}
+
+int device_fill32(b200vo_ctx* ctx, void* p, uint32_t value, size_t words) {
+    if (words == 0) return B200VO_OK;
+    if (!ctx->fill_kernel) {
+        B200VO_CUDA_CHECK(cudaMemsetAsync(p, (int)(value & 0xFF), words * sizeof(uint32_t), ctx->stream));
+        return B200VO_OK;
+    }
+    const size_t threads = (words + 3) / 4;
+    launch_k(ctx, fill32_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, static_cast<uint32_t*>(p), value, words);
+    B200VO_LAUNCH_CHECK(ctx);
+    return B200VO_OK;
+}
+
 int launch_repack_gray(b200vo_ctx* ctx, const uint8_t* d_src, size_t pitch, size_t frame_stride, int first_slot, int n) {
     const LevelGeom& g = ctx->store.lv[0];
     dim3 grid(div_up(div_up(g.w, 16), 256), g.h, n);

@@ -285,7 +285,7 @@ static int launch_five_point_as(b200vo_ctx* ctx, const RansacArgs& ra, int npair
 
 static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     // launch shape (threads x CTAs/SM -> register cap), measured on B200 at 1000 frames, H = 1024 -- see DESIGN.md section 4
-    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.fb_count, 0, sizeof(unsigned), ctx->stream));
+    { const int rcf = device_fill32(ctx, ctx->pairs.fb_count, 0u, 1); if (rcf) return rcf; }
     switch (ctx->fpg_variant) {
         // measured per 250 pairs x 1024 hypotheses (profiles/fpg_variants_r02.jsonl): 256x2 1.42 ms; 192x2 (168 registers, a
         // third of the spills) 1.64; 256x3 (80 registers) 1.75; 128x4 1.68; 160x3 1.70
@@ -536,11 +536,11 @@ int launch_ransac(b200vo_ctx* ctx, int npairs, int64_t first_pair_id, const int3
     ra.min_matches = ctx->opt.min_matches_for_pose;
     // an explicit sample list (parity hooks) is always evaluated completely
     ra.adaptive = (ctx->opt.ransac_adaptive != 0 && d_samples == nullptr) ? 1 : 0;
-    B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.best, 0, (size_t)npairs * sizeof(unsigned long long), ctx->stream));
+    { const int rcf = device_fill32(ctx, ctx->pairs.best, 0u, (size_t)npairs * 2); if (rcf) return rcf; }
     const int block = ra.adaptive ? 128 : nhyp;
     if (ra.adaptive) {
-        B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.done, 0, (size_t)npairs * sizeof(int), ctx->stream));
-        B200VO_CUDA_CHECK(cudaMemsetAsync(ctx->pairs.rounds, 0, (size_t)npairs * sizeof(int), ctx->stream));
+        { int rcf; if ((rcf = device_fill32(ctx, ctx->pairs.done, 0u, (size_t)npairs))) return rcf;
+          if ((rcf = device_fill32(ctx, ctx->pairs.rounds, 0u, (size_t)npairs))) return rcf; }
     }
     for (int h0 = 0; h0 < nhyp; h0 += block) {
         ra.h0 = h0; ra.nround = std::min(block, nhyp - h0);
