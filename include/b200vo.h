@@ -248,19 +248,23 @@ int b200vo_chain_trajectory(const b200vo_pose_record* recs, int n, const double*
  * per device, runs every block on its own context (one host thread each), all-gathers the 160-byte records
  * with NCCL (ncclCommInitAll + ncclAllGather over NVLink; libnccl.so.2 is bound at first use) and hands them to
  * the caller in pair order for b200vo_chain_trajectory.  Pair results are byte-identical to the one-device
- * run: nothing in a pair's computation depends on device, slot or batch. */
+ * run: nothing in a pair's computation depends on device, slot or batch.
+ * A device may be listed k times in adjacent entries (the same k for every device), e.g. {0, 0} or {0, 0, 1, 1}: it
+ * then carries k contexts, each with its own CUDA stream, host thread and contiguous sub-range, so the latency-bound
+ * tail of one context's launch batch overlaps the other's throughput-bound kernels (about 3 % at the headline
+ * configuration with k = 2); NCCL runs over the distinct devices. */
 typedef struct b200vo_group b200vo_group;
 int b200vo_group_create(const b200vo_options* opt, const int* devices, int ndev, b200vo_group** out);
 void b200vo_group_destroy(b200vo_group* g);
 int b200vo_group_size(const b200vo_group* g);
-b200vo_ctx* b200vo_group_ctx(b200vo_group* g, int i);                 /* the i-th device's context (owned by the group) */
+b200vo_ctx* b200vo_group_ctx(b200vo_group* g, int i);                 /* the i-th context (owned by the group) */
 /* Contiguous pair range [lo, hi) of `rank` among `world` (the first ranks take the remainder). */
 int b200vo_partition_pairs(int total_pairs, int world, int rank, int* lo, int* hi);
 /* nframes host frames (layout as b200vo_upload_frames) -> nframes-1 records in pair order.  opt.max_frames of the
  * group must be >= batch_frames + 1. */
 int b200vo_group_process_sequence(b200vo_group* g, const uint8_t* frames, int nframes, size_t pitch, size_t frame_stride,
                                   int channels, int batch_frames, int64_t first_pair_id, b200vo_pose_record* out);
-/* The exchange step alone: device i contributes counts[i] records from its send buffer (filled by
+/* The exchange step alone: context i contributes counts[i] records from its part of the send buffer (filled by
  * b200vo_group_process_sequence); out receives sum(counts) records in rank order. */
 int b200vo_group_allgather_records(b200vo_group* g, const int* counts, b200vo_pose_record* out);
 int b200vo_nccl_version(void);                                          /* 0 when NCCL could not be loaded */

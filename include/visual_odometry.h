@@ -24,7 +24,9 @@ public:
         int device = 0;
         std::vector<int> devices;          // [ext] more than one entry: process_sequence partitions the pair range over these GPUs
                                            // (contiguous blocks, one host thread per GPU, NCCL all-gather of the pose records);
-                                           // process_frame always runs on the first
+                                           // process_frame always runs on the first.  A device may be repeated in adjacent
+                                           // entries ({0, 0} or {0, 0, 1, 1}): that many contexts / CUDA streams on it, whose
+                                           // launch batches overlap (b200vo.h, device groups)
         int batch_frames = 64;             // frames per launch batch in process_sequence
         bool ratio_test = false;           // false: cross-check (reference :87); true: Lowe ratio test on 2-NN
         float ratio = 0.75f;

@@ -7,6 +7,13 @@
 // bundled one in the Python tests and bench) keeps exactly that copy, a plain C++ caller gets the system
 // library.  Only five stable entry points are used.  There is no fallback: without NCCL a group of more
 // than one device cannot be created.
+//
+// A device may be listed k times (adjacent entries, the same k for every device): it then carries k contexts, each on
+// its own CUDA stream and host thread, with contiguous sub-ranges.  Every launch batch ends in latency-bound kernels
+// (filter, deferred five-point, recoverPose) and every kernel in a partially filled last wave; a second stream fills
+// those with the other context's throughput-bound kernels (bench.py MultiRunner: 28.0 -> 27.2 ms per 999 pairs with
+// k = 2).  The contexts of a device write their records into ONE send buffer of the device, its first context (the
+// leader) waits for the others through events and takes part in the NCCL all-gather, which runs over the distinct devices.
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -56,11 +63,14 @@ NcclApi& nccl() {
 using namespace b200vo;
 
 struct b200vo_group {
-    std::vector<b200vo_ctx*> ctx;
-    std::vector<int> devices;
-    std::vector<ncclComm_t> comm;
-    std::vector<b200vo_pose_record*> d_send;     // [per_cap] records of this device's range (padded)
-    std::vector<b200vo_pose_record*> d_recv;     // [ndev * per_cap] gathered
+    std::vector<b200vo_ctx*> ctx;                // n contexts, device-major: context i = k * (device index) + (index on the device)
+    std::vector<int> devices;                    // [n] device of every context
+    std::vector<int> udev;                       // [m] the distinct devices, m = n / k
+    int k = 1;                                   // contexts per device
+    std::vector<ncclComm_t> comm;                // [m] (empty when m == 1)
+    std::vector<b200vo_pose_record*> d_send;     // [m] k * per_cap records: the ranges of the device's contexts (padded)
+    std::vector<b200vo_pose_record*> d_recv;     // [m] n * per_cap gathered
+    std::vector<cudaEvent_t> done;               // [n] recorded on a context's stream when its records are in d_send
     int per_cap = 0;
     int64_t launches_gather = 0;
 };
@@ -73,16 +83,19 @@ static void contiguous_range(int total, int world, int rank, int* lo, int* hi) {
 
 static int ensure_group_buffers(b200vo_group* g, int per) {
     if (per <= g->per_cap) return B200VO_OK;
-    const int n = (int)g->ctx.size();
+    const int n = (int)g->ctx.size(), m = (int)g->udev.size();
     for (int i = 0; i < n; ++i) {
         B200VO_CUDA_CHECK(cudaSetDevice(g->devices[i]));
         B200VO_CUDA_CHECK(cudaStreamSynchronize(g->ctx[i]->stream));
-        if (g->d_send[i]) cudaFree(g->d_send[i]);
-        if (g->d_recv[i]) cudaFree(g->d_recv[i]);
-        g->d_send[i] = g->d_recv[i] = nullptr;
-        B200VO_CUDA_CHECK(cudaMalloc(&g->d_send[i], (size_t)per * sizeof(b200vo_pose_record)));
-        B200VO_CUDA_CHECK(cudaMalloc(&g->d_recv[i], (size_t)per * n * sizeof(b200vo_pose_record)));
-        B200VO_CUDA_CHECK(cudaMemset(g->d_send[i], 0, (size_t)per * sizeof(b200vo_pose_record)));
+    }
+    for (int u = 0; u < m; ++u) {
+        B200VO_CUDA_CHECK(cudaSetDevice(g->udev[u]));
+        if (g->d_send[u]) cudaFree(g->d_send[u]);
+        if (g->d_recv[u]) cudaFree(g->d_recv[u]);
+        g->d_send[u] = g->d_recv[u] = nullptr;
+        B200VO_CUDA_CHECK(cudaMalloc(&g->d_send[u], (size_t)per * g->k * sizeof(b200vo_pose_record)));
+        B200VO_CUDA_CHECK(cudaMalloc(&g->d_recv[u], (size_t)per * n * sizeof(b200vo_pose_record)));
+        B200VO_CUDA_CHECK(cudaMemset(g->d_send[u], 0, (size_t)per * g->k * sizeof(b200vo_pose_record)));
     }
     g->per_cap = per;
     return B200VO_OK;
@@ -92,26 +105,40 @@ extern "C" {
 
 int b200vo_group_create(const b200vo_options* opt, const int* devices, int ndev, b200vo_group** out) {
     if (!opt || !devices || ndev < 1 || ndev > 64 || !out) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
-    for (int i = 0; i < ndev; ++i)
-        for (int j = 0; j < i; ++j)
-            if (devices[i] == devices[j]) { set_error("device %d listed twice", devices[i]); return B200VO_ERR_BAD_ARG; }
-    if (ndev > 1 && !nccl().ok) {
-        set_error("NCCL (libnccl.so.2) could not be loaded: a group of %d devices needs it (no host-gather fallback)", ndev);
+    // distinct devices in order of appearance; a device may be repeated k times in adjacent entries (k contexts on it)
+    std::vector<int> udev;
+    int k = 0;
+    for (int i = 0; i < ndev; ) {
+        int j = i;
+        while (j < ndev && devices[j] == devices[i]) ++j;
+        for (int u : udev) if (u == devices[i]) { set_error("device %d listed in two places (repeat a device in adjacent entries)", devices[i]); return B200VO_ERR_BAD_ARG; }
+        if (k && j - i != k) { set_error("every device must be listed the same number of times"); return B200VO_ERR_BAD_ARG; }
+        k = j - i;
+        udev.push_back(devices[i]);
+        i = j;
+    }
+    const int m = (int)udev.size();
+    if (m > 1 && !nccl().ok) {
+        set_error("NCCL (libnccl.so.2) could not be loaded: a group of %d devices needs it (no host-gather fallback)", m);
         return B200VO_ERR_CUDA;
     }
     b200vo_group* g = new b200vo_group();
     g->devices.assign(devices, devices + ndev);
-    g->d_send.assign(ndev, nullptr);
-    g->d_recv.assign(ndev, nullptr);
+    g->udev = udev;
+    g->k = k;
+    g->d_send.assign(m, nullptr);
+    g->d_recv.assign(m, nullptr);
+    g->done.assign(ndev, nullptr);
     for (int i = 0; i < ndev; ++i) {
         b200vo_ctx* c = nullptr;
         const int rc = b200vo_create(opt, devices[i], &c);
         if (rc) { b200vo_group_destroy(g); return rc; }
         g->ctx.push_back(c);
+        if (cudaEventCreateWithFlags(&g->done[i], cudaEventDisableTiming) != cudaSuccess) { set_error("cudaEventCreate failed"); b200vo_group_destroy(g); return B200VO_ERR_CUDA; }
     }
-    if (ndev > 1) {
-        g->comm.assign(ndev, nullptr);
-        const int rc = nccl().CommInitAll(g->comm.data(), ndev, devices);
+    if (m > 1) {
+        g->comm.assign(m, nullptr);
+        const int rc = nccl().CommInitAll(g->comm.data(), m, udev.data());
         if (rc != 0) {
             set_error("ncclCommInitAll failed: %s", nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
             g->comm.clear();
@@ -128,9 +155,16 @@ void b200vo_group_destroy(b200vo_group* g) {
     for (size_t i = 0; i < g->ctx.size(); ++i) {
         cudaSetDevice(g->devices[i]);
         if (g->ctx[i] && g->ctx[i]->stream) cudaStreamSynchronize(g->ctx[i]->stream);
-        if (i < g->comm.size() && g->comm[i]) nccl().CommDestroy(g->comm[i]);
-        if (g->d_send[i]) cudaFree(g->d_send[i]);
-        if (g->d_recv[i]) cudaFree(g->d_recv[i]);
+    }
+    for (size_t u = 0; u < g->udev.size(); ++u) {
+        cudaSetDevice(g->udev[u]);
+        if (u < g->comm.size() && g->comm[u]) nccl().CommDestroy(g->comm[u]);
+        if (g->d_send[u]) cudaFree(g->d_send[u]);
+        if (g->d_recv[u]) cudaFree(g->d_recv[u]);
+    }
+    for (size_t i = 0; i < g->ctx.size(); ++i) {
+        cudaSetDevice(g->devices[i]);
+        if (i < g->done.size() && g->done[i]) cudaEventDestroy(g->done[i]);
         b200vo_destroy(g->ctx[i]);
     }
     delete g;
@@ -157,25 +191,33 @@ int b200vo_nccl_version(void) {
 // own streams; the gathered records of device 0 are copied to `out` in global pair order.
 int b200vo_group_allgather_records(b200vo_group* g, const int* counts, b200vo_pose_record* out) {
     if (!g || !counts || !out) { set_error("bad arguments"); return B200VO_ERR_BAD_ARG; }
-    const int n = (int)g->ctx.size();
+    const int n = (int)g->ctx.size(), m = (int)g->udev.size(), k = g->k;
     int per = 0, total = 0;
     for (int i = 0; i < n; ++i) { if (counts[i] < 0) { set_error("negative count"); return B200VO_ERR_BAD_ARG; } per = std::max(per, counts[i]); total += counts[i]; }
     if (per > g->per_cap) { set_error("counts exceed the group's record buffers (%d > %d)", per, g->per_cap); return B200VO_ERR_CAPACITY; }
     if (total == 0) return B200VO_OK;
-    const size_t bytes = (size_t)per * sizeof(b200vo_pose_record);
-    if (n > 1) {
+    per = g->per_cap;                     // the layout of d_send / d_recv: context i's records start at i * per_cap
+    // join: the leader stream of every device waits until the device's other contexts have written their records
+    for (int i = 0; i < n; ++i) {
+        if (i % k == 0) continue;
+        B200VO_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+        B200VO_CUDA_CHECK(cudaEventRecord(g->done[i], g->ctx[i]->stream));
+        B200VO_CUDA_CHECK(cudaStreamWaitEvent(g->ctx[i - i % k]->stream, g->done[i], 0));
+    }
+    const size_t bytes = (size_t)per * k * sizeof(b200vo_pose_record);
+    if (m > 1) {
         NcclApi& nc = nccl();
         int rc = nc.GroupStart();
-        for (int i = 0; i < n && rc == 0; ++i)
-            rc = nc.AllGather(g->d_send[i], g->d_recv[i], bytes, kNcclUint8, g->comm[i], g->ctx[i]->stream);
+        for (int u = 0; u < m && rc == 0; ++u)
+            rc = nc.AllGather(g->d_send[u], g->d_recv[u], bytes, kNcclUint8, g->comm[u], g->ctx[(size_t)u * k]->stream);
         const int rc2 = nc.GroupEnd();
         if (rc == 0) rc = rc2;
         if (rc != 0) { set_error("ncclAllGather failed: %s", nc.GetErrorString ? nc.GetErrorString(rc) : "?"); return B200VO_ERR_CUDA; }
-        g->launches_gather += n;
+        g->launches_gather += m;
     }
-    // rank 0's copy -> host, dropping the padding
+    // device 0's copy -> host, dropping the padding
     B200VO_CUDA_CHECK(cudaSetDevice(g->devices[0]));
-    const b200vo_pose_record* src = (n > 1) ? g->d_recv[0] : g->d_send[0];
+    const b200vo_pose_record* src = (m > 1) ? g->d_recv[0] : g->d_send[0];
     int o = 0;
     for (int i = 0; i < n; ++i) {
         if (counts[i])
@@ -231,7 +273,7 @@ int b200vo_group_process_sequence(b200vo_group* g, const uint8_t* frames, int nf
             if (np > 0) {
                 void* dev = nullptr;
                 if ((e = b200vo_process_pairs_device(c, p0, np, first_pair_id + lo + done_p, &dev))) { fail(e); return; }
-                if (cudaMemcpyAsync(g->d_send[(size_t)r] + done_p, dev, (size_t)np * sizeof(b200vo_pose_record), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) {
+                if (cudaMemcpyAsync(g->d_send[(size_t)(r / g->k)] + (size_t)(r % g->k) * g->per_cap + done_p, dev, (size_t)np * sizeof(b200vo_pose_record), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) {
                     set_error("record copy failed"); fail(B200VO_ERR_CUDA); return;
                 }
             }

@@ -356,6 +356,44 @@ def test_group_of_one_device_equals_context(built, seq, records):
     assert recs.tobytes() == batched.tobytes()
 
 
+def test_group_with_two_contexts_on_one_device(built, seq, records):
+    """A device listed twice: two contexts (streams, host threads) on ONE GPU with contiguous sub-ranges, their
+    records joined in the device's send buffer without NCCL.  Byte-identical to the plain context path, for two
+    batch sizes; through the C++ class (Options::devices = {0, 0}) the trajectory equals the one-context one.
+    Malformed lists are refused."""
+    frames = seq[0]
+    batched, _ = records
+    with built.Group(W, H, [0, 0], nfeatures=NF, max_frames=4, ransac_hypotheses=NHYP) as g:
+        recs = g.process_sequence(frames, 3)
+        again = g.process_sequence(frames, 2)
+    assert recs.tobytes() == batched.tobytes() and again.tobytes() == batched.tobytes()
+    with built.Group(W, H, [0, 0, 0], nfeatures=NF, max_frames=NFRAMES + 1, ransac_hypotheses=NHYP) as g:
+        assert g.process_sequence(frames, NFRAMES).tobytes() == batched.tobytes()
+    lib = _host(built)
+    lib.vo_host_create_multi.restype = ctypes.c_void_p
+    devs = (ctypes.c_int * 2)(0, 0)
+    out = {}
+    for name, h in (("multi", lib.vo_host_create_multi(W, H, NF, NHYP, ctypes.c_ulonglong(42), devs, 2, 3)),
+                    ("single", lib.vo_host_create(W, H, NF, NHYP, ctypes.c_ulonglong(42), 0, 3))):
+        assert h, lib.vo_host_last_error()
+        h = ctypes.c_void_p(h)
+        o = np.zeros((NFRAMES, 12))
+        f = np.ascontiguousarray(frames)
+        n = lib.vo_host_process_sequence(h, f.ctypes.data_as(ctypes.c_void_p), NFRAMES, W, H, 1, o.ctypes.data_as(ctypes.c_void_p))
+        assert n == NFRAMES, lib.vo_host_last_error()
+        out[name] = o
+        lib.vo_host_destroy(h)
+    assert out["multi"].tobytes() == out["single"].tobytes()
+    import torch
+    if torch.cuda.device_count() >= 2:
+        with pytest.raises(built.B200VOError):
+            built.Group(W, H, [0, 1, 0], nfeatures=NF, max_frames=4)          # a device in two places
+        with pytest.raises(built.B200VOError):
+            built.Group(W, H, [0, 0, 1], nfeatures=NF, max_frames=4)          # unequal multiplicity
+        with built.Group(W, H, [0, 0, 1, 1], nfeatures=NF, max_frames=4, ransac_hypotheses=NHYP) as g:
+            assert g.process_sequence(frames, 3).tobytes() == batched.tobytes()
+
+
 def test_group_partition_matches_python_helper(built):
     from b200vo import sequence as SQ
     for total, world in ((999, 8), (7, 2), (3, 4), (0, 3), (255, 8)):
