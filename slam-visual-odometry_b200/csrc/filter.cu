@@ -30,20 +30,24 @@ struct FilterArgs {
     int fast_cap;              // <= FL_FAST_CAP; 0 forces the full sort (tests)
 };
 
+// One thread per compare-exchange; steps at distances <= 32 stay inside a warp's own aligned block of 64 elements, so
+// they need only a warp barrier (see bitonic_sort_u64 in select.cu).
 __device__ __forceinline__ void bitonic_sort_u32(uint32_t* keys, int P, int tid) {
+    const int half = P >> 1;
     for (int k = 2; k <= P; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < P; i += FL_THREADS) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const uint32_t x = keys[i], y = keys[p];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { keys[i] = y; keys[p] = x; }
-                }
+            for (int t = tid; t < half; t += FL_THREADS) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int p = i | j;
+                const uint32_t x = keys[i], y = keys[p];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) { keys[i] = y; keys[p] = x; }
             }
-            __syncthreads();
+            const int next_j = (j > 1) ? (j >> 1) : k;
+            if (j > 32 || next_j > 32) __syncthreads(); else __syncwarp();
         }
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(FL_THREADS)
