@@ -322,6 +322,8 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         ctx->pdl = false; ctx->pdl_enabled = true;
         ctx->repack_kernel = true;
         ctx->fill_kernel = false;
+        ctx->small_batch_max = kMergedLevelsMaxFrames;
+        if (const char* v = getenv("B200VO_SMALL_BATCH_MAX")) { const int c = atoi(v); if (c >= 0 && c <= kMergedLevelsMaxFrames) ctx->small_batch_max = c; }
         if (const char* v = getenv("B200VO_FILL_KERNEL")) ctx->fill_kernel = (atoi(v) != 0);
         if (const char* v = getenv("B200VO_REPACK_KERNEL")) ctx->repack_kernel = (atoi(v) != 0);
         if (const char* v = getenv("B200VO_PDL")) ctx->pdl_enabled = (atoi(v) != 0);
@@ -494,7 +496,7 @@ int b200vo_detect(b200vo_ctx* ctx, int first_slot, int n) {
     int rc;
     // small batches (the per-frame streaming step) are a chain of dependent launches of a few CTAs each:
     // programmatic dependent launch overlaps each launch latency with the predecessor's tail (common.cuh)
-    ctx->pdl = ctx->pdl_enabled && !ctx->timing && n <= kMergedLevelsMaxFrames;
+    ctx->pdl = ctx->pdl_enabled && !ctx->timing && n <= ctx->small_batch_max;
     struct PdlOff { b200vo_ctx* c; ~PdlOff() { c->pdl = false; } } pdl_off{ctx};
     StageClock clk(ctx);
     if ((rc = launch_pyramid(ctx, first_slot, n))) return rc;  clk.mark();
@@ -687,7 +689,7 @@ int b200vo_match(b200vo_ctx* ctx, int slot1, int slot2, b200vo_dmatch* out, int 
 static int run_pairs(b200vo_ctx* ctx, int first_slot, int npairs, int slot_b_override, int64_t first_pair_id,
                      const int32_t* d_samples, int nhyp) {
     int rc;
-    ctx->pdl = ctx->pdl_enabled && !ctx->timing && npairs <= kMergedLevelsMaxFrames;
+    ctx->pdl = ctx->pdl_enabled && !ctx->timing && npairs <= ctx->small_batch_max;
     struct PdlOff { b200vo_ctx* c; ~PdlOff() { c->pdl = false; } } pdl_off{ctx};
     StageClock clk(ctx);
     if ((rc = launch_match_slots(ctx, first_slot, npairs, slot_b_override))) return rc;    clk.mark();

@@ -277,7 +277,7 @@ int launch_blur(b200vo_ctx* ctx, int first_slot, int n) {
     LevelTiles lt;
     lt.first[0] = 0;
     for (int l = 0; l < kLevels; ++l) level_tiles_add(lt, l, div_up(ctx->store.lv[l].w, BL_W), div_up(ctx->store.lv[l].h, BL_H), n);
-    if (n <= kMergedLevelsMaxFrames) {
+    if (n <= ctx->small_batch_max) {
         // one launch for all eight levels
         launch_k(ctx, blur_kernel<true>, dim3(lt.first[kLevels]), dim3(256), 0, ctx->store, lt, 0, first_slot, maps, ctx->use_tma ? 1 : 0);
         B200VO_LAUNCH_CHECK(ctx);

@@ -177,6 +177,8 @@ struct b200vo_ctx {
     int blur_rows;             // rows per warp strip of the large-batch blur (16 or 24; 0: the two-pass tile kernel; B200VO_BLUR_R)
     int match_variant;         // inner-loop variant of match_kernel (see match.cu)
     int match_csa;             // 0: 8 POPC, 1: 2 CSA + 6 POPC, 2: full Harley-Seal (4 POPC), 3: 3 CSA + 5 POPC (default)
+    int small_batch_max;       // batches of at most this many frames / pairs take the small-batch code paths (kMergedLevelsMaxFrames;
+                               // B200VO_SMALL_BATCH_MAX=0 sends even single frames through the large-batch kernels: tests)
     bool fill_kernel;          // device_fill32 by kernel (B200VO_FILL_KERNEL=1) instead of cudaMemsetAsync (default; byte-replicated values only)
     bool repack_kernel;        // device-side ingest of gray frames by kernel (default) or cudaMemcpy3DAsync (B200VO_REPACK_KERNEL=0)
     bool pdl;                  // programmatic dependent launch for the current call (small batches only; B200VO_PDL=0 disables)

@@ -309,7 +309,7 @@ int launch_fast(b200vo_ctx* ctx, int first_slot, int n) {
         level_tiles_add(wide, l, any ? div_up(iw, FastTile<128>::FT_W) : 0, (any && w) ? div_up(ih, FastTile<128>::FT_H) : 0, n);
         level_tiles_add(narrow, l, any ? div_up(iw, FastTile<64>::FT_W) : 0, (any && !w) ? div_up(ih, FastTile<64>::FT_H) : 0, n);
     }
-    if (n <= kMergedLevelsMaxFrames) {
+    if (n <= ctx->small_batch_max) {
         // two launches: the wide-tile levels (0..4) and the narrow-tile levels (5..7)
         if (wide.first[kLevels] > 0) {
             launch_k(ctx, fast_levels_kernel<128>, dim3(wide.first[kLevels]), dim3(256), 0, ctx->store, wide, first_slot, maps, tma);

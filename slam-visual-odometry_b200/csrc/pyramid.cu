@@ -323,7 +323,7 @@ int launch_bgr2gray(b200vo_ctx* ctx, const uint8_t* d_bgr, size_t pitch, size_t 
 int launch_pyramid(b200vo_ctx* ctx, int first_slot, int n) {
     for (int l = 1; l < kLevels; ++l) {
         const LevelGeom& g = ctx->store.lv[l];
-        if (ctx->use_tma && ctx->resize_strip && ctx->resize_strip_ok[l] && n > kMergedLevelsMaxFrames) {
+        if (ctx->use_tma && ctx->resize_strip && ctx->resize_strip_ok[l] && n > ctx->small_batch_max) {
             dim3 grid(div_up(g.w, RZ_W), div_up(g.h, 8 * kResizeStripRows), n);
             launch_k(ctx, resize_strip_kernel<kResizeStripRows>, dim3(grid), dim3(256), 0, ctx->store, ctx->d_tab, l, first_slot, ctx->tmap_resize_strip[l - 1]);
         } else if (ctx->use_tma) {

@@ -269,7 +269,7 @@ template <int THREADS, int MINB>
 static int launch_five_point_as(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     constexpr int GROUPS = 3 * (THREADS / 32);
     const size_t smem = GROUPS * sizeof(geom::GroupShared);
-    if (THREADS == 256 && MINB == 2 && npairs <= kMergedLevelsMaxFrames) {
+    if (THREADS == 256 && MINB == 2 && npairs <= ctx->small_batch_max) {
         launch_k(ctx, five_point_group_kernel<256, 2, true>, dim3(dim3(div_up(ra.nround, GROUPS), npairs)), dim3(THREADS), smem, ctx->pairs, ra);
         B200VO_LAUNCH_CHECK(ctx);
         return B200VO_OK;

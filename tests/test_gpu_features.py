@@ -233,6 +233,29 @@ def test_odd_sizes_bit_exact(built, W, H, NF):
         assert rec["n_matches"] >= 0
 
 
+@pytest.mark.parametrize("W,H,NF", [(100, 80, 300), (333, 222, 700), (1999, 1001, 5000), (64, 64, 100), (4095, 300, 2000), (1241, 376, 3000)])
+def test_large_batch_kernels_at_odd_sizes(built, W, H, NF, monkeypatch):
+    """The kernels of large launch batches (warp-strip pyramid and blur, one FAST / blur launch per level, plain launches)
+    forced onto two-frame batches with B200VO_SMALL_BATCH_MAX=0, at sizes whose tiles overhang in both directions, whose
+    levels are smaller than one tile, and at the bench size: pyramid levels, blurred levels, keypoints and descriptors
+    byte-identical to the small-batch kernels (which test_odd_sizes_bit_exact pins against the oracle)."""
+    from b200vo import synth
+    frames = synth.make_sequence(W, H, 2, device="cuda")[0].cpu().numpy()
+    out = {}
+    for mode in ("16", "0"):
+        monkeypatch.setenv("B200VO_SMALL_BATCH_MAX", mode)
+        with built.Context(W, H, nfeatures=NF, max_frames=3, ransac_hypotheses=64) as ctx:
+            ctx.upload_frames(frames, 0)
+            ctx.detect(0, 2)
+            out[mode] = ([ctx.get_features(s) for s in range(2)], [ctx.get_pyramid_level(1, l) for l in range(8)],
+                         [ctx.get_pyramid_level(1, l, blurred=True) for l in range(8)], ctx.process_pairs(0, 1, 0))
+    for (ka, da), (kb, db) in zip(out["16"][0], out["0"][0]):
+        assert ka.tobytes() == kb.tobytes() and np.array_equal(da, db)
+    for a, b in zip(out["16"][1] + out["16"][2], out["0"][1] + out["0"][2]):
+        assert np.array_equal(a, b)
+    assert out["16"][3].tobytes() == out["0"][3].tobytes()
+
+
 @pytest.mark.parametrize("thr", [1, 40, 127, 128, 200])
 def test_fast_threshold_range(built, seq_small, thr):
     """FAST corners for thresholds across the supported range (the byte-SIMD pre-test switches formula at
