@@ -436,7 +436,7 @@ static int upload_common(b200vo_ctx* ctx, const void* src, int n, size_t pitch, 
         }
         B200VO_CUDA_CHECK(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[sb], 0));
         if (pitch == row && frame_stride == fbytes) {
-            B200VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_stage[sb], src, need, cudaMemcpyHostToDevice, ctx->copy_stream));
+            B200VO_CUDA_CHECK(cudaMemcpyAsync(ctx->d_stage[sb], src, need, cudaMemcpyDefault, ctx->copy_stream));   // Default: tools/e2e_probe.py feeds a device buffer through the staged path
         } else {
             for (int i = 0; i < n; ++i)
                 B200VO_CUDA_CHECK(cudaMemcpy2DAsync(ctx->d_stage[sb] + (size_t)i * fbytes, row,
