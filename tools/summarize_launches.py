@@ -24,7 +24,7 @@ def main(path):
         d[0] += 1
         d[1] += v
     # ncu prints the namespace only in some modes (not with -k filters): recognise the library's kernels by name too
-    lib = re.compile(r"b200vo::|^(resize_tma|resize|bgr2gray|fast|fast_levels|select|orient|keypoint_finalize|describe|blur|brief|match|match_knn2|filter|"
+    lib = re.compile(r"b200vo::|^(resize_tma|resize_strip|resize|repack_gray|fill32|blur_strip|bgr2gray|fast|fast_levels|select|orient|keypoint_finalize|describe|blur|brief|match|match_knn2|filter|"
                      r"five_point_group|five_point_deferred|score|score_models|finalize|pose_decompose|pose_vote|pose_select|pose_mask|"
                      r"clear_detect_state|adaptive_update|stamp_rounds|popc_rate)_kernel")
     ours = {k: v for k, v in agg.items() if lib.search(k)}
