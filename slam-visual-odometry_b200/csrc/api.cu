@@ -312,7 +312,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         ctx->use_tma = true;
         if (const char* v = getenv("B200VO_TMA")) ctx->use_tma = (atoi(v) != 0);
         ctx->match_csa = 3;
-        ctx->match_variant = 1;
+        ctx->match_variant = 3;
         ctx->blur_rows = 24;
         ctx->resize_strip = true;
         if (const char* v = getenv("B200VO_RESIZE_STRIP")) ctx->resize_strip = (atoi(v) != 0);
@@ -332,7 +332,7 @@ int b200vo_create(const b200vo_options* opt, int device, b200vo_ctx** out) {
         if (const char* v = getenv("B200VO_FPG")) ctx->fpg_variant = atoi(v);
         if (const char* v = getenv("B200VO_FILTER_FAST_CAP")) ctx->filter_fast_cap = atoi(v);
         if (const char* v = getenv("B200VO_MATCH_CSA")) { const int c = atoi(v); if (c >= 0 && c <= 3) ctx->match_csa = c; }
-        if (const char* v = getenv("B200VO_MATCH_V")) { const int c = atoi(v); if (c >= 0 && c <= 2) ctx->match_variant = c; }
+        if (const char* v = getenv("B200VO_MATCH_V")) { const int c = atoi(v); if (c >= 0 && c <= 3) ctx->match_variant = c; }
         void* fnp = nullptr;
         cudaDriverEntryPointQueryResult qres;
         TRYCUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &qres));

@@ -102,8 +102,11 @@ __device__ __forceinline__ void resolve_pair(const MatchArgs& a, int pair, const
 //      is one IMAD on the FMA pipe
 //   2  as 1, and the last of the R rows takes the full Harley-Seal tree (4 POPC + 22 LOP3): 19 instead of 20 POPC per
 //      column of four rows, which balances the POPC pipe (8 clk per warp instruction) against the ALU pipe (2 clk)
+//   3  as 1 with __launch_bounds__(256, 4): 64 registers instead of 76, four CTAs (32 warps) per SM instead of three -- the
+//      default (2.802 -> 2.774 ms per 250 pairs; unrolling the column loop by 4 instead of 2, and column chunks of 500
+//      instead of 512 so that all CTAs are equal, measured no gain)
 template <int R, int CSA, int V>
-__global__ void __launch_bounds__(MT_THREADS)
+__global__ void __launch_bounds__(MT_THREADS, V == 3 ? 4 : 0)
 match_kernel(MatchArgs a) {
     pdl_grid_sync();
     __shared__ __align__(16) uint32_t s_t[MT_MAXCHUNK * 8];
@@ -310,7 +313,7 @@ static int run_match(b200vo_ctx* ctx, MatchArgs a, int n1max, int n2max, int n1_
          else if (csa == 1) launch_k(ctx, match_kernel<RR, 1, VV>, dim3(grid), dim3(MT_THREADS), 0, a); \
          else launch_k(ctx, match_kernel<RR, 0, VV>, dim3(grid), dim3(MT_THREADS), 0, a); } while (0)
 #define LAUNCH_MATCH(RR) \
-    do { if (variant == 2) LAUNCH_MATCH_V(RR, 2); else if (variant == 1) LAUNCH_MATCH_V(RR, 1); else LAUNCH_MATCH_V(RR, 0); } while (0)
+    do { if (variant == 2) LAUNCH_MATCH_V(RR, 2); else if (variant == 1) LAUNCH_MATCH_V(RR, 1); else if (variant == 3) LAUNCH_MATCH_V(RR, 3); else LAUNCH_MATCH_V(RR, 0); } while (0)
     switch (R) {
         case 8: LAUNCH_MATCH(8); break;
         case 6: LAUNCH_MATCH(6); break;
