@@ -204,7 +204,7 @@ __device__ __forceinline__ uint32_t blur_col4(const float4& a0, const float4& a1
 }
 
 template <int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)          // 64 registers, 4 CTAs / SM; capping at 48 / 40 registers (5 / 6 CTAs) spills the ring: 0.448 -> 0.481 / 0.513 ms
 blur_strip_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap) {
     pdl_grid_sync();
     constexpr int TH = 8 * R, SH = TH + 6;

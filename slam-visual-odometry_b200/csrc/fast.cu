@@ -14,6 +14,10 @@
 
 namespace b200vo {
 
+#ifndef FAST_MINB
+#define FAST_MINB 7
+#endif
+
 // Tile geometry: 60x30 outputs -> a 64x32 score tile (NMS halo; cell 0 sits on a 4-byte aligned pixel column, so the
 // pre-test reads aligned words: the halo is 3 cells on the left, 1 on the right) -> a 70x38 pixel tile (+3 ring).
 // The pixel tile is fetched as aligned 32-bit words (row of 20 words; `shift` = misalignment of the
@@ -63,9 +67,9 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
     __shared__ __align__(128) uint8_t s_img[FT_SH * FT_SW];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ __align__(4) uint8_t s_score[FT_CH * FT_CW];
-    __shared__ uint16_t s_surv[FT_CH * FT_CW];
+    __shared__ __align__(4) uint16_t s_surv[FT_CH * FT_CW];
     __shared__ uint16_t s_corn[FT_CH * FT_CW];
-    __shared__ uint32_t s_list[FT_CH * FT_CW / 4];
+    uint32_t* s_list = reinterpret_cast<uint32_t*>(s_surv);      // phase 4's output list (<= cells / 4 entries) reuses the survivor list, dead after phase 2
     __shared__ int s_nsurv, s_ncorn, s_n, s_base;
     __shared__ int s_hist[256];                     // score histogram of this tile, flushed once (one global atomic per non-empty bin)
 
@@ -257,7 +261,7 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
 
 // one pyramid level per launch (large batches): the level is a kernel parameter
 template <int CW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FAST_MINB)
 fast_kernel(StoreView sv, int level, int first_slot, const __grid_constant__ CUtensorMap tmap, int use_tma) {
     pdl_grid_sync();
     fast_tile<CW>(sv, level, blockIdx.x, blockIdx.y, blockIdx.z, first_slot, &tmap, use_tma);

@@ -229,7 +229,7 @@ resize_tma_kernel(StoreView sv, const int* __restrict__ tab, int level, int firs
 // source footprint arrives as ONE TMA box of 176 x kResizeStripBoxH bytes; the row taps of the tile are staged in shared
 // memory while the box is in flight.  Same integer arithmetic as above, bit-exact.
 template <int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)       // 40 registers, no spills: 6 CTAs / SM instead of 5 at 47 registers (0.275 -> 0.257 ms per 251 frames)
 resize_strip_kernel(StoreView sv, const int* __restrict__ tab, int level, int first_slot, const __grid_constant__ CUtensorMap tmap) {
     pdl_grid_sync();
     constexpr int TH = 8 * R;
