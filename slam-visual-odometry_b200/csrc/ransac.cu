@@ -204,7 +204,7 @@ __device__ __forceinline__ int warp_count_inliers(const PairView& pv, int pair, 
 // double->float conversions were 13 % of the kernel's instructions.
 constexpr int SC_THREADS = 256;
 constexpr int SC_HB = 32;
-constexpr int SC_MAXPTS = 2048;                            // staging capacity: 32 KB of float4 (pairs with more good matches read global memory)
+constexpr int SC_MAXPTS = 1536;                            // staging capacity: 24 KB of float4 (pairs with more good matches read global memory); with the float models 36 KB: 5 CTAs per SM
 constexpr int SC_SLOTS = SC_HB * kMaxSolutions;
 
 __global__ void __launch_bounds__(SC_THREADS)
@@ -220,9 +220,10 @@ score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
     const int hb0 = ra.h0 + blockIdx.x * SC_HB;
     const int hb1 = min(hb0 + SC_HB, ra.h0 + ra.nround);
     const int tid = threadIdx.x;
-    double* s_E = reinterpret_cast<double*>(sc_smem);                      // [SC_SLOTS][9] (exact re-evaluation inside the threshold band)
-    float* s_Ef = reinterpret_cast<float*>(sc_smem + SC_SLOTS * 9 * sizeof(double));   // [SC_SLOTS][9] the same rounded to float, converted once
-    float4* s_pts = reinterpret_cast<float4*>(sc_smem + SC_SLOTS * 9 * (sizeof(double) + sizeof(float)));
+    // the models as float (converted once); the exact re-evaluation inside the threshold band (0.3 % of the points) reads the
+    // double model from global memory: keeping a double copy in shared memory too (23 KB) held the kernel at 3 CTAs per SM
+    float* s_Ef = reinterpret_cast<float*>(sc_smem);                       // [SC_SLOTS][9]
+    float4* s_pts = reinterpret_cast<float4*>(sc_smem + SC_SLOTS * 9 * sizeof(float));
     const float4* xf = pv.xf + (size_t)pair * pv.kp_cap;
     const bool staged = m <= stage_cap;                    // uniform over the CTA
     if (tid == 0) { s_n = 0; s_best = pv.counts ? 0 : (int)(pv.best[pair] >> 32); }
@@ -239,9 +240,7 @@ score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
     const int n = s_n;
     for (int i = tid; i < n * 9; i += SC_THREADS) {
         const int j = i / 9, k = i - j * 9;
-        const double v = pv.models[(slot0 + s_slot[j]) * 9 + k];
-        s_E[i] = v;
-        s_Ef[i] = (float)v;
+        s_Ef[i] = (float)pv.models[(slot0 + s_slot[j]) * 9 + k];
     }
     __syncthreads();
     const int lane = tid & 31, warp = tid >> 5;
@@ -252,8 +251,9 @@ score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
         // since.  No global read inside the loop: the round-2 profile of the first staged version showed the per-model
         // read of the global best (L2 round trip, consumed one model later) as 62 % of all stall samples.
         const int floor_count = pv.counts ? 0 : *(volatile int*)&s_best;
-        const int cnt = staged ? warp_count_inliers<true>(pv, pair, m, s_E + j * 9, s_Ef + j * 9, xf, thr, lane, floor_count)
-                               : warp_count_inliers<false>(pv, pair, m, s_E + j * 9, s_Ef + j * 9, xf, thr, lane, floor_count);
+        const double* Ed = pv.models + (slot0 + slot) * 9;
+        const int cnt = staged ? warp_count_inliers<true>(pv, pair, m, Ed, s_Ef + j * 9, xf, thr, lane, floor_count)
+                               : warp_count_inliers<false>(pv, pair, m, Ed, s_Ef + j * 9, xf, thr, lane, floor_count);
         if (lane == 0) {
             if (pv.counts) pv.counts[slot0 + slot] = cnt;
             if (cnt >= floor_count) {
@@ -300,13 +300,13 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
 static int launch_score(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     const dim3 grid(div_up(ra.nround, SC_HB), npairs);
     const int cap = std::min(ctx->pairs.kp_cap, SC_MAXPTS);
-    launch_k(ctx, score_kernel, dim3(grid), dim3(SC_THREADS), SC_SLOTS * 9 * (sizeof(double) + sizeof(float)) + (size_t)cap * sizeof(float4), ctx->pairs, ra, cap);
+    launch_k(ctx, score_kernel, dim3(grid), dim3(SC_THREADS), SC_SLOTS * 9 * sizeof(float) + (size_t)cap * sizeof(float4), ctx->pairs, ra, cap);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
 
 int init_ransac_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_SLOTS * 9 * (sizeof(double) + sizeof(float)) + SC_MAXPTS * sizeof(float4)));
+    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_SLOTS * 9 * sizeof(float) + SC_MAXPTS * sizeof(float4)));
     auto fpg_attr = [&](auto main_k, auto def_k, int threads) {
         const int bytes = 3 * (threads / 32) * (int)sizeof(geom::GroupShared);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(main_k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
