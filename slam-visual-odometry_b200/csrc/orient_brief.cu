@@ -194,7 +194,7 @@ constexpr int DK_KP = 8, DK_THREADS = 128;          // 32 KB of boxes per CTA: 7
                                                     // 33 % of the stall samples at the phase barriers, issue utilisation 39 %)
 constexpr int DK_OBOX = (kOrientBoxW * kOrientBoxH + 127) / 128 * 128;      // 1536: TMA destinations are 128-byte aligned
 constexpr int DK_BBOX = (kBriefBoxW * kBriefBoxH + 127) / 128 * 128;        // 2560
-constexpr int DK_SMEM = DK_KP * (DK_OBOX + DK_BBOX);
+constexpr int DK_SMEM = DK_KP * DK_BBOX;               // the unblurred box of a keypoint is dead after phase A: the blurred box lands in the same 2.5 KB
 
 __global__ void __launch_bounds__(DK_THREADS)
 describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps maps_pyr, const __grid_constant__ LevelMaps maps_blur) {
@@ -226,8 +226,8 @@ describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps 
     const int nk = min(DK_KP, min(cnt - i0, sv.kp_cap - (base + i0)));          // uniform over the CTA
     if (nk <= 0) return;
     const LevelGeom g = sv.lv[level];
-    uint8_t* s_obox = dk_smem;
-    uint8_t* s_bbox = dk_smem + DK_KP * DK_OBOX;
+    uint8_t* s_obox = dk_smem;                              // keypoint j: [j * DK_BBOX, + DK_OBOX) during phase A ...
+    uint8_t* s_bbox = dk_smem;                              // ... then [j * DK_BBOX, + DK_BBOX) holds the blurred box
     const size_t lk = (size_t)slot * sv.lkp_total + sv.lkp_off[level] + i0;
     if (tid == 0) {
         tma::mbar_init(&s_bar[0], 1); tma::mbar_init(&s_bar[1], 1); tma::fence_mbar_init();
@@ -239,8 +239,7 @@ describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps 
         const uint32_t key = sv.lkp_key[lk + tid];
         const int x = (key >> 8) & 0xFFF, y = key >> 20;
         s_x[tid] = x; s_y[tid] = y;
-        tma::load_3d(s_obox + tid * DK_OBOX, &maps_pyr.m[level], &s_bar[0], (x - kHalfPatch) & ~15, y - kHalfPatch, slot);
-        tma::load_3d(s_bbox + tid * DK_BBOX, &maps_blur.m[level], &s_bar[1], (x - kBriefReach) & ~15, y - kBriefReach, slot);
+        tma::load_3d(s_obox + tid * DK_BBOX, &maps_pyr.m[level], &s_bar[0], (x - kHalfPatch) & ~15, y - kHalfPatch, slot);
     }
     __syncthreads();
     tma::mbar_wait(&s_bar[0], 0);
@@ -248,7 +247,7 @@ describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps 
     // ---- phase A: moments, warp per keypoint
     for (int j = warp; j < nk; j += DK_THREADS / 32) {
         const int sh = (s_x[j] - kHalfPatch) & 15;                                // byte shift of the disc's first column in the box
-        const uint32_t* __restrict__ b32 = reinterpret_cast<const uint32_t*>(s_obox + j * DK_OBOX) + (sh >> 2);
+        const uint32_t* __restrict__ b32 = reinterpret_cast<const uint32_t*>(s_obox + j * DK_BBOX) + (sh >> 2);
         const uint2* __restrict__ tab = d_ic_table[sh & 3];
         int m10 = 0, m01 = 0;
 #pragma unroll
@@ -271,6 +270,10 @@ describe_kernel(StoreView sv, int first_slot, const __grid_constant__ LevelMaps 
     // ---- phase B: angle, rotation, final keypoint record (canonical (octave, y, x) order), thread per keypoint
     if (tid < nk) {
         const int x = s_x[tid], y = s_y[tid];
+        // the blurred box overwrites the unblurred one (every warp is past phase A: the barrier above); it lands while this
+        // thread computes the angle.  Generic-proxy reads before, async-proxy writes after: proxy fence in between.
+        tma::fence_proxy_async();
+        tma::load_3d(s_bbox + tid * DK_BBOX, &maps_blur.m[level], &s_bar[1], (x - kBriefReach) & ~15, y - kBriefReach, slot);
         const int2 mom = s_mom[tid];
         b200vo_keypoint kp;
         kp.x = __fmul_rn((float)x, g.scale);
