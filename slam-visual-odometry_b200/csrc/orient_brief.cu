@@ -190,8 +190,8 @@ brief_kernel(StoreView sv, int first_slot) {
 // Phase C: warp per keypoint, lane = descriptor byte, the 512 taps read shared memory.  The moments and the
 // rotation never touch global memory (round 1: three kernels, kp_mom / kp_rot round trips, 512 scattered global
 // byte loads per keypoint -- long-scoreboard 43 % in brief_kernel).  The blurred box lands while phases A and B run.
-constexpr int DK_KP = 8, DK_THREADS = 128;          // 32 KB of boxes per CTA: 7 CTAs = 28 warps per SM (16 keypoints / 64 KB: 12 warps,
-                                                    // 33 % of the stall samples at the phase barriers, issue utilisation 39 %)
+constexpr int DK_KP = 8, DK_THREADS = 128;          // 20 KB of boxes per CTA: 9 CTAs = 36 warps per SM (registers).  Measured per 251 frames: 8 keypoints
+                                                    // with separate boxes (32 KB, 6-7 CTAs) 0.578 ms; 8 keypoints, shared box 0.490 ms; 16 keypoints / 256 threads 0.600 ms
 constexpr int DK_OBOX = (kOrientBoxW * kOrientBoxH + 127) / 128 * 128;      // 1536: TMA destinations are 128-byte aligned
 constexpr int DK_BBOX = (kBriefBoxW * kBriefBoxH + 127) / 128 * 128;        // 2560
 constexpr int DK_SMEM = DK_KP * DK_BBOX;               // the unblurred box of a keypoint is dead after phase A: the blurred box lands in the same 2.5 KB
