@@ -206,6 +206,7 @@ constexpr int SC_THREADS = 256;
 constexpr int SC_HB = 32;
 constexpr int SC_MAXPTS = 1536;                            // staging capacity: 24 KB of float4 (pairs with more good matches read global memory); with the float models 36 KB: 5 CTAs per SM
 constexpr int SC_SLOTS = SC_HB * kMaxSolutions;
+constexpr int SC_MAXPTS_LIMIT = 4096;                      // largest staging capacity the kernel may be launched with (B200VO_SCORE_CAP)
 
 __global__ void __launch_bounds__(SC_THREADS)
 score_kernel(PairView pv, RansacArgs ra, int stage_cap) {
@@ -299,14 +300,15 @@ static int launch_five_point(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) 
 
 static int launch_score(b200vo_ctx* ctx, const RansacArgs& ra, int npairs) {
     const dim3 grid(div_up(ra.nround, SC_HB), npairs);
-    const int cap = std::min(ctx->pairs.kp_cap, SC_MAXPTS);
+    int cap = std::min(ctx->pairs.kp_cap, SC_MAXPTS);
+    if (const char* v = getenv("B200VO_SCORE_CAP")) { const int c = atoi(v); if (c >= 0 && c <= SC_MAXPTS_LIMIT) cap = std::min(ctx->pairs.kp_cap, c); }
     launch_k(ctx, score_kernel, dim3(grid), dim3(SC_THREADS), SC_SLOTS * 9 * sizeof(float) + (size_t)cap * sizeof(float4), ctx->pairs, ra, cap);
     B200VO_LAUNCH_CHECK(ctx);
     return B200VO_OK;
 }
 
 int init_ransac_kernels() {
-    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_SLOTS * 9 * sizeof(float) + SC_MAXPTS * sizeof(float4)));
+    cudaError_t e = cudaFuncSetAttribute(score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SC_SLOTS * 9 * sizeof(float) + SC_MAXPTS_LIMIT * sizeof(float4)));
     auto fpg_attr = [&](auto main_k, auto def_k, int threads) {
         const int bytes = 3 * (threads / 32) * (int)sizeof(geom::GroupShared);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(main_k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
