@@ -161,10 +161,13 @@ __device__ __forceinline__ void fast_tile(const StoreView& sv, int level, int bx
         int base = 0;
         if (lane == 31 && incl) base = atomicAdd(&s_nsurv, incl);
         base = __shfl_sync(0xffffffffu, base, 31) + incl - cnt;
-        while (flags) {                                             // ~3 survivors per thread on a textured frame
-            const int b = __ffs(flags) - 1;
-            flags &= flags - 1;
-            s_surv[base++] = (uint16_t)((cy0 + (b >> 2) * ROWS_PER_IT) * FT_CW + 4 * j + (b & 3));
+        // One predicated store per cell instead of a loop over the set bits: the loop ran as long as the fullest lane of the
+        // warp needed (~12 rounds of ~11 instructions with a third of the lanes active: 12 % of the kernel's instructions);
+        // unrolled, every lane spends 4 instructions per cell whether it survives or not.
+        const int c0 = cy0 * FT_CW + 4 * j;
+#pragma unroll
+        for (int b = 0; b < 4 * ITERS; ++b) {
+            if (flags & (1u << b)) s_surv[base++] = (uint16_t)(c0 + (b >> 2) * ROWS_PER_IT * FT_CW + (b & 3));
         }
     }
     __syncthreads();
