@@ -222,15 +222,72 @@ select_kernel(StoreView sv, int first_slot) {
     __syncthreads();
     const int outn = s_out;
     const int nsort = min(outn, P2);
-    int P = 1;
-    while (P < nsort) P <<= 1;
-    for (int i = nsort + tid; i < P; i += SEL_THREADS) pairs[i] = ~0ull;
-    __syncthreads();
-    bitonic_sort_u64(pairs, P);
+    const unsigned long long* sorted = pairs;
+    // Raster order by a counting sort on the row: the keys are (y << 20 | x << 8 | score) with a handful of keypoints per
+    // row, so a row histogram, its prefix sum, a scatter and an insertion sort inside each row order the list in seven
+    // barriers and O(n) work (the bitonic network: 55 steps for 1024 pairs).  The working arrays live in the key / response
+    // arrays, dead by now.  Levels whose rows do not fit there, or with a crowded row, take the bitonic sort.
+    int* rowcnt = reinterpret_cast<int*>(keys);                    // [h + 1]
+    int* rowpos = rowcnt + (g.h + 1);                              // [h + 1] start of the row in `out`, then its fill pointer
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(rowpos + (g.h + 1));      // 2 (h + 1) ints behind an 8-byte aligned base: aligned
+    const bool fits = 2 * (g.h + 1) + 2 * nsort + 2 <= 2 * g.sel_cap && g.h + 1 <= 16 * SEL_THREADS;
+    bool counted = false;
+    if (fits && nsort > 64) {
+        __shared__ int s_wsum[SEL_THREADS / 32], s_crowded;
+        for (int i = tid; i <= g.h; i += SEL_THREADS) rowcnt[i] = 0;
+        if (tid == 0) s_crowded = 0;
+        __syncthreads();
+        for (int i = tid; i < nsort; i += SEL_THREADS) atomicAdd(&rowcnt[(uint32_t)(pairs[i] >> 32) >> 20], 1);
+        __syncthreads();
+        // exclusive prefix sum over the rows: a thread owns E consecutive rows
+        const int E = (g.h + 1 + SEL_THREADS - 1) / SEL_THREADS;
+        int local = 0, mx = 0;
+        for (int e = 0; e < E; ++e) { const int r = tid * E + e; if (r <= g.h) { local += rowcnt[r]; mx = max(mx, rowcnt[r]); } }
+        int incl = local;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += v; }
+        if (lane == 31) s_wsum[tid >> 5] = incl;
+        if (mx > 32) s_crowded = 1;
+        __syncthreads();
+        int pre = incl - local;
+        for (int w = 0; w < (tid >> 5); ++w) pre += s_wsum[w];
+        for (int e = 0; e < E; ++e) { const int r = tid * E + e; if (r <= g.h) { rowpos[r] = pre; pre += rowcnt[r]; } }
+        const bool crowded = s_crowded != 0;
+        __syncthreads();
+        if (!crowded) {
+            for (int i = tid; i < nsort; i += SEL_THREADS) {
+                const unsigned long long v = pairs[i];
+                out[atomicAdd(&rowpos[(uint32_t)(v >> 32) >> 20], 1)] = v;
+            }
+            __syncthreads();
+            for (int r = tid; r <= g.h; r += SEL_THREADS) {              // rowpos[r] is the END of row r now
+                const int c = rowcnt[r];
+                if (c > 1) {
+                    unsigned long long* a = out + rowpos[r] - c;
+                    for (int i = 1; i < c; ++i) {
+                        const unsigned long long v = a[i];
+                        int j = i - 1;
+                        while (j >= 0 && a[j] > v) { a[j + 1] = a[j]; --j; }
+                        a[j + 1] = v;
+                    }
+                }
+            }
+            __syncthreads();
+            sorted = out;
+            counted = true;
+        }
+    }
+    if (!counted) {
+        int P = 1;
+        while (P < nsort) P <<= 1;
+        for (int i = nsort + tid; i < P; i += SEL_THREADS) pairs[i] = ~0ull;
+        __syncthreads();
+        bitonic_sort_u64(pairs, P);
+    }
     uint32_t* okey = sv.lkp_key + (size_t)slot * sv.lkp_total + sv.lkp_off[level];
     float* oresp = sv.lkp_resp + (size_t)slot * sv.lkp_total + sv.lkp_off[level];
     for (int i = tid; i < min(nsort, g.kp_cap); i += SEL_THREADS) {
-        const unsigned long long v = pairs[i];
+        const unsigned long long v = sorted[i];
         okey[i] = (uint32_t)(v >> 32);
         oresp[i] = __uint_as_float((uint32_t)v);
     }
