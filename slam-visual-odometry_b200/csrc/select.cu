@@ -100,10 +100,15 @@ __device__ __forceinline__ float harris_at(const uint8_t* __restrict__ img, int 
         const uint8_t* q = p + (size_t)(row + 2) * pitch;
 #pragma unroll
         for (int i = 0; i < 9; ++i) r2[i] = __ldg(q + i);
+        // separable form of the same integer sums: vertical [1 2 1] smoothing / difference per column once, then the
+        // horizontal difference / smoothing per output pixel (69 instead of ~105 instructions per patch row)
+        int vs[9], vd[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { vs[i] = r0[i] + 2 * r1[i] + r2[i]; vd[i] = r2[i] - r0[i]; }
 #pragma unroll
         for (int i = 1; i < 8; ++i) {
-            const int ix = (r1[i + 1] - r1[i - 1]) * 2 + (r0[i + 1] - r0[i - 1]) + (r2[i + 1] - r2[i - 1]);
-            const int iy = (r2[i] - r0[i]) * 2 + (r2[i - 1] - r0[i - 1]) + (r2[i + 1] - r0[i + 1]);
+            const int ix = vs[i + 1] - vs[i - 1];
+            const int iy = vd[i - 1] + 2 * vd[i] + vd[i + 1];
             a += ix * ix; b += iy * iy; c += ix * iy;
         }
 #pragma unroll
@@ -117,7 +122,7 @@ __device__ __forceinline__ float harris_at(const uint8_t* __restrict__ img, int 
     return __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(af, bf), __fmul_rn(cf, cf)), t3), s4);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(SEL_THREADS, 3)      // 40 registers: the separable Harris sums need 46 (59 before), three CTAs per SM pay now (0.240 -> 0.232 ms)
 select_kernel(StoreView sv, int first_slot) {
     pdl_grid_sync();
     extern __shared__ __align__(8) unsigned char smem_raw[];
