@@ -83,3 +83,16 @@ extern "C" int hs_cheirality_fast_path(const double* R, const double* t, const d
     for (int i = 0; i < n; ++i) { fast[i] = (unsigned char)cheirality_fast_path(R, t, x1[2*i], x1[2*i+1], x2[2*i], x2[2*i+1]); c += fast[i]; }
     return c;
 }
+// register-resident Horner / bracket solver of the exact root path vs the run-time-degree versions: must agree bit for bit
+// (leading zero coefficients leave every intermediate value unchanged)
+extern "C" int hs_bracket_root_both(const double* c, int deg, double a, double b, double* out_runtime, double* out_reg10) {
+    double cr[11];
+    for (int i = 0; i <= 10; ++i) cr[i] = (i <= deg) ? c[i] : 0.0;
+    const double fa = horner(c, deg, a), fa2 = horner_reg10(cr, a);
+    const double fb = horner(c, deg, b), fb2 = horner_reg10(cr, b);
+    if (std::memcmp(&fa, &fa2, 8) != 0 || std::memcmp(&fb, &fb2, 8) != 0) return -1;
+    if (fa == 0.0 || fb == 0.0 || (fa < 0.0) == (fb < 0.0)) return 0;
+    *out_runtime = bracket_root_fast(c, deg, a, b, fa);
+    *out_reg10 = bracket_root_fast_reg10(cr, a, b, fa2);
+    return 1;
+}

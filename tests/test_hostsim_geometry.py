@@ -156,3 +156,31 @@ def test_dlt_null_vector_by_adjugate_equals_svd(hs):
             ref = G.cheirality_mask(Rc, tc, x1, x2)
             assert np.array_equal(ok.astype(bool), ref), (zmax, noise, int((ok.astype(bool) != ref).sum()))
     assert fast_total >= 0.98 * n_total, (fast_total, n_total)
+
+
+def test_register_resident_root_solver_is_bit_identical(hs):
+    """The exact root path keeps the level polynomial in registers padded with zero coefficients up to degree 10
+    (horner_reg10 / bracket_root_fast_reg10) instead of looping over its true degree from shared memory.  The claim is
+    bit-identity, not closeness: compared here on random polynomials of every degree, with roots near the interval
+    ends and near-double roots."""
+    rng = np.random.default_rng(11)
+    hs.hs_bracket_root_both.restype = ctypes.c_int
+    solved = 0
+    for trial in range(4000):
+        deg = int(rng.integers(1, 11))
+        if trial % 3 == 0:                                   # a near-double root inside (-1, 1)
+            r = rng.uniform(-0.9, 0.9, deg)
+            if deg >= 2:
+                r[1] = r[0] + rng.choice([1e-3, 1e-6, 1e-9])
+            c = np.poly(r)[::-1].copy()
+        else:
+            c = rng.standard_normal(deg + 1)
+        c = np.ascontiguousarray(np.concatenate([c, np.zeros(11 - len(c))]))
+        a, b = np.sort(rng.uniform(-1.0, 1.0, 2))
+        o1, o2 = ctypes.c_double(), ctypes.c_double()
+        rc = hs.hs_bracket_root_both(P(c), deg, ctypes.c_double(a), ctypes.c_double(b), ctypes.byref(o1), ctypes.byref(o2))
+        assert rc >= 0, "Horner values differ"
+        if rc == 1:
+            solved += 1
+            assert np.float64(o1.value).tobytes() == np.float64(o2.value).tobytes(), (deg, a, b, o1.value, o2.value)
+    assert solved > 1000
