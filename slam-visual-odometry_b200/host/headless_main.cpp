@@ -26,19 +26,19 @@ int main(int argc, char** argv) {
     std::vector<std::string> paths;
     try { paths = load_image_paths(dir); } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
     if (paths.empty()) { std::fprintf(stderr, "No images found in dataset directory: %s\n", dir.c_str()); return 1; }      // main.cpp:92-95
-    // load_image_paths lists what the reference lists (png / jpg / jpeg, src/main.cpp:26-49) plus Netpbm; this build has no
-    // image codecs, so a directory it cannot read completely is refused up front instead of silently pairing other frames
+    // load_image_paths lists what the reference lists (png / jpg / jpeg, src/main.cpp:26-49) plus Netpbm; this build decodes
+    // png and Netpbm, so a directory it cannot read completely is refused up front instead of silently pairing other frames
     for (const std::string& p : paths) {
         const size_t dot = p.find_last_of('.');
         std::string ext = dot == std::string::npos ? "" : p.substr(dot + 1);
         for (char& c : ext) c = (char)std::tolower((unsigned char)c);
-        if (ext != "pgm" && ext != "ppm" && ext != "pnm") {
-            std::fprintf(stderr, "%s: this build decodes binary Netpbm (P5/P6) only -- convert the sequence, or build with OpenCV and use cv::imread\n", p.c_str());
+        if (ext != "png" && ext != "pgm" && ext != "ppm" && ext != "pnm") {
+            std::fprintf(stderr, "%s: this build decodes png and binary Netpbm (P5/P6) only -- convert the sequence, or build with OpenCV and use cv::imread\n", p.c_str());
             return 1;
         }
     }
-    const cv::Mat first = read_pnm(paths[0]);
-    if (first.empty()) { std::fprintf(stderr, "Failed to load first image: %s (this build decodes P5/P6 only)\n", paths[0].c_str()); return 1; }
+    const cv::Mat first = read_image(paths[0]);
+    if (first.empty()) { std::fprintf(stderr, "Failed to load first image: %s (this build decodes png and P5/P6 only)\n", paths[0].c_str()); return 1; }
     try {
         VisualOdometry::Options opt;
         opt.nfeatures = nfeatures;
@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
         if (batched) {
             std::vector<cv::Mat> images;
             for (size_t i = 0; i < paths.size(); ++i) {
-                cv::Mat im = read_pnm(paths[i]);
+                cv::Mat im = read_image(paths[i]);
                 if (im.empty()) { std::fprintf(stderr, "Failed to load image: %s\n", paths[i].c_str()); continue; }         // main.cpp:137-140
                 images.push_back(im);
                 stamps.push_back(timestamp_from_path(paths[i], i));
@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
             vo.process_sequence(images);
         } else {
             for (size_t i = 0; i < paths.size(); ++i) {
-                cv::Mat im = read_pnm(paths[i]);
+                cv::Mat im = read_image(paths[i]);
                 if (im.empty()) { std::fprintf(stderr, "Failed to load image: %s\n", paths[i].c_str()); continue; }
                 Frame frame((int)i, im);
                 frame.timestamp = timestamp_from_path(paths[i], i);

@@ -124,6 +124,17 @@ int vo_host_read_pnm(const char* path, unsigned char* data, int cap, int* rows, 
     return ch;
 }
 
+// the same through read_image (PNG or Netpbm by content)
+int vo_host_read_image(const char* path, unsigned char* data, int cap, int* rows, int* cols) {
+    const cv::Mat m = read_image(path);
+    if (m.empty()) return 0;
+    const int ch = m.channels();
+    if (cap < m.rows * m.cols * ch) return -2;
+    for (int y = 0; y < m.rows; ++y) std::memcpy(data + (size_t)y * m.cols * ch, m.ptr<uint8_t>(y), (size_t)m.cols * ch);
+    *rows = m.rows; *cols = m.cols;
+    return ch;
+}
+
 int vo_host_write_pnm(const char* path, const unsigned char* data, int rows, int cols, int channels) {
     cv::Mat m(rows, cols, channels == 3 ? CV_8UC3 : CV_8UC1, const_cast<unsigned char*>(data));
     return write_pnm(path, m) ? 1 : 0;

@@ -6,6 +6,9 @@
 #include <cstdio>
 #include <filesystem>
 #include <cstdlib>
+#include <cstring>
+
+#include <zlib.h>
 
 #include "pose.h"
 
@@ -63,6 +66,134 @@ cv::Mat read_pnm(const std::string& path) {
             for (int x = 0; x < w; ++x) std::swap(p[3 * x], p[3 * x + 2]);
     }
     return img;
+}
+
+// ---- PNG (the reference's datasets are png files read with cv::imread, src/main.cpp:136) -------------------------------
+// A plain decoder on zlib: every colour type and bit depth of the PNG specification, no interlacing.  The result is what
+// the reference's pipeline gets out of cv::imread + cvtColor: 8 bits per channel, alpha dropped, 16-bit samples reduced to
+// their high byte (libpng's strip_16, which OpenCV uses), gray kept as one channel (cv::imread would replicate it into
+// three equal channels that BGR2GRAY maps back to the same value), colour as BGR.
+static uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+cv::Mat read_png(const std::string& path) {
+    FILE* in = std::fopen(path.c_str(), "rb");
+    if (!in) return cv::Mat();
+    struct Closer { FILE* f; ~Closer() { std::fclose(f); } } closer{in};
+    uint8_t sig[8];
+    static const uint8_t kSig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1A, '\n'};
+    if (std::fread(sig, 1, 8, in) != 8 || std::memcmp(sig, kSig, 8) != 0) return cv::Mat();
+    uint32_t w = 0, h = 0;
+    int depth = 0, ctype = -1;
+    std::vector<uint8_t> idat, plte;
+    bool have_ihdr = false, done = false;
+    while (!done) {
+        uint8_t hdr[8];
+        if (std::fread(hdr, 1, 8, in) != 8) return cv::Mat();
+        const uint32_t len = be32(hdr);
+        if (len > (1u << 30)) return cv::Mat();
+        std::vector<uint8_t> data(len);
+        uint8_t crcb[4];
+        if ((len && std::fread(data.data(), 1, len, in) != len) || std::fread(crcb, 1, 4, in) != 4) return cv::Mat();
+        uLong crc = crc32(0L, hdr + 4, 4);
+        if (len) crc = crc32(crc, data.data(), len);
+        if ((uint32_t)crc != be32(crcb)) return cv::Mat();
+        if (std::memcmp(hdr + 4, "IHDR", 4) == 0) {
+            if (len != 13) return cv::Mat();
+            w = be32(data.data()); h = be32(data.data() + 4);
+            depth = data[8]; ctype = data[9];
+            if (data[10] != 0 || data[11] != 0 || data[12] != 0) return cv::Mat();     // compression, filter method, interlace: only the plain ones
+            have_ihdr = true;
+        } else if (std::memcmp(hdr + 4, "PLTE", 4) == 0) {
+            plte = data;
+        } else if (std::memcmp(hdr + 4, "IDAT", 4) == 0) {
+            idat.insert(idat.end(), data.begin(), data.end());
+        } else if (std::memcmp(hdr + 4, "IEND", 4) == 0) {
+            done = true;
+        }
+    }
+    if (!have_ihdr || w == 0 || h == 0 || w > 65535 || h > 65535) return cv::Mat();
+    int samples;                                                  // samples per pixel
+    switch (ctype) {
+        case 0: samples = 1; break;                               // gray
+        case 2: samples = 3; break;                               // RGB
+        case 3: samples = 1; break;                               // palette index
+        case 4: samples = 2; break;                               // gray + alpha
+        case 6: samples = 4; break;                               // RGBA
+        default: return cv::Mat();
+    }
+    const bool depth_ok = (ctype == 0 && (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) ||
+                          (ctype == 3 && (depth == 1 || depth == 2 || depth == 4 || depth == 8)) ||
+                          ((ctype == 2 || ctype == 4 || ctype == 6) && (depth == 8 || depth == 16));
+    if (!depth_ok || (ctype == 3 && plte.size() < 3)) return cv::Mat();
+    const size_t row_bytes = ((size_t)w * samples * depth + 7) / 8;
+    const int bpp = std::max(1, samples * depth / 8);             // filter distance in bytes
+    std::vector<uint8_t> raw((row_bytes + 1) * h);
+    uLongf raw_len = (uLongf)raw.size();
+    if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) return cv::Mat();
+    // undo the per-row filters in place (row r starts at r * (row_bytes + 1) with its filter type byte)
+    std::vector<uint8_t> zero(row_bytes, 0);
+    for (uint32_t y = 0; y < h; ++y) {
+        uint8_t* cur = raw.data() + (size_t)y * (row_bytes + 1);
+        const int ft = cur[0];
+        uint8_t* x = cur + 1;
+        const uint8_t* up = y ? raw.data() + (size_t)(y - 1) * (row_bytes + 1) + 1 : zero.data();
+        for (size_t i = 0; i < row_bytes; ++i) {
+            const int a = i >= (size_t)bpp ? x[i - bpp] : 0, b = up[i], c = i >= (size_t)bpp ? up[i - bpp] : 0;
+            int pred;
+            switch (ft) {
+                case 0: pred = 0; break;
+                case 1: pred = a; break;
+                case 2: pred = b; break;
+                case 3: pred = (a + b) >> 1; break;
+                case 4: {
+                    const int pp = a + b - c, pa = std::abs(pp - a), pb = std::abs(pp - b), pc = std::abs(pp - c);
+                    pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+                    break;
+                }
+                default: return cv::Mat();
+            }
+            x[i] = (uint8_t)(x[i] + pred);
+        }
+    }
+    const bool colour = (ctype == 2 || ctype == 6 || ctype == 3);
+    cv::Mat img((int)h, (int)w, colour ? CV_8UC3 : CV_8UC1);
+    const int maxv = (1 << depth) - 1;
+    for (uint32_t y = 0; y < h; ++y) {
+        const uint8_t* x = raw.data() + (size_t)y * (row_bytes + 1) + 1;
+        uint8_t* o = img.ptr<uint8_t>((int)y);
+        for (uint32_t px = 0; px < w; ++px) {
+            auto sample = [&](int k) -> int {                     // k-th sample of pixel px as an 8-bit value (16 bit: high byte)
+                if (depth == 8) return x[(size_t)px * samples + k];
+                if (depth == 16) return x[((size_t)px * samples + k) * 2];
+                const size_t bit = (size_t)px * depth;            // 1 / 2 / 4 bits: one sample per pixel
+                return (x[bit >> 3] >> (8 - depth - (bit & 7))) & maxv;
+            };
+            if (ctype == 3) {
+                const size_t idx = (size_t)sample(0) * 3;
+                if (idx + 2 >= plte.size()) { o[3 * px] = o[3 * px + 1] = o[3 * px + 2] = 0; continue; }      // index beyond the palette
+                o[3 * px] = plte[idx + 2]; o[3 * px + 1] = plte[idx + 1]; o[3 * px + 2] = plte[idx];
+            } else if (colour) {
+                o[3 * px] = (uint8_t)sample(2); o[3 * px + 1] = (uint8_t)sample(1); o[3 * px + 2] = (uint8_t)sample(0);
+            } else {
+                const int v = sample(0);
+                o[px] = (uint8_t)(depth < 8 ? v * 255 / maxv : v);
+            }
+        }
+    }
+    return img;
+}
+
+// by content: PNG signature or Netpbm magic (cv::imread decides by content too)
+cv::Mat read_image(const std::string& path) {
+    FILE* in = std::fopen(path.c_str(), "rb");
+    if (!in) return cv::Mat();
+    uint8_t m[2] = {0, 0};
+    const size_t got = std::fread(m, 1, 2, in);
+    std::fclose(in);
+    if (got != 2) return cv::Mat();
+    if (m[0] == 0x89 && m[1] == 'P') return read_png(path);
+    if (m[0] == 'P' && (m[1] == '5' || m[1] == '6')) return read_pnm(path);
+    return cv::Mat();                                             // jpeg and the rest: no codec in this build
 }
 
 bool write_pnm(const std::string& path, const cv::Mat& image) {

