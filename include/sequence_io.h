@@ -23,3 +23,5 @@ cv::Mat read_png(const std::string& path);
 cv::Mat read_image(const std::string& path);
 // "timestamp tx ty tz r00 r01 ... r22" per line (T_wc)
 bool save_trajectory_text(const std::string& path, const std::vector<double>& timestamps, const std::vector<class Pose>& poses);
+// "timestamp tx ty tz qx qy qz qw" per line (TUM format, T_wc): what trajectory evaluation tools read
+bool save_trajectory_tum(const std::string& path, const std::vector<double>& timestamps, const std::vector<class Pose>& poses);

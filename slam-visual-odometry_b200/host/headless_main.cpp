@@ -13,16 +13,17 @@
 #include "visual_odometry.h"
 
 int main(int argc, char** argv) {
-    std::string dir, out = "trajectory.txt";
+    std::string dir, out = "trajectory.txt", tum;
     bool batched = false;
     int nfeatures = 1200;
     for (int i = 1; i < argc; ++i) {
         if (!std::strcmp(argv[i], "--batched")) batched = true;
         else if (!std::strcmp(argv[i], "--features") && i + 1 < argc) nfeatures = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
+        else if (!std::strcmp(argv[i], "--tum") && i + 1 < argc) tum = argv[++i];
         else dir = argv[i];
     }
-    if (dir.empty()) { std::fprintf(stderr, "usage: %s <image directory> [--batched] [--features N] [--out file]\n", argv[0]); return 2; }
+    if (dir.empty()) { std::fprintf(stderr, "usage: %s <image directory> [--batched] [--features N] [--out file] [--tum file]\n", argv[0]); return 2; }
     std::vector<std::string> paths;
     try { paths = load_image_paths(dir); } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
     if (paths.empty()) { std::fprintf(stderr, "No images found in dataset directory: %s\n", dir.c_str()); return 1; }      // main.cpp:92-95
@@ -65,6 +66,7 @@ int main(int argc, char** argv) {
         }
         const std::vector<Pose> traj = vo.get_trajectory_poses();
         if (!save_trajectory_text(out, stamps, traj)) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
+        if (!tum.empty() && !save_trajectory_tum(tum, stamps, traj)) { std::fprintf(stderr, "cannot write %s\n", tum.c_str()); return 1; }
         std::printf("%zu frames, trajectory written to %s\n", traj.size(), out.c_str());
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());

@@ -124,6 +124,24 @@ int vo_host_read_pnm(const char* path, unsigned char* data, int cap, int* rows, 
     return ch;
 }
 
+// poses12: n rows [R_wc row-major | t_wc]; stamps: n doubles or NULL
+int vo_host_save_tum(const char* path, const double* poses12, int n, const double* stamps) {
+    try {
+        std::vector<Pose> poses;
+        std::vector<double> ts;
+        for (int i = 0; i < n; ++i) {
+            cv::Mat R(3, 3, CV_64F), t(3, 1, CV_64F);
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 3; ++c) R.at<double>(r, c) = poses12[i * 12 + r * 3 + c];
+                t.at<double>(r, 0) = poses12[i * 12 + 9 + r];
+            }
+            poses.emplace_back(R, t);
+            if (stamps) ts.push_back(stamps[i]);
+        }
+        return save_trajectory_tum(path, ts, poses) ? 1 : 0;
+    } catch (const std::exception& e) { g_msg = e.what(); return -1; }
+}
+
 // the same through read_image (PNG or Netpbm by content)
 int vo_host_read_image(const char* path, unsigned char* data, int cap, int* rows, int* cols) {
     const cv::Mat m = read_image(path);

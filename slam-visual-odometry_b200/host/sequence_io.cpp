@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <filesystem>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 
 #include <zlib.h>
@@ -227,4 +228,36 @@ bool save_trajectory_text(const std::string& path, const std::vector<double>& ti
     }
     std::fclose(f);
     return true;
+}
+
+// TUM trajectory format, one line per frame: "timestamp tx ty tz qx qy qz qw" of T_wc (camera -> world, as Pose) -- what
+// evaluation tools (evo, the TUM / KITTI scripts) read; the reference itself only shows the trajectory in its viewer
+// (src/trajectory_viewer.cpp).  Same quaternion branch rule as b200vo/trajectory.py::save_tum.
+bool save_trajectory_tum(const std::string& path, const std::vector<double>& timestamps, const std::vector<Pose>& poses) {
+    FILE* f = std::fopen(path.c_str(), "w");
+    if (!f) return false;
+    std::fprintf(f, "# timestamp tx ty tz qx qy qz qw   (T_wc: camera -> world, as Pose in include/pose.h)\n");
+    for (size_t n = 0; n < poses.size(); ++n) {
+        const Pose& p = poses[n];
+        double R[3][3];
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) R[r][c] = p.R_wc.at<double>(r, c);
+        double q[4];
+        const double tr = R[0][0] + R[1][1] + R[2][2];
+        if (tr > 0) {
+            const double s = std::sqrt(tr + 1.0) * 2;
+            q[0] = (R[2][1] - R[1][2]) / s; q[1] = (R[0][2] - R[2][0]) / s; q[2] = (R[1][0] - R[0][1]) / s; q[3] = 0.25 * s;
+        } else {
+            int i = 0;
+            if (R[1][1] > R[i][i]) i = 1;
+            if (R[2][2] > R[i][i]) i = 2;
+            const int j = (i + 1) % 3, k = (i + 2) % 3;
+            const double s = std::sqrt(1.0 + R[i][i] - R[j][j] - R[k][k]) * 2;
+            q[i] = 0.25 * s; q[j] = (R[j][i] + R[i][j]) / s; q[k] = (R[k][i] + R[i][k]) / s; q[3] = (R[k][j] - R[j][k]) / s;
+        }
+        const double nrm = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+        std::fprintf(f, "%.9f %.9f %.9f %.9f %.9f %.9f %.9f %.9f\n", n < timestamps.size() ? timestamps[n] : (double)n,
+                     p.t_wc.at<double>(0, 0), p.t_wc.at<double>(1, 0), p.t_wc.at<double>(2, 0), q[0] / nrm, q[1] / nrm, q[2] / nrm, q[3] / nrm);
+    }
+    return std::fclose(f) == 0;
 }

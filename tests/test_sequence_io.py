@@ -285,3 +285,31 @@ def test_cpp_png_reader_equals_cv2_imread(built, host, tmp_path):
     # Netpbm through the same entry point
     cv2.imwrite(str(tmp_path / "g.pgm"), noisy)
     assert np.array_equal(_cpp_read(host, str(tmp_path / "g.pgm")), noisy)
+
+
+def test_cpp_tum_export_equals_python(built, host, tmp_path):
+    """save_trajectory_tum of the C++ host layer (slam_vo_headless --tum) writes the file b200vo.trajectory.save_tum writes:
+    same lines for rotations in all four quaternion branches, and load_tum recovers the poses."""
+    from b200vo import trajectory as T
+    rng = np.random.default_rng(3)
+    Rs = [np.eye(3)]
+    for ax in range(3):                                   # 180-degree turns hit the three trace <= 0 branches
+        R = -np.eye(3); R[ax, ax] = 1.0
+        Rs.append(R)
+    for _ in range(20):
+        q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        Rs.append(q * np.sign(np.linalg.det(q)))
+    Rs = np.array(Rs)
+    ts = rng.standard_normal((len(Rs), 3)) * 10
+    stamps = np.arange(len(Rs)) * 0.1 + 5
+    poses12 = np.ascontiguousarray(np.hstack([Rs.reshape(-1, 9), ts]))
+    a, b = str(tmp_path / "cpp.tum"), str(tmp_path / "py.tum")
+    assert host.vo_host_save_tum(a.encode(), poses12.ctypes.data_as(ctypes.c_void_p), len(Rs), stamps.ctypes.data_as(ctypes.c_void_p)) == 1
+    T.save_tum(b, Rs, ts, stamps)
+    la, lb = open(a).read().splitlines(), open(b).read().splitlines()
+    assert len(la) == len(lb) == len(Rs) + 1
+    va = np.array([l.split() for l in la[1:]], float)
+    vb = np.array([l.split() for l in lb[1:]], float)
+    assert np.allclose(va, vb, atol=2e-9)
+    s2, R2, t2 = T.load_tum(a)
+    assert np.allclose(s2, stamps) and np.allclose(R2, Rs, atol=1e-8) and np.allclose(t2, ts, atol=1e-8)
