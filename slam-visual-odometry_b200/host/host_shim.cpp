@@ -142,6 +142,28 @@ int vo_host_save_tum(const char* path, const double* poses12, int n, const doubl
     } catch (const std::exception& e) { g_msg = e.what(); return -1; }
 }
 
+// est12 / gt12: n rows [R_wc row-major | t_wc]; out[5]: frames, ATE rmse, scale, RPE rotation, RPE translation direction
+int vo_host_trajectory_report(const double* est12, const double* gt12, int n, double* out) {
+    try {
+        auto mk = [n](const double* p) {
+            std::vector<Pose> v;
+            for (int i = 0; i < n; ++i) {
+                cv::Mat R(3, 3, CV_64F), t(3, 1, CV_64F);
+                for (int r = 0; r < 3; ++r) {
+                    for (int c = 0; c < 3; ++c) R.at<double>(r, c) = p[i * 12 + r * 3 + c];
+                    t.at<double>(r, 0) = p[i * 12 + 9 + r];
+                }
+                v.emplace_back(R, t);
+            }
+            return v;
+        };
+        TrajectoryReport rep;
+        if (!trajectory_report(mk(est12), mk(gt12), &rep)) return 0;
+        out[0] = rep.frames; out[1] = rep.ate_rmse_aligned; out[2] = rep.alignment_scale; out[3] = rep.rpe_rot_deg_mean; out[4] = rep.rpe_trans_dir_deg_mean;
+        return 1;
+    } catch (const std::exception& e) { g_msg = e.what(); return -1; }
+}
+
 // the same through read_image (PNG or Netpbm by content)
 int vo_host_read_image(const char* path, unsigned char* data, int cap, int* rows, int* cols) {
     const cv::Mat m = read_image(path);

@@ -261,3 +261,109 @@ bool save_trajectory_tum(const std::string& path, const std::vector<double>& tim
     }
     return std::fclose(f) == 0;
 }
+
+// ---- accuracy report against a reference trajectory (b200vo/trajectory.py::accuracy_report in C++) ----------------------
+// The reference applies a FIXED translation scale of 0.3 per successful step (src/visual_odometry.cpp:352), so positions are
+// compared after a similarity alignment (Horn's closed form: the rotation is the dominant eigenvector of a symmetric 4x4
+// matrix built from the cross-covariance, found here by Jacobi rotations), and relative poses by rotation angle and by
+// the angle between the translation DIRECTIONS.
+namespace {
+void jacobi_eigen4(double A[4][4], double V[4][4]) {
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) V[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = 0.0;
+        for (int i = 0; i < 4; ++i) for (int j = i + 1; j < 4; ++j) off += A[i][j] * A[i][j];
+        if (off < 1e-30) break;
+        for (int p = 0; p < 4; ++p)
+            for (int q = p + 1; q < 4; ++q) {
+                if (std::fabs(A[p][q]) < 1e-300) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 4; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - sn * akq; A[k][q] = sn * akp + c * akq; }
+                for (int k = 0; k < 4; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - sn * aqk; A[q][k] = sn * apk + c * aqk; }
+                for (int k = 0; k < 4; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq; }
+            }
+    }
+}
+double angle_deg(double c) { return std::acos(std::max(-1.0, std::min(1.0, c))) * 180.0 / 3.14159265358979323846; }
+}  // namespace
+
+bool trajectory_report(const std::vector<Pose>& est, const std::vector<Pose>& gt, TrajectoryReport* out) {
+    const size_t n = std::min(est.size(), gt.size());
+    if (!out || n < 2) return false;
+    std::vector<double> pe(3 * n), pg(3 * n);
+    double me[3] = {0, 0, 0}, mg[3] = {0, 0, 0};
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k) {
+            pe[3 * i + k] = est[i].t_wc.at<double>(k, 0); pg[3 * i + k] = gt[i].t_wc.at<double>(k, 0);
+            me[k] += pe[3 * i + k] / (double)n; mg[k] += pg[3 * i + k] / (double)n;
+        }
+    // cross-covariance S = sum (est - me)(gt - mg)^T, Horn's 4x4 matrix, rotation = eigenvector of the largest eigenvalue
+    double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, var = 0.0;
+    for (size_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+            const double ea = pe[3 * i + a] - me[a];
+            var += ea * ea;
+            for (int b = 0; b < 3; ++b) S[a][b] += ea * (pg[3 * i + b] - mg[b]);
+        }
+    double N[4][4] = {{S[0][0] + S[1][1] + S[2][2], S[1][2] - S[2][1], S[2][0] - S[0][2], S[0][1] - S[1][0]},
+                      {S[1][2] - S[2][1], S[0][0] - S[1][1] - S[2][2], S[0][1] + S[1][0], S[2][0] + S[0][2]},
+                      {S[2][0] - S[0][2], S[0][1] + S[1][0], -S[0][0] + S[1][1] - S[2][2], S[1][2] + S[2][1]},
+                      {S[0][1] - S[1][0], S[2][0] + S[0][2], S[1][2] + S[2][1], -S[0][0] - S[1][1] + S[2][2]}};
+    double V[4][4];
+    jacobi_eigen4(N, V);
+    int best = 0;
+    for (int k = 1; k < 4; ++k) if (N[k][k] > N[best][best]) best = k;
+    const double w = V[0][best], x = V[1][best], y = V[2][best], z = V[3][best];
+    const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
+                            {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
+                            {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
+    // scale that minimises the residual for this rotation: sum (gt_c . R est_c) / sum |est_c|^2
+    double num = 0.0;
+    for (size_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+            double re = 0.0;
+            for (int b = 0; b < 3; ++b) re += R[a][b] * (pe[3 * i + b] - me[b]);
+            num += re * (pg[3 * i + a] - mg[a]);
+        }
+    const double sc = var > 0 ? num / var : 1.0;
+    double sq = 0.0;
+    for (size_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+            double re = 0.0;
+            for (int b = 0; b < 3; ++b) re += R[a][b] * (pe[3 * i + b] - me[b]);
+            const double d = (pg[3 * i + a] - mg[a]) - sc * re;
+            sq += d * d;
+        }
+    out->frames = (int)n;
+    out->ate_rmse_aligned = std::sqrt(sq / (double)n);
+    out->alignment_scale = sc;
+    // relative pose errors between consecutive frames
+    double rot = 0.0, dir = 0.0;
+    int ndir = 0;
+    auto Rm = [](const Pose& p, int r, int c) { return p.R_wc.at<double>(r, c); };
+    for (size_t i = 0; i + 1 < n; ++i) {
+        // trace(dRe^T dRg) with dR = R_i^T R_{i+1}
+        double dRe[3][3], dRg[3][3];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                dRe[a][b] = dRg[a][b] = 0.0;
+                for (int k = 0; k < 3; ++k) { dRe[a][b] += Rm(est[i], k, a) * Rm(est[i + 1], k, b); dRg[a][b] += Rm(gt[i], k, a) * Rm(gt[i + 1], k, b); }
+            }
+        double tr = 0.0;
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) tr += dRe[a][b] * dRg[a][b];
+        rot += angle_deg((tr - 1.0) / 2.0);
+        double te[3] = {0, 0, 0}, tg[3] = {0, 0, 0};
+        for (int a = 0; a < 3; ++a)
+            for (int k = 0; k < 3; ++k) {
+                te[a] += Rm(est[i], k, a) * (pe[3 * (i + 1) + k] - pe[3 * i + k]);
+                tg[a] += Rm(gt[i], k, a) * (pg[3 * (i + 1) + k] - pg[3 * i + k]);
+            }
+        const double ne = std::sqrt(te[0] * te[0] + te[1] * te[1] + te[2] * te[2]), ng = std::sqrt(tg[0] * tg[0] + tg[1] * tg[1] + tg[2] * tg[2]);
+        if (ne > 1e-12 && ng > 1e-12) { dir += angle_deg((te[0] * tg[0] + te[1] * tg[1] + te[2] * tg[2]) / (ne * ng)); ++ndir; }
+    }
+    out->rpe_rot_deg_mean = rot / (double)(n - 1);
+    out->rpe_trans_dir_deg_mean = ndir ? dir / ndir : 0.0;
+    return true;
+}

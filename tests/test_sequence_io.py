@@ -313,3 +313,38 @@ def test_cpp_tum_export_equals_python(built, host, tmp_path):
     assert np.allclose(va, vb, atol=2e-9)
     s2, R2, t2 = T.load_tum(a)
     assert np.allclose(s2, stamps) and np.allclose(R2, Rs, atol=1e-8) and np.allclose(t2, ts, atol=1e-8)
+
+
+def test_cpp_trajectory_report_equals_python(built, host):
+    """trajectory_report of the C++ host layer (Horn alignment by a 4x4 Jacobi eigen-solver) against
+    b200vo.trajectory.accuracy_report (Umeyama by numpy SVD): a noisy, scaled, rotated copy of a curved trajectory."""
+    from b200vo import trajectory as T, synth
+    R_gt, C_gt = synth.make_trajectory(120)
+    rng = np.random.default_rng(2)
+    q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+    q *= np.sign(np.linalg.det(q))
+    R_est = np.array([R @ _small_rot(rng, 0.01) for R in R_gt])
+    t_est = (0.3 * (q @ C_gt.T).T + np.array([3.0, -2.0, 7.0])) + rng.standard_normal(C_gt.shape) * 0.02
+    est12 = np.ascontiguousarray(np.hstack([R_est.reshape(-1, 9), t_est]))
+    gt12 = np.ascontiguousarray(np.hstack([np.asarray(R_gt).reshape(-1, 9), C_gt]))
+    out = np.zeros(5)
+    assert host.vo_host_trajectory_report(est12.ctypes.data_as(ctypes.c_void_p), gt12.ctypes.data_as(ctypes.c_void_p), len(est12),
+                                          out.ctypes.data_as(ctypes.c_void_p)) == 1
+    ref = T.accuracy_report(est12, R_gt, C_gt)
+    ate, sc = T.ate_rmse(t_est, C_gt)
+    rr, rt = T.rpe(R_est, t_est, np.asarray(R_gt), C_gt)
+    assert int(out[0]) == ref["frames"] == 120
+    assert abs(out[1] - ate) < 1e-9 * max(1.0, ate) + 1e-9 and abs(out[2] - sc) < 1e-9
+    assert abs(out[3] - rr) < 1e-7 and abs(out[4] - rt) < 1e-7
+    # an exact similarity copy has zero error
+    t2 = 2.5 * (q @ C_gt.T).T + 1.0
+    e2 = np.ascontiguousarray(np.hstack([np.asarray(R_gt).reshape(-1, 9), t2]))
+    assert host.vo_host_trajectory_report(e2.ctypes.data_as(ctypes.c_void_p), gt12.ctypes.data_as(ctypes.c_void_p), len(e2), out.ctypes.data_as(ctypes.c_void_p)) == 1
+    assert out[1] < 1e-9 and abs(out[2] - 0.4) < 1e-12
+
+
+def _small_rot(rng, sigma):
+    w = rng.standard_normal(3) * sigma
+    th = np.linalg.norm(w)
+    K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+    return np.eye(3) + K + K @ K / 2 if th < 1e-12 else np.eye(3) + np.sin(th) / th * K + (1 - np.cos(th)) / th ** 2 * K @ K
