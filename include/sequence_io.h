@@ -25,6 +25,7 @@ cv::Mat read_image(const std::string& path);
 bool save_trajectory_text(const std::string& path, const std::vector<double>& timestamps, const std::vector<class Pose>& poses);
 // "timestamp tx ty tz qx qy qz qw" per line (TUM format, T_wc): what trajectory evaluation tools read
 bool save_trajectory_tum(const std::string& path, const std::vector<double>& timestamps, const std::vector<class Pose>& poses);
+bool load_trajectory_tum(const std::string& path, std::vector<double>* timestamps, std::vector<class Pose>* poses);
 // Accuracy of an estimated trajectory against a reference one (positions after a similarity alignment, since the reference
 // steps with a fixed scale of 0.3; relative rotation error and angle between the translation directions per step): the
 // numbers b200vo/trajectory.py::accuracy_report and bench.py's result_check give

@@ -13,7 +13,7 @@
 #include "visual_odometry.h"
 
 int main(int argc, char** argv) {
-    std::string dir, out = "trajectory.txt", tum;
+    std::string dir, out = "trajectory.txt", tum, gt;
     bool batched = false;
     int nfeatures = 1200;
     for (int i = 1; i < argc; ++i) {
@@ -21,9 +21,10 @@ int main(int argc, char** argv) {
         else if (!std::strcmp(argv[i], "--features") && i + 1 < argc) nfeatures = std::atoi(argv[++i]);
         else if (!std::strcmp(argv[i], "--out") && i + 1 < argc) out = argv[++i];
         else if (!std::strcmp(argv[i], "--tum") && i + 1 < argc) tum = argv[++i];
+        else if (!std::strcmp(argv[i], "--gt") && i + 1 < argc) gt = argv[++i];
         else dir = argv[i];
     }
-    if (dir.empty()) { std::fprintf(stderr, "usage: %s <image directory> [--batched] [--features N] [--out file] [--tum file]\n", argv[0]); return 2; }
+    if (dir.empty()) { std::fprintf(stderr, "usage: %s <image directory> [--batched] [--features N] [--out file] [--tum file] [--gt tum-file]\n", argv[0]); return 2; }
     std::vector<std::string> paths;
     try { paths = load_image_paths(dir); } catch (const std::exception& e) { std::fprintf(stderr, "%s\n", e.what()); return 1; }
     if (paths.empty()) { std::fprintf(stderr, "No images found in dataset directory: %s\n", dir.c_str()); return 1; }      // main.cpp:92-95
@@ -68,6 +69,13 @@ int main(int argc, char** argv) {
         if (!save_trajectory_text(out, stamps, traj)) { std::fprintf(stderr, "cannot write %s\n", out.c_str()); return 1; }
         if (!tum.empty() && !save_trajectory_tum(tum, stamps, traj)) { std::fprintf(stderr, "cannot write %s\n", tum.c_str()); return 1; }
         std::printf("%zu frames, trajectory written to %s\n", traj.size(), out.c_str());
+        if (!gt.empty()) {       // accuracy against a ground-truth trajectory in TUM format (frame i <-> line i)
+            std::vector<Pose> ref;
+            TrajectoryReport rep;
+            if (!load_trajectory_tum(gt, nullptr, &ref) || !trajectory_report(traj, ref, &rep)) { std::fprintf(stderr, "cannot evaluate against %s\n", gt.c_str()); return 1; }
+            std::printf("vs %s: %d frames, ATE rmse (similarity-aligned) %.6f, scale %.6f, RPE rotation %.4f deg, translation direction %.4f deg\n",
+                        gt.c_str(), rep.frames, rep.ate_rmse_aligned, rep.alignment_scale, rep.rpe_rot_deg_mean, rep.rpe_trans_dir_deg_mean);
+        }
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

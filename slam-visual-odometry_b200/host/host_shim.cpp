@@ -164,6 +164,23 @@ int vo_host_trajectory_report(const double* est12, const double* gt12, int n, do
     } catch (const std::exception& e) { g_msg = e.what(); return -1; }
 }
 
+// poses12_out: up to cap rows [R_wc | t_wc]; returns the number of poses in the file or < 0
+int vo_host_load_tum(const char* path, double* poses12_out, double* stamps_out, int cap) {
+    try {
+        std::vector<Pose> poses;
+        std::vector<double> ts;
+        if (!load_trajectory_tum(path, &ts, &poses)) return -1;
+        for (int i = 0; i < (int)poses.size() && i < cap; ++i) {
+            for (int r = 0; r < 3; ++r) {
+                for (int c = 0; c < 3; ++c) poses12_out[i * 12 + r * 3 + c] = poses[(size_t)i].R_wc.at<double>(r, c);
+                poses12_out[i * 12 + 9 + r] = poses[(size_t)i].t_wc.at<double>(r, 0);
+            }
+            if (stamps_out) stamps_out[i] = ts[(size_t)i];
+        }
+        return (int)poses.size();
+    } catch (const std::exception& e) { g_msg = e.what(); return -2; }
+}
+
 // the same through read_image (PNG or Netpbm by content)
 int vo_host_read_image(const char* path, unsigned char* data, int cap, int* rows, int* cols) {
     const cv::Mat m = read_image(path);

@@ -367,3 +367,31 @@ bool trajectory_report(const std::vector<Pose>& est, const std::vector<Pose>& gt
     out->rpe_trans_dir_deg_mean = ndir ? dir / ndir : 0.0;
     return true;
 }
+
+// the inverse of save_trajectory_tum: lines "timestamp tx ty tz qx qy qz qw", '#' comments and blank lines skipped
+bool load_trajectory_tum(const std::string& path, std::vector<double>* timestamps, std::vector<Pose>* poses) {
+    FILE* f = std::fopen(path.c_str(), "r");
+    if (!f || !poses) { if (f) std::fclose(f); return false; }
+    char line[512];
+    bool ok = true;
+    while (std::fgets(line, sizeof(line), f)) {
+        const char* p = line;
+        while (*p == ' ' || *p == '\t') ++p;
+        if (*p == '#' || *p == '\n' || *p == '\r' || *p == 0) continue;
+        double v[8];
+        if (std::sscanf(p, "%lf %lf %lf %lf %lf %lf %lf %lf", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6], &v[7]) != 8) { ok = false; break; }
+        const double nq = std::sqrt(v[4] * v[4] + v[5] * v[5] + v[6] * v[6] + v[7] * v[7]);
+        if (!(nq > 0)) { ok = false; break; }
+        const double x = v[4] / nq, y = v[5] / nq, z = v[6] / nq, w = v[7] / nq;
+        cv::Mat R(3, 3, CV_64F), t(3, 1, CV_64F);
+        const double r[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                             2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                             2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)};
+        for (int i = 0; i < 9; ++i) R.at<double>(i / 3, i % 3) = r[i];
+        for (int i = 0; i < 3; ++i) t.at<double>(i, 0) = v[1 + i];
+        poses->emplace_back(R, t);
+        if (timestamps) timestamps->push_back(v[0]);
+    }
+    std::fclose(f);
+    return ok;
+}

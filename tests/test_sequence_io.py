@@ -313,6 +313,13 @@ def test_cpp_tum_export_equals_python(built, host, tmp_path):
     assert np.allclose(va, vb, atol=2e-9)
     s2, R2, t2 = T.load_tum(a)
     assert np.allclose(s2, stamps) and np.allclose(R2, Rs, atol=1e-8) and np.allclose(t2, ts, atol=1e-8)
+    # and the C++ loader reads both files back
+    for path in (a, b):
+        back, st = np.zeros((len(Rs), 12)), np.zeros(len(Rs))
+        assert host.vo_host_load_tum(path.encode(), back.ctypes.data_as(ctypes.c_void_p), st.ctypes.data_as(ctypes.c_void_p), len(Rs)) == len(Rs)
+        assert np.allclose(st, stamps) and np.allclose(back[:, :9].reshape(-1, 3, 3), Rs, atol=1e-8) and np.allclose(back[:, 9:], ts, atol=1e-8)
+    open(str(tmp_path / "bad.tum"), "w").write("1 2 3\n")
+    assert host.vo_host_load_tum(str(tmp_path / "bad.tum").encode(), back.ctypes.data_as(ctypes.c_void_p), None, 1) < 0
 
 
 def test_cpp_trajectory_report_equals_python(built, host):
