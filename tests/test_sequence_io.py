@@ -148,6 +148,14 @@ def test_run_directory_equals_batched_pipeline(built, seq_small, tmp_path):
     r = subprocess.run([exe, str(png), "--features", "1000", "--out", out2], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert open(out2).read() == open(out).read()
+    # TUM export and the accuracy report against a ground-truth file (here: its own trajectory -> zero error, scale 1)
+    tum = str(tmp_path / "traj.tum")
+    r = subprocess.run([exe, str(png), "--features", "1000", "--out", out2, "--tum", tum], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ts, Rt, tt = T.load_tum(tum)
+    assert np.allclose(ts, [0, 1, 2]) and np.allclose(tt, rows[:, 1:4], atol=1e-8) and np.allclose(Rt.reshape(-1, 9), rows[:, 4:13], atol=1e-8)
+    r = subprocess.run([exe, str(png), "--features", "1000", "--out", out2, "--gt", tum], capture_output=True, text=True)
+    assert r.returncode == 0 and "ATE rmse (similarity-aligned) 0.000000, scale 1.000000" in r.stdout, r.stdout + r.stderr
     # a directory with a frame this build cannot decode is refused as a whole
     open(str(png / "000001.jpg"), "wb").write(b"\xff\xd8\xff")
     r = subprocess.run([exe, str(png), "--out", out2], capture_output=True, text=True)
